@@ -1,0 +1,142 @@
+/*
+ * mfvgp.h -- C ABI of the B200-native MeanFieldVarGP free-energy path.
+ *
+ * The reference (vrettasm/MeanFieldVarGP) is pure Python and has no FFI; its
+ * boundary for this path is the class API of src/var_bayes/free_energy.py and
+ * src/numerical/scaled_cg.py.  Each entry point below names the reference
+ * interface it replaces (file:line under the reference repository).  All
+ * arithmetic is FP64.  Matrices are row-major exactly as the reference lays
+ * them out: mean points [D][3M+4], variance points [D][2M+3] (M = number of
+ * observation times), x = [means | log-variances] (free_energy.py:678-684).
+ *
+ * Pointer kinds: names ending in _h are HOST pointers, names ending in _d are
+ * DEVICE pointers on the handle's device.  The library owns only its
+ * workspace handle; callers own every buffer they pass.  A handle is
+ * re-entrant across handles, not thread-safe within one.  Every function
+ * returns 0 on success, a negative MFVGP_ERR_* code otherwise;
+ * mfvgp_last_error() gives the message.  There is no CPU fallback: without a
+ * CUDA device every compute entry fails with MFVGP_ERR_CUDA.
+ */
+#ifndef MFVGP_H_
+#define MFVGP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFVGP_VERSION 100
+
+/* drift plug-ins: src/dynamical_systems/{double_well,ornstein_uhlenbeck,
+ * lorenz_63,lorenz_96}.py and their .sym expression files                  */
+enum { MFVGP_SYS_DW = 0, MFVGP_SYS_OU = 1, MFVGP_SYS_L63 = 2, MFVGP_SYS_L96 = 3 };
+
+enum {
+    MFVGP_OK = 0,
+    MFVGP_ERR_ARG = -1,      /* bad argument (dimension, NULL, system id)   */
+    MFVGP_ERR_CUDA = -2,     /* CUDA runtime error / no device              */
+    MFVGP_ERR_STATE = -3     /* problem data not set yet                    */
+};
+
+/* status bits written by the device (free_energy.py:313-316, 547-550,
+ * 615-618: the reference raises RuntimeError on the first three)           */
+enum {
+    MFVGP_ST_ESDE_NONFINITE = 1,
+    MFVGP_ST_E0_NONFINITE = 2,
+    MFVGP_ST_EOBS_NONFINITE = 4,
+    MFVGP_ST_REFINED = 8,        /* >=1 interval took the adaptive path      */
+    MFVGP_ST_REFINE_LIMIT = 16   /* adaptive path hit scipy's limit=100      */
+};
+
+typedef struct mfvgp_handle mfvgp_handle;
+
+int mfvgp_version(void);
+const char *mfvgp_last_error(void);
+
+/* number of CUDA devices visible (0 => every compute call fails loudly)    */
+int mfvgp_device_count(void);
+
+/*
+ * Workspace for one FreeEnergy object: FreeEnergy.__init__
+ * (free_energy.py:30-179).  D = state dimension (sigma.size, :95),
+ * M = len(obs_times) (:150), d = observed dimensions (:136-147).
+ * L96 needs D >= 4 (lorenz_96.py:60-63); DW/OU need D = 1; L63 D = 3.
+ * interval range [n_begin, n_end) of the L = M-1 integrated intervals
+ * (free_energy.py:490) is the shard this handle evaluates; pass 0, -1 for all.
+ */
+int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
+                 int device, int n_begin, int n_end);
+int mfvgp_destroy(mfvgp_handle *h);
+
+/* drift / diffusion parameters: sde.theta, sde.sigma captured at
+ * free_energy.py:76-77 and replaceable through the setters at :241-279     */
+int mfvgp_set_sde(mfvgp_handle *h, const double *sigma_h /*[D]*/,
+                  const double *theta_h, int ntheta);
+
+/* prior moments (free_energy.py:68-72, setters :191-229)                   */
+int mfvgp_set_prior(mfvgp_handle *h, const double *mu0_h /*[D]*/,
+                    const double *tau0_h /*[D]*/);
+
+/* observation model (free_energy.py:90-177): obs_mask NULL = all observed  */
+int mfvgp_set_obs(mfvgp_handle *h, const double *obs_times_h /*[M]*/,
+                  const double *obs_values_h /*[M][d]*/,
+                  const double *obs_noise_h /*[d]*/,
+                  const uint8_t *obs_mask_h /*[D] or NULL*/);
+
+/*
+ * FreeEnergy.E_sde(mean_pts, vars_pts, output_gradients)
+ * (free_energy.py:461-565; single_interval :338-459; the quadrature is
+ * scipy.integrate.quad_vec as called at :405-417).
+ * out_d[0] = Esde.  dEsde_dm_d [L][D][4], dEsde_ds_d [L][D][3] (may be NULL
+ * when want_grad = 0).  status_d[0] receives MFVGP_ST_* bits.
+ */
+int mfvgp_esde(mfvgp_handle *h, const double *mean_pts_d, int64_t ldm,
+               const double *vars_pts_d, int64_t lds, int want_grad,
+               double *out_d, double *dEsde_dm_d, double *dEsde_ds_d,
+               int32_t *status_d, void *cuda_stream);
+
+/*
+ * FreeEnergy.E_cost(x, output_gradients) (free_energy.py:651-751), including
+ * E_kl0 (:281-336) and E_obs (:567-649).  out_d[0..3] = F, E0, Esde, Eobs.
+ * grad_d [D*(3M+4) + D*(2M+3)] (may be NULL when want_grad = 0).
+ */
+int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad,
+                double *out_d /*[4]*/, double *grad_d, int32_t *status_d,
+                void *cuda_stream);
+
+/* Same calls on HOST buffers (what a numpy caller of the reference passes):
+ * the copies to and from the device happen inside, then the stream is
+ * synchronised.  status_h receives the MFVGP_ST_* bits.                    */
+int mfvgp_esde_host(mfvgp_handle *h, const double *mean_pts_h,
+                    const double *vars_pts_h, int want_grad, double *Esde_h,
+                    double *dEsde_dm_h, double *dEsde_ds_h, int32_t *status_h);
+int mfvgp_ecost_host(mfvgp_handle *h, const double *x_h, int want_grad,
+                     double *out_h /*[4]*/, double *grad_h, int32_t *status_h);
+
+/*
+ * SCG.minimize(x0) over E_cost (scaled_cg.py:107-386 as driven by
+ * FreeEnergy.find_minimum, free_energy.py:815-830).  Iterates, gradients and
+ * the line-search dot products stay on the device; x_d is updated in place.
+ * fx_hist_h / dfx_hist_h [max_it] = SCG._stats["fx"], ["dfx"] (:284-285).
+ * result_h[0] = fx returned, result_h[1] = nit, result_h[2] = func_eval,
+ * result_h[3] = OR of status bits seen.
+ */
+int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
+              double f_tol, double *fx_hist_h, double *dfx_hist_h,
+              double *result_h /*[4]*/, void *cuda_stream);
+int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x_tol,
+                   double f_tol, double *fx_hist_h, double *dfx_hist_h,
+                   double *result_h /*[4]*/);
+
+/* counters for benchmarks: number of kernels this handle has launched      */
+int64_t mfvgp_launch_count(const mfvgp_handle *h);
+
+/* FP64 FMA micro-benchmark used as the roofline denominator (returns
+ * achieved TFLOP/s on the handle's device, FMA = 2 FLOP)                   */
+int mfvgp_fp64_peak(int device, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFVGP_H_ */

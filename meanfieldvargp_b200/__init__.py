@@ -1,0 +1,13 @@
+"""
+meanfieldvargp_b200 -- B200-native (sm_100a, FP64 CUDA) free-energy path of
+vrettasm/MeanFieldVarGP: E_sde + gradients, E_kl0, E_obs, E_cost and the SCG
+loop, behind the reference's own FreeEnergy / SCG Python API and the C ABI of
+include/mfvgp.h.
+"""
+from ._lib import MfvgpError, load as load_library          # noqa: F401
+from .free_energy import FreeEnergy                          # noqa: F401
+from .systems import (DoubleWell, Lorenz63, Lorenz96,        # noqa: F401
+                      OrnsteinUhlenbeck, StochasticProcess)
+
+__all__ = ["FreeEnergy", "DoubleWell", "OrnsteinUhlenbeck", "Lorenz63", "Lorenz96",
+           "StochasticProcess", "MfvgpError", "load_library"]

@@ -1,0 +1,77 @@
+"""
+ctypes binding of the C ABI declared in ``include/mfvgp.h`` (built in-tree as
+``meanfieldvargp_b200/lib/libmfvgp.so`` by ``make`` / ``__graft_entry__.build``).
+
+There is no CPU fallback: a missing library or a missing CUDA device raises.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, c_char_p, c_double, c_int, c_int32, c_int64,
+                    c_uint8, c_void_p)
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmfvgp.so"
+
+SYS_ID = {"DW": 0, "OU": 1, "L63": 2, "L96": 3}
+ST_ESDE, ST_E0, ST_EOBS, ST_REFINED, ST_LIMIT = 1, 2, 4, 8, 16
+
+_P = c_void_p     # every data pointer crosses the ABI as a plain address
+
+# name -> (restype, argtypes); kept in one table so tests can check that the
+# library exports every symbol the header declares
+SIGNATURES = {
+    "mfvgp_version": (c_int, []),
+    "mfvgp_last_error": (c_char_p, []),
+    "mfvgp_device_count": (c_int, []),
+    "mfvgp_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mfvgp_destroy": (c_int, [c_void_p]),
+    "mfvgp_set_sde": (c_int, [c_void_p, _P, _P, c_int]),
+    "mfvgp_set_prior": (c_int, [c_void_p, _P, _P]),
+    "mfvgp_set_obs": (c_int, [c_void_p, _P, _P, _P, _P]),
+    "mfvgp_esde": (c_int, [c_void_p, _P, c_int64, _P, c_int64, c_int, _P, _P, _P, _P, c_void_p]),
+    "mfvgp_ecost": (c_int, [c_void_p, _P, c_int, _P, _P, _P, c_void_p]),
+    "mfvgp_esde_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P, _P, _P]),
+    "mfvgp_ecost_host": (c_int, [c_void_p, _P, c_int, _P, _P, _P]),
+    "mfvgp_scg": (c_int, [c_void_p, _P, c_int, c_double, c_double, _P, _P, _P, c_void_p]),
+    "mfvgp_scg_host": (c_int, [c_void_p, _P, c_int, c_double, c_double, _P, _P, _P]),
+    "mfvgp_launch_count": (c_int64, [c_void_p]),
+    "mfvgp_fp64_peak": (c_int, [c_int, POINTER(c_double)]),
+}
+
+_lib = None
+
+
+class MfvgpError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raise loudly if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("MFVGP_LIB", LIB_PATH))
+    if not path.is_file():
+        raise MfvgpError(f"{path} not found: build it with `make` (or "
+                         f"`python -c 'import __graft_entry__ as g; g.build()'`). "
+                         f"meanfieldvargp_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mfvgp_last_error().decode("utf-8", "replace")
+        raise MfvgpError(f"{what} failed (code {rc}): {msg}")
+
+
+def require_device():
+    lib = load()
+    if lib.mfvgp_device_count() < 1:
+        raise MfvgpError("no CUDA device visible: the free-energy path runs "
+                         "only on the GPU (no CPU fallback)")
+    return lib

@@ -1,0 +1,527 @@
+// CUDA kernels (sm_100a, FP64) for the MeanFieldVarGP free-energy path.
+//
+// Reference functions replaced (files under the reference repository):
+//   FreeEnergy.single_interval  src/var_bayes/free_energy.py:338-459
+//   FreeEnergy.E_sde            src/var_bayes/free_energy.py:461-565
+//   FreeEnergy.E_kl0 / E_obs    src/var_bayes/free_energy.py:281-336, 567-649
+//   FreeEnergy.E_cost           src/var_bayes/free_energy.py:651-751
+//   Lorenz96._construct_functions src/dynamical_systems/lorenz_96.py:187-381
+//   StochasticProcess.energy/grad_mean/grad_variance
+//                               src/dynamical_systems/stochastic_process.py:299-448
+//
+// Data layout in HBM is the reference's: mean points [D][Nm], variance points
+// [D][Ns] (row = state dimension, time contiguous), per-interval gradients
+// dEsde_dm [L][D][4], dEsde_ds [L][D][3].
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "drift.cuh"
+#include "tables.h"
+
+namespace mfvgp {
+
+// [42][16] table of the fixed 42-node rule (tables.h)
+__constant__ double c_tab[kNodes * kTabStride];
+
+constexpr int kPartStride = 8;   // doubles per (interval, dim-tile) partial
+// partial slots (raw sums; scaled by h = dt/4 in guard_reduce_kernel)
+//  0: sum_i sum_r v_r E_i / Sigma_i         (weighted energy)
+//  1: sum_i (sum_r v_r E_i)^2               (|I_E|^2 for quad_vec's tol)
+//  2,3: sum_i (sum_r c_r E_i)^2, panels 1,2 (Kronrod - Gauss, quad_vec's err)
+//  4,5: sum_i sum_k (sum_r c_r dS_own_ik)^2, panels 1,2
+//  6: sum_i (sum_r v_r dS_own_i1)^2         (lower bound of |I_dS|^2)
+
+struct EsdeArgs {
+    const double *mean;     // [D][ldm]
+    const double *vars;     // [D][lds]   variances, or log-variances if log_vars
+    int64_t ldm, lds;
+    const double *obs_times;  // [M]
+    const double *sigma;      // [D]
+    const double *theta;      // [ntheta]
+    double *dm_out;           // [L][D][4] or nullptr
+    double *ds_out;           // [L][D][3] or nullptr
+    double *part;             // [(n_end-n_begin)*ntiles][kPartStride]
+    int D, n_begin, n_end, ntiles, log_vars;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum of NV values per thread; result valid in thread 0.
+template <int NV, int NT>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *sh /*[NV*NT/32]*/) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    if (NW > 1) {
+        if (lane == 0)
+#pragma unroll
+            for (int i = 0; i < NV; ++i) sh[i * NW + w] = v[i];
+        __syncthreads();
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                double s = sh[i * NW];
+                for (int k = 1; k < NW; ++k) s += sh[i * NW + k];
+                v[i] = s;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Lorenz 96: one thread per (state dimension, interval) cell, 42-node loop.
+// A CTA covers TE consecutive "extended" dimensions of one interval: TE-6
+// output dimensions plus a wrap-around halo of 3 on each side, because the
+// energy of dimension i couples (i, i+1, i-1, i-2) (lorenz_96.py:232-235) and
+// the gradient of dimension j gathers from energies j, j-1, j+1, j+2.  The
+// neighbour values travel through shared memory; the gather form needs no
+// atomics, so results are deterministic.
+// ---------------------------------------------------------------------------
+template <int TE>
+__global__ void __launch_bounds__(TE)
+esde_l96_kernel(const EsdeArgs a) {
+    constexpr int TD = TE - 6;
+    __shared__ double sh_m[TE], sh_s[TE];
+    __shared__ double sh_A[TE], sh_B[TE], sh_C[TE], sh_Dv[TE];
+    __shared__ double sh_red[7 * (TE / 32)];
+
+    const int e = threadIdx.x;
+    const int tile = blockIdx.x % a.ntiles;
+    const int n = a.n_begin + blockIdx.x / a.ntiles;
+    const int d0 = tile * TD;
+    const int D = a.D;
+    int j = (d0 - 3 + e) % D;
+    if (j < 0) j += D;
+    const bool has_energy = (e >= 2) && (e <= TE - 2);
+    const bool is_out = (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
+
+    const double ti = a.obs_times[n], tj = a.obs_times[n + 1];
+    const double dt = fabs(tj - ti);
+    const double inv_dt = 1.0 / dt;
+
+    const double *mp = a.mean + (int64_t)j * a.ldm + 3 * (int64_t)n;
+    const double *sp = a.vars + (int64_t)j * a.lds + 2 * (int64_t)n;
+    const double P0 = mp[0], P1 = mp[1], P2 = mp[2], P3 = mp[3];
+    double S0 = sp[0], S1 = sp[1], S2 = sp[2];
+    if (a.log_vars) { S0 = exp(S0); S1 = exp(S1); S2 = exp(S2); }
+    const double Sig = a.sigma[j];
+    const double inv_sig = 1.0 / Sig;
+    const double theta = a.theta[0];
+
+    double accM[4] = {0, 0, 0, 0}, accS[3] = {0, 0, 0};
+    double accE = 0.0, kgE = 0.0, kgS[3] = {0, 0, 0}, ownS1 = 0.0;
+    double eE1 = 0.0, eS1 = 0.0;
+
+#pragma unroll 1
+    for (int q = 0; q < kNodes; ++q) {
+        const double *T = c_tab + q * kTabStride;
+        const double m = P0 * T[T_B3] + P1 * T[T_B3 + 1] + P2 * T[T_B3 + 2] + P3 * T[T_B3 + 3];
+        const double dm = (P0 * T[T_DB3] + P1 * T[T_DB3 + 1] + P2 * T[T_DB3 + 2]
+                           + P3 * T[T_DB3 + 3]) * inv_dt;
+        const double s = S0 * T[T_B2] + S1 * T[T_B2 + 1] + S2 * T[T_B2 + 2];
+        const double ds = (S0 * T[T_DB2] + S1 * T[T_DB2 + 1] + S2 * T[T_DB2 + 2]) * inv_dt;
+        sh_m[e] = m;
+        sh_s[e] = s;
+        __syncthreads();
+
+        double own_m = 0.0, own_s = 0.0, own_ds = 0.0;
+        if (has_energy) {
+            const double ma = sh_m[e + 1], mb = sh_m[e - 1], mc = sh_m[e - 2];
+            const double sa = sh_s[e + 1], sb = sh_s[e - 1], sc = sh_s[e - 2];
+            const double u = ma - mc, su = sa + sc;
+            const double R = fma(u, mb, theta - m) - dm;       // E[f_i] - dm_i
+            const Rational r(s, ds, Sig);
+            const double E = R * R + s + sb * u * u + mb * mb * su + su * sb + r.rat + r.q;
+            const double w = T[T_V] * inv_sig;
+            const double wR2 = 2.0 * w * R;
+            sh_A[e] = wR2 * mb + 2.0 * w * sb * u;             // w dE_i/dm_{i+1} (= -w dE_i/dm_{i-2})
+            sh_B[e] = wR2 * u + 2.0 * w * mb * su;             // w dE_i/dm_{i-1}
+            sh_C[e] = w * (mb * mb + sb);                      // w dE_i/ds_{i+1} = w dE_i/ds_{i-2}
+            sh_Dv[e] = w * (u * u + su);                       // w dE_i/ds_{i-1}
+            own_m = -wR2;                                      // w dE_i/dm_i = w dE_i/d(dm_i)
+            const double es = 1.0 + r.rat_s, eds = r.rat_ds + 1.0;
+            own_s = w * es;
+            own_ds = w * eds;
+            if (is_out) {
+                accE = fma(w, E, accE);
+                const double c = T[T_C];
+                kgE = fma(c, E, kgE);
+                const double ces = c * es, ceds = c * eds * inv_dt;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    kgS[k] += ces * T[T_B2 + k] + ceds * T[T_DB2 + k];
+                ownS1 += T[T_V] * (es * T[T_B2 + 1] + eds * inv_dt * T[T_DB2 + 1]);
+            }
+        }
+        __syncthreads();
+        if (is_out) {
+            const double Gm = own_m + sh_A[e - 1] + sh_B[e + 1] - sh_A[e + 2];
+            const double Gs = own_s + sh_C[e - 1] + sh_Dv[e + 1] + sh_C[e + 2];
+            const double Hm = own_m * inv_dt, Hs = own_ds * inv_dt;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                accM[k] += Gm * T[T_B3 + k] + Hm * T[T_DB3 + k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                accS[k] += Gs * T[T_B2 + k] + Hs * T[T_DB2 + k];
+        }
+        if (q == kNodesPerPanel - 1) {                         // end of panel 1
+            eE1 = kgE * kgE;
+            eS1 = kgS[0] * kgS[0] + kgS[1] * kgS[1] + kgS[2] * kgS[2];
+            kgE = 0.0;
+            kgS[0] = kgS[1] = kgS[2] = 0.0;
+        }
+    }
+
+    // free_energy.py:446-458: the 1/2 factors; h = dt/4 is the panel half width
+    const double scale = 0.5 * (0.25 * dt);
+    if (is_out && a.dm_out != nullptr) {
+        double *om = a.dm_out + ((int64_t)n * D + j) * 4;
+        double *os = a.ds_out + ((int64_t)n * D + j) * 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) om[k] = scale * accM[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) os[k] = scale * accS[k];
+    }
+    const double KE = accE * Sig;                              // raw sum_r v_r E_i
+    double red[7] = {accE, KE * KE, eE1, kgE * kgE, eS1,
+                     kgS[0] * kgS[0] + kgS[1] * kgS[1] + kgS[2] * kgS[2], ownS1 * ownS1};
+    if (!is_out)
+#pragma unroll
+        for (int i = 0; i < 7; ++i) red[i] = 0.0;
+    block_sum<7, TE>(red, sh_red);
+    if (threadIdx.x == 0) {
+        double *p = a.part + (int64_t)blockIdx.x * kPartStride;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) p[i] = red[i];
+        p[7] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// DW / OU / L63 (D <= 3): one CTA per interval, one thread per quadrature
+// node; each thread evaluates all dimensions at its node, the 42 node values
+// are then summed in scipy's order (panel 1 then panel 2, r = 0..20).
+// ---------------------------------------------------------------------------
+template <int SYS>
+__global__ void __launch_bounds__(64)
+esde_small_kernel(const EsdeArgs a) {
+    using Dr = Drift<SYS>;
+    constexpr int D = Dr::D;
+    constexpr int NV = 1 + 4 * D + 3 * D + D + 3 * D;   // see value layout below
+    constexpr int V_E = 0, V_DM = 1, V_DS = V_DM + 4 * D, V_RE = V_DS + 3 * D,
+                  V_RS = V_RE + D;
+    __shared__ double vals[NV][kNodes];
+    __shared__ double sums[NV][4];                       // K1, K2, KG1, KG2
+
+    const int n = a.n_begin + blockIdx.x;
+    const int q = threadIdx.x;
+    const double ti = a.obs_times[n], tj = a.obs_times[n + 1];
+    const double dt = fabs(tj - ti);
+    const double inv_dt = 1.0 / dt;
+
+    if (q < kNodes) {
+        const double *T = c_tab + q * kTabStride;
+        double m[D], dm[D], s[D], ds[D], Sig[D], inv_sig[D], th[Dr::NTHETA];
+#pragma unroll
+        for (int i = 0; i < Dr::NTHETA; ++i) th[i] = a.theta[i];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double *mp = a.mean + (int64_t)j * a.ldm + 3 * (int64_t)n;
+            const double *sp = a.vars + (int64_t)j * a.lds + 2 * (int64_t)n;
+            double S0 = sp[0], S1 = sp[1], S2 = sp[2];
+            if (a.log_vars) { S0 = exp(S0); S1 = exp(S1); S2 = exp(S2); }
+            m[j] = mp[0] * T[T_B3] + mp[1] * T[T_B3 + 1] + mp[2] * T[T_B3 + 2]
+                   + mp[3] * T[T_B3 + 3];
+            dm[j] = (mp[0] * T[T_DB3] + mp[1] * T[T_DB3 + 1] + mp[2] * T[T_DB3 + 2]
+                     + mp[3] * T[T_DB3 + 3]) * inv_dt;
+            s[j] = S0 * T[T_B2] + S1 * T[T_B2 + 1] + S2 * T[T_B2 + 2];
+            ds[j] = (S0 * T[T_DB2] + S1 * T[T_DB2 + 1] + S2 * T[T_DB2 + 2]) * inv_dt;
+            Sig[j] = a.sigma[j];
+            inv_sig[j] = 1.0 / Sig[j];
+        }
+        double E[D], Em[D][D], Edm[D], Es[D][D], Eds[D];
+        Dr::nodal(m, dm, s, ds, Sig, th, E, Em, Edm, Es, Eds);
+        double we = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) we += inv_sig[i] * E[i];
+        vals[V_E][q] = we;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            double gm = 0.0, gs = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                gm += inv_sig[i] * Em[i][j];
+                gs += inv_sig[i] * Es[i][j];
+            }
+            const double hm = inv_sig[j] * Edm[j] * inv_dt;
+            const double hs = inv_sig[j] * Eds[j] * inv_dt;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                vals[V_DM + 4 * j + k][q] = gm * T[T_B3 + k] + hm * T[T_DB3 + k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                vals[V_DS + 3 * j + k][q] = gs * T[T_B2 + k] + hs * T[T_DB2 + k];
+                vals[V_RS + 3 * j + k][q] =
+                    Es[j][j] * T[T_B2 + k] + Eds[j] * inv_dt * T[T_DB2 + k];
+            }
+            vals[V_RE + j][q] = E[j];
+        }
+    }
+    __syncthreads();
+    if (q < NV) {
+        double K1 = 0.0, K2 = 0.0, G1 = 0.0, G2 = 0.0;
+        for (int r = 0; r < kNodesPerPanel; ++r) {
+            const double v = c_tab[r * kTabStride + T_V], c = c_tab[r * kTabStride + T_C];
+            const double f1 = vals[q][r], f2 = vals[q][kNodesPerPanel + r];
+            K1 = fma(v, f1, K1);
+            K2 = fma(v, f2, K2);
+            G1 = fma(c, f1, G1);
+            G2 = fma(c, f2, G2);
+        }
+        sums[q][0] = K1; sums[q][1] = K2; sums[q][2] = G1; sums[q][3] = G2;
+        const double scale = 0.5 * (0.25 * dt);
+        if (a.dm_out != nullptr) {
+            if (q >= V_DM && q < V_DS)
+                a.dm_out[(int64_t)n * D * 4 + (q - V_DM)] = scale * (K1 + K2);
+            else if (q >= V_DS && q < V_RE)
+                a.ds_out[(int64_t)n * D * 3 + (q - V_DS)] = scale * (K1 + K2);
+        }
+    }
+    __syncthreads();
+    if (q == 0) {
+        double p[kPartStride] = {0, 0, 0, 0, 0, 0, 0, 0};
+        p[0] = sums[V_E][0] + sums[V_E][1];
+        for (int i = 0; i < D; ++i) {
+            const double KE = sums[V_RE + i][0] + sums[V_RE + i][1];
+            p[1] += KE * KE;
+            p[2] += sums[V_RE + i][2] * sums[V_RE + i][2];
+            p[3] += sums[V_RE + i][3] * sums[V_RE + i][3];
+            for (int k = 0; k < 3; ++k) {
+                const double *sv = sums[V_RS + 3 * i + k];
+                p[4] += sv[2] * sv[2];
+                p[5] += sv[3] * sv[3];
+            }
+            const double KS = sums[V_RS + 3 * i + 1][0] + sums[V_RS + 3 * i + 1][1];
+            p[6] += KS * KS;
+        }
+        double *out = a.part + (int64_t)blockIdx.x * kPartStride;
+        for (int i = 0; i < kPartStride; ++i) out[i] = p[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Per-interval reduction of the dim-tile partials: the interval's Esde share
+// and a conservative version of quad_vec's convergence test after its first
+// bisection (scipy _quad_vec.py: err_p <= 200 |(K-G) h|, converged when
+// sum_p err_p < max(epsabs, epsrel |I|)/8).  An interval whose bound fails is
+// flagged for the adaptive kernels; otherwise the fixed rule IS quad_vec's
+// answer.  One warp per interval.
+// ---------------------------------------------------------------------------
+struct GuardArgs {
+    const double *part;        // [(n_end-n_begin)*ntiles][kPartStride]
+    const double *obs_times;
+    double *esde_n;            // [L] per-interval Esde (already * 1/2)
+    int32_t *flags;            // [L] bit0 energy integrand, bit1 dS integrand
+    int n_begin, n_end, ntiles;
+};
+
+__global__ void __launch_bounds__(256)
+guard_reduce_kernel(const GuardArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n = a.n_begin + warp;
+    if (n >= a.n_end) return;
+    double p[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int t = lane; t < a.ntiles; t += 32) {
+        const double *src = a.part + ((int64_t)warp * a.ntiles + t) * kPartStride;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) p[i] += src[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) p[i] = warp_sum(p[i]);
+    if (lane == 0) {
+        const double dt = fabs(a.obs_times[n + 1] - a.obs_times[n]);
+        const double h = 0.25 * dt;
+        a.esde_n[n] = 0.5 * h * p[0];
+        const double tolE = fmax(1.0e-6, 1.0e-6 * h * sqrt(p[1]));
+        const double tolS = fmax(1.0e-6, 1.0e-6 * h * sqrt(p[6]));
+        const double ubE = 202.0 * h * (sqrt(p[2]) + sqrt(p[3]));
+        const double ubS = 202.0 * h * (sqrt(p[4]) + sqrt(p[5]));
+        int32_t f = 0;
+        if (!(ubE < 0.125 * tolE)) f |= 1;
+        if (!(ubS < 0.125 * tolS)) f |= 2;
+        a.flags[n] = f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// E_cost assembly (free_energy.py:686-750): stitches the per-interval
+// gradients (shared end points add), adds dE0 at column 0 and dEobs at the
+// observation columns, applies the log-variance chain rule, and accumulates
+// the E_kl0 / E_obs energy terms.  One CTA per state dimension (row of x).
+// ---------------------------------------------------------------------------
+struct AssembleArgs {
+    const double *x;          // [D*Nm + D*Ns]
+    const double *dm;         // [L][D][4]
+    const double *ds;         // [L][D][3]
+    const double *mu0, *tau0;
+    const double *obs_values; // [M][d]
+    const double *obs_noise;  // [d]
+    const int32_t *obs_idx;   // [D] index into the observed dims or -1
+    double *grad;             // same layout as x (may be nullptr)
+    double *apart;            // [D][4]: sum log(tau0/s0), sum kl0 quad, sum obs, -
+    int D, M, d, Nm, Ns;
+    int n_begin, n_end, L;    // owned intervals; L = M-1
+    int with_e0;              // this shard owns column 0
+};
+
+__global__ void __launch_bounds__(256)
+assemble_kernel(const AssembleArgs a) {
+    __shared__ double sh_red[3 * 8];
+    const int j = blockIdx.x;
+    const int jo = a.obs_idx[j];
+    const double Ri = jo >= 0 ? 1.0 / a.obs_noise[jo] : 0.0;
+    const double *xm = a.x + (int64_t)j * a.Nm;
+    const double *xs = a.x + (int64_t)a.D * a.Nm + (int64_t)j * a.Ns;
+    double *gm = a.grad ? a.grad + (int64_t)j * a.Nm : nullptr;
+    double *gs = a.grad ? a.grad + (int64_t)a.D * a.Nm + (int64_t)j * a.Ns : nullptr;
+    // owned column ranges of this shard
+    const int cm0 = 3 * a.n_begin, cm1 = (a.n_end == a.L) ? a.Nm : 3 * a.n_end;
+    const int cs0 = 2 * a.n_begin, cs1 = (a.n_end == a.L) ? a.Ns : 2 * a.n_end;
+    double acc[3] = {0.0, 0.0, 0.0};
+
+    for (int c = cm0 + threadIdx.x; c < cm1; c += blockDim.x) {
+        const int n = c / 3, k = c - 3 * n;
+        double g = 0.0;
+        if (a.dm != nullptr) {
+            if (n >= a.n_begin && n < a.n_end)
+                g = a.dm[((int64_t)n * a.D + j) * 4 + k];
+            if (k == 0 && n - 1 >= a.n_begin && n - 1 < a.n_end)
+                g += a.dm[((int64_t)(n - 1) * a.D + j) * 4 + 3];
+        }
+        const double m = xm[c];
+        if (c == 0 && a.with_e0) {
+            const double z0 = m - a.mu0[j];
+            g += z0 / a.tau0[j];
+            acc[1] += z0 * z0 / a.tau0[j];
+        }
+        if (k == 0 && n >= 1 && n <= a.M && jo >= 0) {
+            const double r = a.obs_values[(int64_t)(n - 1) * a.d + jo] - m;
+            g -= Ri * r;
+            acc[2] += Ri * r * r;
+        }
+        if (gm) gm[c] = g;
+    }
+    for (int c = cs0 + threadIdx.x; c < cs1; c += blockDim.x) {
+        const int n = c >> 1, k = c & 1;
+        double g = 0.0;
+        if (a.ds != nullptr) {
+            if (n >= a.n_begin && n < a.n_end)
+                g = a.ds[((int64_t)n * a.D + j) * 3 + k];
+            if (k == 0 && n - 1 >= a.n_begin && n - 1 < a.n_end)
+                g += a.ds[((int64_t)(n - 1) * a.D + j) * 3 + 2];
+        }
+        const double s = exp(xs[c]);
+        if (c == 0 && a.with_e0) {
+            const double t0 = a.tau0[j];
+            g += 0.5 * (1.0 / t0 - 1.0 / s);
+            acc[0] += log(t0 / s);
+            acc[1] += (s - t0) / t0;
+        }
+        if (k == 0 && n >= 1 && n <= a.M && jo >= 0) {
+            g += 0.5 * Ri;
+            acc[2] += Ri * s;
+        }
+        if (gs) gs[c] = g * s;                       // free_energy.py:743
+    }
+    block_sum<3, 256>(acc, sh_red);
+    if (threadIdx.x == 0) {
+        double *p = a.apart + (int64_t)j * 4;
+        p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Final scalar reduction (fixed order => deterministic), status bits.
+// out[0..3] = F, E0, Esde, Eobs.
+// ---------------------------------------------------------------------------
+struct FinalArgs {
+    const double *esde_n;     // [L]
+    const int32_t *flags;     // [L]
+    const double *apart;      // [D][4] or nullptr (E_sde only)
+    double *out;              // [4]
+    int32_t *status;          // [1]
+    int n_begin, n_end, D;
+    int with_e0;
+    double eobs_const;        // M (d log 2pi + safe_log(prod R)), 0 on non-owning shards
+};
+
+__global__ void __launch_bounds__(256)
+final_kernel(const FinalArgs a) {
+    __shared__ double sh_red[4 * 8];
+    __shared__ int sh_flag;
+    if (threadIdx.x == 0) sh_flag = 0;
+    __syncthreads();
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int anyflag = 0;
+    for (int n = a.n_begin + threadIdx.x; n < a.n_end; n += blockDim.x) {
+        acc[0] += a.esde_n[n];
+        anyflag |= a.flags[n];
+    }
+    if (a.apart != nullptr)
+        for (int j = threadIdx.x; j < a.D; j += blockDim.x) {
+            acc[1] += a.apart[(int64_t)j * 4 + 0];
+            acc[2] += a.apart[(int64_t)j * 4 + 1];
+            acc[3] += a.apart[(int64_t)j * 4 + 2];
+        }
+    if (anyflag) atomicOr(&sh_flag, anyflag);
+    block_sum<4, 256>(acc, sh_red);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double Esde = acc[0];
+        double E0 = 0.0, Eobs = 0.0;
+        if (a.apart != nullptr) {
+            if (a.with_e0) {
+                // safe_log(prod(tau0/s0)) (utilities.py:73-76): clamp in log space
+                const double lo = -690.77552789821368, hi = 690.77552789821368;
+                const double lg = fmin(fmax(acc[1], lo), hi);
+                E0 = 0.5 * (lg + acc[2]);
+            }
+            Eobs = 0.5 * (acc[3] + a.eobs_const);
+        }
+        a.out[0] = E0 + Esde + Eobs;
+        a.out[1] = E0;
+        a.out[2] = Esde;
+        a.out[3] = Eobs;
+        int32_t st = 0;
+        if (!isfinite(Esde)) st |= 1;
+        if (!isfinite(E0)) st |= 2;
+        if (!isfinite(Eobs)) st |= 4;
+        if (sh_flag) st |= 8;
+        a.status[0] = st;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// FP64 FMA throughput micro-benchmark: the roofline denominator for the Esde
+// kernels (MEASURED_PEAKS.json has no FP64 entry).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace mfvgp

@@ -1,0 +1,589 @@
+// C ABI (include/mfvgp.h) over the kernels in kernels.cuh / scg.cuh.
+// Pure CUDA runtime: no torch types cross this boundary.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mfvgp.h"
+#include "kernels.cuh"
+#include "scg.cuh"
+
+using namespace mfvgp;
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                              \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) {                                              \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);       \
+            return MFVGP_ERR_CUDA;                                            \
+        }                                                                     \
+    } while (0)
+
+#define ARG(cond, msg)                                                        \
+    do {                                                                      \
+        if (!(cond)) {                                                        \
+            g_err = msg;                                                      \
+            return MFVGP_ERR_ARG;                                             \
+        }                                                                     \
+    } while (0)
+
+struct mfvgp_handle {
+    int system = 0, D = 0, M = 0, d = 0, device = 0;
+    int L = 0, n_begin = 0, n_end = 0, Nm = 0, Ns = 0, ntheta = 0;
+    int te = 64, ntiles = 1;
+    bool have_sde = false, have_prior = false, have_obs = false;
+    double eobs_const = 0.0;
+    // problem data (device)
+    double *sigma = nullptr, *theta = nullptr, *mu0 = nullptr, *tau0 = nullptr;
+    double *obs_times = nullptr, *obs_values = nullptr, *obs_noise = nullptr;
+    int32_t *obs_idx = nullptr;
+    // workspaces (device)
+    double *dm_ws = nullptr, *ds_ws = nullptr, *part = nullptr, *esde_n = nullptr;
+    double *apart = nullptr, *out_ws = nullptr;
+    int32_t *flags = nullptr, *status_ws = nullptr;
+    // host-API staging
+    double *x_dev = nullptr, *grad_dev = nullptr;
+    double *pin = nullptr;   // pinned: out[4] + status
+    // SCG workspace (device): two iterates, direction, 3 rotating gradients, g_plus
+    double *scg_vec[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *scg_part = nullptr, *scg_scal = nullptr;
+    int scg_nblk = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+};
+
+static int dev_alloc(double **p, size_t n) {
+    CK(cudaMalloc((void **)p, (n ? n : 1) * sizeof(double)));
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_version(void) { return MFVGP_VERSION; }
+extern "C" const char *mfvgp_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mfvgp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int64_t mfvgp_launch_count(const mfvgp_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
+                            int device, int n_begin, int n_end) {
+    ARG(out != nullptr, "mfvgp_create: out is NULL");
+    ARG(system >= MFVGP_SYS_DW && system <= MFVGP_SYS_L96, "mfvgp_create: unknown system");
+    ARG(M >= 2, "mfvgp_create: need at least 2 observation times");
+    ARG(d >= 1 && d <= D, "mfvgp_create: need 1 <= d <= D");
+    if (system == MFVGP_SYS_DW || system == MFVGP_SYS_OU) ARG(D == 1, "DW/OU need D = 1");
+    if (system == MFVGP_SYS_L63) ARG(D == 3, "L63 needs D = 3");
+    // lorenz_96.py:60-63
+    if (system == MFVGP_SYS_L96) ARG(D >= 4, "Lorenz96: Insufficient state vector dimensions");
+    const int L = M - 1;
+    if (n_end < 0) n_end = L;
+    ARG(n_begin >= 0 && n_begin < n_end && n_end <= L, "mfvgp_create: bad interval range");
+    if (mfvgp_device_count() <= device) {
+        g_err = "mfvgp_create: no CUDA device (this library has no CPU fallback)";
+        return MFVGP_ERR_CUDA;
+    }
+    CK(cudaSetDevice(device));
+    mfvgp_handle *h = new mfvgp_handle();
+    h->system = system; h->D = D; h->M = M; h->d = d; h->device = device;
+    h->L = L; h->n_begin = n_begin; h->n_end = n_end;
+    h->Nm = 3 * M + 4; h->Ns = 2 * M + 3;
+    const int64_t cells = (int64_t)D * (n_end - n_begin);
+    if (system == MFVGP_SYS_L96) {
+        h->te = D <= 26 ? 32 : (cells <= 148 * 512 ? 64 : 128);
+        h->ntiles = (D + h->te - 7) / (h->te - 6);
+    }
+    const int nl = n_end - n_begin;
+    double tab[kNodes * kTabStride];
+    build_fixed_table(tab);
+    CK(cudaMemcpyToSymbol(c_tab, tab, sizeof(tab)));
+    if (dev_alloc(&h->sigma, D) || dev_alloc(&h->theta, 8) || dev_alloc(&h->mu0, D) ||
+        dev_alloc(&h->tau0, D) || dev_alloc(&h->obs_times, M) ||
+        dev_alloc(&h->obs_values, (size_t)M * d) || dev_alloc(&h->obs_noise, d) ||
+        dev_alloc(&h->dm_ws, (size_t)L * D * 4) || dev_alloc(&h->ds_ws, (size_t)L * D * 3) ||
+        dev_alloc(&h->part, (size_t)nl * h->ntiles * kPartStride) ||
+        dev_alloc(&h->esde_n, L) || dev_alloc(&h->apart, (size_t)D * 4) ||
+        dev_alloc(&h->out_ws, 4))
+        return MFVGP_ERR_CUDA;
+    CK(cudaMalloc((void **)&h->obs_idx, D * sizeof(int32_t)));
+    CK(cudaMalloc((void **)&h->flags, L * sizeof(int32_t)));
+    CK(cudaMalloc((void **)&h->status_ws, sizeof(int32_t)));
+    CK(cudaMemset(h->flags, 0, L * sizeof(int32_t)));
+    CK(cudaMemset(h->esde_n, 0, L * sizeof(double)));
+    CK(cudaMallocHost((void **)&h->pin, 16 * sizeof(double)));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    *out = h;
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_destroy(mfvgp_handle *h) {
+    if (!h) return MFVGP_OK;
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->sigma, h->theta, h->mu0, h->tau0, h->obs_times, h->obs_values,
+                    h->obs_noise, h->obs_idx, h->dm_ws, h->ds_ws, h->part, h->esde_n,
+                    h->apart, h->out_ws, h->flags, h->status_ws, h->x_dev, h->grad_dev,
+                    h->scg_vec[0], h->scg_vec[1], h->scg_vec[2], h->scg_vec[3], h->scg_vec[4],
+                    h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_set_sde(mfvgp_handle *h, const double *sigma_h, const double *theta_h,
+                             int ntheta) {
+    ARG(h && sigma_h && theta_h, "mfvgp_set_sde: NULL argument");
+    const int need = h->system == MFVGP_SYS_OU ? 2 : (h->system == MFVGP_SYS_L63 ? 3 : 1);
+    ARG(ntheta == need, "mfvgp_set_sde: wrong number of drift parameters");
+    for (int i = 0; i < h->D; ++i)   // stochastic_process.py:112-115
+        ARG(sigma_h[i] > 0.0, "SDE noise vector is not positive");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(h->sigma, sigma_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->theta, theta_h, ntheta * sizeof(double), cudaMemcpyHostToDevice));
+    h->ntheta = ntheta;
+    h->have_sde = true;
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_set_prior(mfvgp_handle *h, const double *mu0_h, const double *tau0_h) {
+    ARG(h && mu0_h && tau0_h, "mfvgp_set_prior: NULL argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(h->mu0, mu0_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->tau0, tau0_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
+    h->have_prior = true;
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_set_obs(mfvgp_handle *h, const double *obs_times_h,
+                             const double *obs_values_h, const double *obs_noise_h,
+                             const uint8_t *obs_mask_h) {
+    ARG(h && obs_times_h && obs_values_h && obs_noise_h, "mfvgp_set_obs: NULL argument");
+    std::vector<int32_t> idx(h->D, -1);
+    int cnt = 0;
+    for (int j = 0; j < h->D; ++j)
+        if (obs_mask_h == nullptr || obs_mask_h[j]) idx[j] = cnt++;
+    ARG(cnt == h->d, "mfvgp_set_obs: observation mask does not select d dimensions");
+    // free_energy.py:612 -- num_M (dim_d log2pi + safe_log(prod(obs_noise)))
+    double prod = 1.0;
+    for (int i = 0; i < h->d; ++i) prod *= obs_noise_h[i];
+    const double clamped = fmax(fmin(prod, 1.0e300), 1.0e-300);
+    h->eobs_const = h->M * (h->d * 1.8378770664093453 + log(clamped));
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(h->obs_times, obs_times_h, h->M * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->obs_values, obs_values_h, (size_t)h->M * h->d * sizeof(double),
+                  cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->obs_noise, obs_noise_h, h->d * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->obs_idx, idx.data(), h->D * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->have_obs = true;
+    return MFVGP_OK;
+}
+
+// ---- launch helpers ---------------------------------------------------------
+static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const double *vars,
+                       int64_t lds, int log_vars, double *dm, double *ds, cudaStream_t st) {
+    EsdeArgs a;
+    a.mean = mean; a.vars = vars; a.ldm = ldm; a.lds = lds;
+    a.obs_times = h->obs_times; a.sigma = h->sigma; a.theta = h->theta;
+    a.dm_out = dm; a.ds_out = ds; a.part = h->part;
+    a.D = h->D; a.n_begin = h->n_begin; a.n_end = h->n_end; a.ntiles = h->ntiles;
+    a.log_vars = log_vars;
+    const int nl = h->n_end - h->n_begin;
+    switch (h->system) {
+        case MFVGP_SYS_DW: esde_small_kernel<0><<<nl, 64, 0, st>>>(a); break;
+        case MFVGP_SYS_OU: esde_small_kernel<1><<<nl, 64, 0, st>>>(a); break;
+        case MFVGP_SYS_L63: esde_small_kernel<2><<<nl, 64, 0, st>>>(a); break;
+        default: {
+            const unsigned grid = (unsigned)nl * h->ntiles;
+            if (h->te == 32) esde_l96_kernel<32><<<grid, 32, 0, st>>>(a);
+            else if (h->te == 64) esde_l96_kernel<64><<<grid, 64, 0, st>>>(a);
+            else esde_l96_kernel<128><<<grid, 128, 0, st>>>(a);
+        }
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    GuardArgs g;
+    g.part = h->part; g.obs_times = h->obs_times; g.esde_n = h->esde_n; g.flags = h->flags;
+    g.n_begin = h->n_begin; g.n_end = h->n_end; g.ntiles = h->ntiles;
+    guard_reduce_kernel<<<(nl * 32 + 255) / 256, 256, 0, st>>>(g);
+    h->launches++;
+    CK(cudaGetLastError());
+    return MFVGP_OK;
+}
+
+static int launch_final(mfvgp_handle *h, const double *apart, double *out, int32_t *status,
+                        cudaStream_t st) {
+    FinalArgs f;
+    f.esde_n = h->esde_n; f.flags = h->flags; f.apart = apart; f.out = out; f.status = status;
+    f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = h->D;
+    f.with_e0 = h->n_begin == 0;
+    f.eobs_const = h->n_begin == 0 ? h->eobs_const : 0.0;
+    final_kernel<<<1, 256, 0, st>>>(f);
+    h->launches++;
+    CK(cudaGetLastError());
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_esde(mfvgp_handle *h, const double *mean_pts_d, int64_t ldm,
+                          const double *vars_pts_d, int64_t lds, int want_grad, double *out_d,
+                          double *dEsde_dm_d, double *dEsde_ds_d, int32_t *status_d,
+                          void *cuda_stream) {
+    ARG(h && mean_pts_d && vars_pts_d && out_d && status_d, "mfvgp_esde: NULL argument");
+    ARG(!want_grad || (dEsde_dm_d && dEsde_ds_d), "mfvgp_esde: gradient buffers are NULL");
+    if (!h->have_sde || !h->have_obs) {
+        g_err = "mfvgp_esde: set_sde/set_obs not called";
+        return MFVGP_ERR_STATE;
+    }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = launch_esde(h, mean_pts_d, ldm, vars_pts_d, lds, 0,
+                         want_grad ? dEsde_dm_d : nullptr, want_grad ? dEsde_ds_d : nullptr, st);
+    if (rc) return rc;
+    // E_sde alone: out[0] = Esde (reported through the F slot as well)
+    rc = launch_final(h, nullptr, h->out_ws, status_d, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_d, h->out_ws + 2, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, double *out_d,
+                           double *grad_d, int32_t *status_d, void *cuda_stream) {
+    ARG(h && x_d && out_d && status_d, "mfvgp_ecost: NULL argument");
+    ARG(!want_grad || grad_d, "mfvgp_ecost: gradient buffer is NULL");
+    if (!h->have_sde || !h->have_obs || !h->have_prior) {
+        g_err = "mfvgp_ecost: set_sde/set_prior/set_obs not called";
+        return MFVGP_ERR_STATE;
+    }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const double *mean = x_d;
+    const double *lvar = x_d + (int64_t)h->D * h->Nm;
+    int rc = launch_esde(h, mean, h->Nm, lvar, h->Ns, 1, want_grad ? h->dm_ws : nullptr,
+                         want_grad ? h->ds_ws : nullptr, st);
+    if (rc) return rc;
+    AssembleArgs a;
+    a.x = x_d; a.dm = want_grad ? h->dm_ws : nullptr; a.ds = want_grad ? h->ds_ws : nullptr;
+    a.mu0 = h->mu0; a.tau0 = h->tau0; a.obs_values = h->obs_values; a.obs_noise = h->obs_noise;
+    a.obs_idx = h->obs_idx; a.grad = want_grad ? grad_d : nullptr; a.apart = h->apart;
+    a.D = h->D; a.M = h->M; a.d = h->d; a.Nm = h->Nm; a.Ns = h->Ns;
+    a.n_begin = h->n_begin; a.n_end = h->n_end; a.L = h->L; a.with_e0 = h->n_begin == 0;
+    assemble_kernel<<<h->D, 256, 0, st>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    return launch_final(h, h->apart, out_d, status_d, st);
+}
+
+static int ensure_host_staging(mfvgp_handle *h) {
+    const size_t nx = (size_t)h->D * (h->Nm + h->Ns);
+    if (!h->x_dev) {
+        if (dev_alloc(&h->x_dev, nx) || dev_alloc(&h->grad_dev, nx)) return MFVGP_ERR_CUDA;
+    }
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_ecost_host(mfvgp_handle *h, const double *x_h, int want_grad,
+                                double *out_h, double *grad_h, int32_t *status_h) {
+    ARG(h && x_h && out_h && status_h, "mfvgp_ecost_host: NULL argument");
+    ARG(!want_grad || grad_h, "mfvgp_ecost_host: gradient buffer is NULL");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const size_t nx = (size_t)h->D * (h->Nm + h->Ns);
+    CK(cudaMemcpyAsync(h->x_dev, x_h, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = mfvgp_ecost(h, h->x_dev, want_grad, h->out_ws, h->grad_dev, h->status_ws, h->stream);
+    if (rc) return rc;
+    if (want_grad)
+        CK(cudaMemcpyAsync(grad_h, h->grad_dev, nx * sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+    CK(cudaMemcpyAsync(h->pin, h->out_ws, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin + 8, h->status_ws, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out_h, h->pin, 4 * sizeof(double));
+    memcpy(status_h, h->pin + 8, sizeof(int32_t));
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_esde_host(mfvgp_handle *h, const double *mean_pts_h,
+                               const double *vars_pts_h, int want_grad, double *Esde_h,
+                               double *dEsde_dm_h, double *dEsde_ds_h, int32_t *status_h) {
+    ARG(h && mean_pts_h && vars_pts_h && Esde_h && status_h, "mfvgp_esde_host: NULL argument");
+    ARG(!want_grad || (dEsde_dm_h && dEsde_ds_h), "mfvgp_esde_host: gradient buffers are NULL");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const size_t nm = (size_t)h->D * h->Nm, ns = (size_t)h->D * h->Ns;
+    CK(cudaMemcpyAsync(h->x_dev, mean_pts_h, nm * sizeof(double), cudaMemcpyHostToDevice,
+                       h->stream));
+    CK(cudaMemcpyAsync(h->x_dev + nm, vars_pts_h, ns * sizeof(double), cudaMemcpyHostToDevice,
+                       h->stream));
+    rc = mfvgp_esde(h, h->x_dev, h->Nm, h->x_dev + nm, h->Ns, want_grad, h->out_ws + 3,
+                    h->dm_ws, h->ds_ws, h->status_ws, h->stream);
+    if (rc) return rc;
+    if (want_grad) {
+        CK(cudaMemcpyAsync(dEsde_dm_h, h->dm_ws, (size_t)h->L * h->D * 4 * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(dEsde_ds_h, h->ds_ws, (size_t)h->L * h->D * 3 * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaMemcpyAsync(h->pin, h->out_ws + 3, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin + 8, h->status_ws, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *Esde_h = h->pin[0];
+    memcpy(status_h, h->pin + 8, sizeof(int32_t));
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_fp64_peak(int device, double *tflops_out) {
+    ARG(tflops_out != nullptr, "mfvgp_fp64_peak: NULL argument");
+    if (mfvgp_device_count() <= device) {
+        g_err = "mfvgp_fp64_peak: no CUDA device";
+        return MFVGP_ERR_CUDA;
+    }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *buf = nullptr;
+    CK(cudaMalloc((void **)&buf, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, threads>>>(buf, iters, 0.999999, 1.0e-9);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+        const double tf = flops / (ms * 1.0e-3) * 1.0e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    *tflops_out = best;
+    return MFVGP_OK;
+}
+
+// ---- scaled conjugate gradient (scaled_cg.py:107-386) -----------------------
+namespace {
+
+struct ScgRun {
+    mfvgp_handle *h;
+    cudaStream_t st;
+    int64_t n;
+    int status_or = 0;
+
+    int fold() {
+        scg_fold_kernel<<<1, kRedBlock, 0, st>>>(h->scg_part, h->scg_nblk, h->scg_scal);
+        h->launches++;
+        CK(cudaGetLastError());
+        return MFVGP_OK;
+    }
+    // reads scal[0..3] (fold output), scal[4..7] (E_cost output) and the status
+    int read(double *s8) {
+        CK(cudaMemcpyAsync(h->pin, h->scg_scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->pin + 8, h->status_ws, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                           st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(s8, h->pin, 8 * sizeof(double));
+        int32_t stt;
+        memcpy(&stt, h->pin + 8, sizeof(int32_t));
+        status_or |= stt;
+        return MFVGP_OK;
+    }
+    int eval(const double *x, double *g) {
+        return mfvgp_ecost(h, x, 1, h->scg_scal + 4, g, h->status_ws, st);
+    }
+    int direction(double *d, const double *g, double gamma, int restart) {
+        scg_direction_kernel<<<h->scg_nblk, kRedBlock, 0, st>>>(d, g, gamma, restart, n,
+                                                                h->scg_part);
+        h->launches++;
+        CK(cudaGetLastError());
+        return fold();
+    }
+    int axpy(double *y, const double *x, const double *d, double a) {
+        scg_axpy_kernel<<<h->scg_nblk, kRedBlock, 0, st>>>(y, x, d, a, n);
+        h->launches++;
+        CK(cudaGetLastError());
+        return MFVGP_OK;
+    }
+    int theta(const double *d, const double *gp, const double *g) {
+        scg_theta_kernel<<<h->scg_nblk, kRedBlock, 0, st>>>(d, gp, g, n, h->scg_part);
+        h->launches++;
+        CK(cudaGetLastError());
+        return fold();
+    }
+    int stats(const double *g_now, const double *g_new, const double *d) {
+        scg_stats_kernel<<<h->scg_nblk, kRedBlock, 0, st>>>(g_now, g_new, d, n, h->scg_part);
+        h->launches++;
+        CK(cudaGetLastError());
+        return fold();
+    }
+};
+
+#define RC(call)                \
+    do {                        \
+        int rc_ = (call);       \
+        if (rc_) return rc_;    \
+    } while (0)
+
+}  // namespace
+
+extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol, double f_tol,
+                         double *fx_hist_h, double *dfx_hist_h, double *result_h,
+                         void *cuda_stream) {
+    ARG(h && x_d && fx_hist_h && dfx_hist_h && result_h, "mfvgp_scg: NULL argument");
+    ARG(max_it >= 1, "mfvgp_scg: max_it must be positive");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int64_t n = (int64_t)h->D * (h->Nm + h->Ns);
+    if (!h->scg_vec[0]) {
+        for (int i = 0; i < 7; ++i)
+            if (dev_alloc(&h->scg_vec[i], n)) return MFVGP_ERR_CUDA;
+        int64_t nb = (n + kRedBlock * 4 - 1) / (kRedBlock * 4);
+        h->scg_nblk = (int)(nb < 1 ? 1 : (nb > 1184 ? 1184 : nb));
+        if (dev_alloc(&h->scg_part, (size_t)h->scg_nblk * kRedSlots) ||
+            dev_alloc(&h->scg_scal, 8))
+            return MFVGP_ERR_CUDA;
+    }
+    ScgRun R{h, st, n};
+    double *x = h->scg_vec[0], *xt = h->scg_vec[1], *d = h->scg_vec[2];
+    double *gnew = h->scg_vec[3], *gold = h->scg_vec[4], *gnow = h->scg_vec[5];
+    double *gp = h->scg_vec[6];
+    double s8[8];
+    for (int i = 0; i < max_it; ++i) fx_hist_h[i] = dfx_hist_h[i] = 0.0;   // :123-124
+    CK(cudaMemcpyAsync(x, x_d, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+
+    int nit = max_it, func_eval = 0;
+    double fx = 0.0;
+    // scaled_cg.py:145-175
+    RC(R.eval(x, gnew));
+    RC(R.stats(gnew, gnew, gnew));
+    RC(R.read(s8));
+    double f_now = s8[4], sa_new = s8[0];
+    func_eval++;
+    bool failed = (R.status_or & 7) != 0;
+    CK(cudaMemcpyAsync(gold, gnew, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    double sa_old = sa_new, f_old = f_now;
+    RC(R.direction(d, gnew, 0.0, 1));                            // d = -grad_new
+    RC(R.read(s8));
+    double mu = s8[0], kappa = s8[1], theta = 0.0, beta = 1.0;
+    const double beta_min = 1.0e-15, beta_max = 1.0e100, eps = 2.220446049250313e-16;
+    bool success = true, done = failed;
+    int64_t count_success = 0;
+    if (failed) { nit = 0; fx = f_now; }
+
+    for (int j = 0; j < max_it && !done; ++j) {                   // :186
+        if (success) {
+            if (mu >= 0.0) {                                      // :194-197
+                RC(R.direction(d, gnew, 0.0, 1));
+                RC(R.read(s8));
+                mu = s8[0]; kappa = s8[1];
+            }
+            if (kappa < eps) { fx = f_now; nit = j + 1; done = true; break; }   // :203
+            const double sigma = 1.0e-3 / sqrt(kappa);
+            RC(R.axpy(xt, x, d, sigma));
+            RC(R.eval(xt, gp));                                   // :222
+            RC(R.theta(d, gp, gnew));
+            RC(R.read(s8));
+            func_eval++;
+            if (R.status_or & 7) { fx = f_now; nit = j + 1; done = true; break; }
+            theta = s8[0] / sigma;                                // :228
+        }
+        double delta = theta + beta * kappa;                      // :232-236
+        if (delta <= 0.0) {
+            delta = beta * kappa;
+            beta = beta - theta / kappa;
+        }
+        const double alpha = -(mu / delta);
+        RC(R.axpy(xt, x, d, alpha));
+        RC(R.eval(xt, gnow));                                     // :247
+        RC(R.stats(gnow, gnew, d));
+        RC(R.read(s8));
+        func_eval++;
+        if (R.status_or & 7) { fx = f_now; nit = j + 1; done = true; break; }
+        const double f_new = s8[4], sa_now = s8[0], gg = s8[1], prnum = s8[2], maxd = s8[3];
+        const double Delta = 2.0 * (f_new - f_old) / (alpha * mu);   // :253
+        double total_grad;
+        if (Delta >= 0.0) {
+            success = true;
+            count_success++;
+            f_now = f_new;
+            double *t = x; x = xt; xt = t;                        // :266
+            total_grad = sa_now;
+        } else {
+            success = false;
+            f_now = f_old;
+            total_grad = sa_old;                                  // :277 g_now <- grad_old
+        }
+        fx_hist_h[j] = f_now;                                     // :284-285
+        dfx_hist_h[j] = total_grad;
+        if (success) {
+            if (fabs(alpha) * maxd <= x_tol && fabs(f_new - f_old) <= f_tol) {   // :306
+                fx = f_new; nit = j + 1; done = true; break;
+            }
+            f_old = f_new;
+            // :324-327 grad_old <- grad_new; (f_now, grad_new) = func(x).  x is the
+            // point just evaluated and E_cost is deterministic, so the re-evaluation
+            // returns (f_new, g_now) bit for bit: rotate the buffers instead.
+            double *t = gold; gold = gnew; gnew = gnow; gnow = t;
+            sa_old = sa_new; sa_new = sa_now;
+            func_eval++;
+            f_now = f_new;
+            if (fabs(gg) <= 1.0e-8) { fx = f_now; nit = j + 1; done = true; break; }   // :333
+        }
+        if (Delta < 0.25) beta = fmin(4.0 * beta, beta_max);      // :350-356
+        if (Delta > 0.75) beta = fmax(0.5 * beta, beta_min);
+        if (count_success == n) {                                 // :361-369
+            RC(R.direction(d, gnew, 0.0, 1));
+            RC(R.read(s8));
+            mu = s8[0]; kappa = s8[1];
+            count_success = 0;
+        } else if (success) {
+            const double gamma = fmax(prnum / mu, 0.0);
+            RC(R.direction(d, gnew, gamma, 0));
+            RC(R.read(s8));
+            mu = s8[0]; kappa = s8[1];
+        }
+    }
+    if (!done) fx = f_old;                                        // :379
+    CK(cudaMemcpyAsync(x_d, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    result_h[0] = fx;
+    result_h[1] = nit;
+    result_h[2] = func_eval;
+    result_h[3] = R.status_or;
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x_tol,
+                              double f_tol, double *fx_hist_h, double *dfx_hist_h,
+                              double *result_h) {
+    ARG(h && x_h, "mfvgp_scg_host: NULL argument");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const size_t nx = (size_t)h->D * (h->Nm + h->Ns);
+    CK(cudaMemcpyAsync(h->x_dev, x_h, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = mfvgp_scg(h, h->x_dev, max_it, x_tol, f_tol, fx_hist_h, dfx_hist_h, result_h,
+                   h->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(x_h, h->x_dev, nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MFVGP_OK;
+}

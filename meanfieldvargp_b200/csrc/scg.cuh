@@ -1,0 +1,138 @@
+// Device-resident vector kernels for the scaled conjugate gradient loop
+// (reference: SCG.minimize, src/numerical/scaled_cg.py:107-386).  Iterates,
+// gradients and search direction never leave the device; every dot product is
+// a fixed-order two-stage reduction so the accept/reject branches
+// (scaled_cg.py:194, :233, :254) are reproducible run to run.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mfvgp {
+
+constexpr int kRedBlock = 256;
+constexpr int kRedSlots = 4;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-level combine of kRedSlots values (slots 0..2 summed, slot 3 max'ed)
+// and store to part[blockIdx.x][*].
+__device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part) {
+    __shared__ double sh[kRedSlots][kRedBlock / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = warp_sum_d(v[i]);
+    v[3] = warp_max_d(v[3]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) sh[i][w] = v[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r[kRedSlots];
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) r[i] = sh[i][0];
+        for (int k = 1; k < kRedBlock / 32; ++k) {
+            r[0] += sh[0][k]; r[1] += sh[1][k]; r[2] += sh[2][k];
+            r[3] = fmax(r[3], sh[3][k]);
+        }
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) part[(int64_t)blockIdx.x * kRedSlots + i] = r[i];
+    }
+}
+
+// d = gamma*d - g (gamma = 0 and d arbitrary gives the restart d = -g);
+// partials: [0] mu = d.g, [1] kappa = d.d     (scaled_cg.py:192-200, 361-369)
+__global__ void __launch_bounds__(kRedBlock)
+scg_direction_kernel(double *d, const double *g, double gamma, int restart, int64_t n,
+                     double *part) {
+    double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double gi = g[i];
+        const double di = restart ? -gi : gamma * d[i] - gi;
+        d[i] = di;
+        v[0] = fma(di, gi, v[0]);
+        v[1] = fma(di, di, v[1]);
+    }
+    red_store(v, part);
+}
+
+// y = x + a*d                                   (scaled_cg.py:222, :242)
+__global__ void __launch_bounds__(kRedBlock)
+scg_axpy_kernel(double *y, const double *x, const double *d, double a, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = x[i] + a * d[i];
+}
+
+// partial [0] = d.(gp - g)                      (scaled_cg.py:228)
+__global__ void __launch_bounds__(kRedBlock)
+scg_theta_kernel(const double *d, const double *gp, const double *g, int64_t n, double *part) {
+    double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        v[0] = fma(d[i], gp[i] - g[i], v[0]);
+    red_store(v, part);
+}
+
+// After the trial evaluation at x + alpha d:
+// [0] sum |g_now| (:281), [1] g_now.g_now (:333), [2] g_now.(g_new - g_now)
+// (Polak-Ribiere numerator once g_now becomes grad_new and g_new grad_old,
+// :367), [3] max |d| (:306).
+__global__ void __launch_bounds__(kRedBlock)
+scg_stats_kernel(const double *g_now, const double *g_new, const double *d, int64_t n,
+                 double *part) {
+    double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = g_now[i];
+        v[0] += fabs(a);
+        v[1] = fma(a, a, v[1]);
+        v[2] = fma(a, g_new[i] - a, v[2]);
+        v[3] = fmax(v[3], fabs(d[i]));
+    }
+    red_store(v, part);
+}
+
+// Second stage: one block folds the per-block partials in a fixed order.
+__global__ void __launch_bounds__(kRedBlock)
+scg_fold_kernel(const double *part, int nblk, double *out) {
+    double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+        v[0] += part[(int64_t)b * kRedSlots + 0];
+        v[1] += part[(int64_t)b * kRedSlots + 1];
+        v[2] += part[(int64_t)b * kRedSlots + 2];
+        v[3] = fmax(v[3], part[(int64_t)b * kRedSlots + 3]);
+    }
+    __shared__ double sh[kRedSlots][kRedBlock / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = warp_sum_d(v[i]);
+    v[3] = warp_max_d(v[3]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) sh[i][w] = v[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r[kRedSlots];
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) r[i] = sh[i][0];
+        for (int k = 1; k < kRedBlock / 32; ++k) {
+            r[0] += sh[0][k]; r[1] += sh[1][k]; r[2] += sh[2][k];
+            r[3] = fmax(r[3], sh[3][k]);
+        }
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) out[i] = r[i];
+    }
+}
+
+}  // namespace mfvgp

@@ -1,0 +1,106 @@
+// Quadrature and interpolation tables for the Esde kernels.
+//
+// The reference integrates every interval with scipy.integrate.quad_vec
+// (free_energy.py:405-417): adaptive Gauss-Kronrod 21.  After its mandatory
+// first bisection the rule is GK21 on [ti,c] + GK21 on [c,tj] = 42 nodes.
+// The node/weight values are the published 21-point Kronrod / 10-point Gauss
+// constants (same table as scipy/_quad_vec.py::_quadrature_gk21).
+//
+// Interpolation: cubic Lagrange for m(t) on knots ti + k*dt/3, quadratic for
+// s(t) on knots ti + k*dt/2 (free_energy.py:386-398, symbolics.py:64-90).
+// In the local coordinate tau = (t - ti)/dt the basis values at the 42 nodes
+// are universal constants; d/dt = (1/dt) d/dtau.
+#pragma once
+
+namespace mfvgp {
+
+constexpr int kNodesPerPanel = 21;
+constexpr int kNodes = 42;          // two panels
+constexpr int kTabStride = 16;      // doubles per node in the device table
+
+// table columns
+constexpr int T_B3 = 0;    // [0..3]   cubic basis value
+constexpr int T_DB3 = 4;   // [4..7]   cubic basis d/dtau
+constexpr int T_B2 = 8;    // [8..10]  quadratic basis value
+constexpr int T_DB2 = 11;  // [11..13] quadratic basis d/dtau
+constexpr int T_V = 14;    // Kronrod weight v_r
+constexpr int T_C = 15;    // v_r - w_(r-1)/2 on odd r (Kronrod minus Gauss), else v_r
+
+// positive half of the Kronrod abscissae, descending (r = 0..9), then 0
+static const long double kGK21_xh[10] = {
+    0.995657163025808080735527280689003L, 0.973906528517171720077964012084452L,
+    0.930157491355708226001207180059508L, 0.865063366688984510732096688423493L,
+    0.780817726586416897063717578345042L, 0.679409568299024406234327365114874L,
+    0.562757134668604683339000099272694L, 0.433395394129247190799265943165784L,
+    0.294392862701460198131126603103866L, 0.148874338981631210884826001129720L};
+// Kronrod weights for r = 0..10 (symmetric)
+static const long double kGK21_vh[11] = {
+    0.011694638867371874278064396062192L, 0.032558162307964727478818972459390L,
+    0.054755896574351996031381300244580L, 0.075039674810919952767043140916190L,
+    0.093125454583697605535065465083366L, 0.109387158802297641899210590325805L,
+    0.123491976262065851077958109831074L, 0.134709217311473325928054001771707L,
+    0.142775938577060080797094273138717L, 0.147739104901338491374841515972068L,
+    0.149445554002916905664936468389821L};
+// Gauss-10 weights for i = 0..4 (symmetric); they sit on odd Kronrod nodes
+static const long double kGK21_wh[5] = {
+    0.066671344308688137593568809893332L, 0.149451349150580593145776339657697L,
+    0.219086362515982043995534934228163L, 0.269266719309996355091226921569469L,
+    0.295524224714752870173892994651338L};
+
+inline long double gk21_x(int r) {
+    return r < 10 ? kGK21_xh[r] : (r == 10 ? 0.0L : -kGK21_xh[20 - r]);
+}
+inline long double gk21_v(int r) { return r <= 10 ? kGK21_vh[r] : kGK21_vh[20 - r]; }
+inline long double gk21_w(int i) { return i < 5 ? kGK21_wh[i] : kGK21_wh[9 - i]; }
+
+// Lagrange basis k of order K-1 on equispaced knots j/(K-1) at tau.
+inline void lagrange_unit(int K, int k, long double tau, long double *val,
+                          long double *der) {
+    long double v = 1.0L, d = 0.0L;
+    const long double step = 1.0L / (K - 1);
+    for (int l = 0; l < K; ++l)
+        if (l != k) v *= (tau - l * step) / ((k - l) * step);
+    for (int j = 0; j < K; ++j) {
+        if (j == k) continue;
+        long double term = 1.0L / ((k - j) * step);
+        for (int l = 0; l < K; ++l)
+            if (l != k && l != j) term *= (tau - l * step) / ((k - l) * step);
+        d += term;
+    }
+    *val = v;
+    *der = d;
+}
+
+// Fills one row of the table for a node at local coordinate tau with
+// Kronrod weight v and Kronrod-minus-Gauss weight c.
+inline void fill_row(double *row, long double tau, long double v, long double c) {
+    for (int k = 0; k < 4; ++k) {
+        long double b, d;
+        lagrange_unit(4, k, tau, &b, &d);
+        row[T_B3 + k] = (double)b;
+        row[T_DB3 + k] = (double)d;
+    }
+    for (int k = 0; k < 3; ++k) {
+        long double b, d;
+        lagrange_unit(3, k, tau, &b, &d);
+        row[T_B2 + k] = (double)b;
+        row[T_DB2 + k] = (double)d;
+    }
+    row[T_V] = (double)v;
+    row[T_C] = (double)c;
+}
+
+// 42-node table of the fixed rule: panel p in {0,1}, node r in 0..20,
+// tau = 0.25 + 0.5 p + 0.25 x_r ; integral over the interval of length dt is
+// (dt/4) * sum_q v_q f(t_q).
+inline void build_fixed_table(double *tab /*[42][16]*/) {
+    for (int p = 0; p < 2; ++p)
+        for (int r = 0; r < kNodesPerPanel; ++r) {
+            long double tau = 0.25L + 0.5L * p + 0.25L * gk21_x(r);
+            long double v = gk21_v(r);
+            long double c = (r & 1) ? v - gk21_w((r - 1) / 2) : v;
+            fill_row(tab + (p * kNodesPerPanel + r) * kTabStride, tau, v, c);
+        }
+}
+
+}  // namespace mfvgp

@@ -1,0 +1,325 @@
+"""
+Drop-in for the reference's ``FreeEnergy`` (src/var_bayes/free_energy.py:19-864)
+whose hot path -- ``E_sde`` (:461-565), ``E_kl0`` (:281-336), ``E_obs``
+(:567-649), ``E_cost`` (:651-751) and the SCG loop behind ``find_minimum``
+(:753-862) -- runs as hand-written FP64 CUDA for sm_100a behind the C ABI of
+``include/mfvgp.h``.
+
+Same constructor, same method names, argument meaning, return shapes and
+exceptions as the reference.  ``n_jobs`` is accepted and ignored (the joblib
+fan-out of free_energy.py:500-508 is one kernel launch here).  numpy in ->
+numpy out (copies inside the call); CUDA ``torch.float64`` tensors in ->
+tensors out (zero copy, caller's current stream).
+
+There is no CPU fallback: without the built library or a CUDA device every
+compute call raises ``MfvgpError``.
+"""
+import ctypes
+from time import perf_counter
+
+import numpy as np
+
+from . import _lib
+from .systems import system_of
+
+
+def _is_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class FreeEnergy(object):
+
+    MAX_CPUs = 1      # kept for interface parity (free_energy.py:22); unused
+
+    def __init__(self, sde, mu0, tau0, obs_times, obs_values, obs_noise,
+                 obs_mask=None, n_jobs=1, device=0, intervals=None):
+        """
+        Arguments as free_energy.py:30-55.  Extra keyword arguments:
+        ``device`` (CUDA ordinal) and ``intervals=(n_begin, n_end)``, the
+        shard of the L = M-1 integrated intervals this object evaluates
+        (multi-GPU; default all).
+        """
+        self.system = system_of(sde)
+        self._mu0 = np.asarray(mu0, dtype=float)
+        self._tau0 = np.asarray(tau0, dtype=float)
+        self.theta = np.atleast_1d(np.asarray(sde.theta, dtype=float))
+        self.sigma = np.atleast_1d(np.asarray(sde.sigma, dtype=float))
+        self.tk = sde.time_window
+        if not np.all(np.diff(self.tk) > 0.0):                   # :83-85
+            raise ValueError(f" {self.__class__.__name__}:"
+                             f" Time window [t0, tf] is not increasing.")
+        self.obs_times = np.asarray(obs_times, dtype=float)
+        self.obs_noise = np.asarray(obs_noise, dtype=float)
+        self.obs_values = np.asarray(obs_values, dtype=float)
+        self.dim_D = self.sigma.size
+        if obs_mask is None:                                     # :98-127
+            self.obs_mask = self.dim_D * [True]
+        else:
+            if len(obs_mask) != self.dim_D:
+                raise RuntimeError(f" {self.__class__.__name__}:"
+                                   f" Observation mask mismatch {len(obs_mask)} != {self.dim_D}")
+            if all(isinstance(item, bool) for item in obs_mask):
+                self.obs_mask = obs_mask
+            else:
+                raise ValueError(f" {self.__class__.__name__}:"
+                                 f" Observation mask contains non-boolean values!")
+            if sum(self.obs_mask) == 0:
+                raise RuntimeError(f" {self.__class__.__name__}:"
+                                   f" Observation mask contains only False values.")
+        self.n_jobs = int(n_jobs)                                # accepted, ignored
+        self.dim_d = 1 if self.obs_values.ndim in (0, 1) else self.obs_values.shape[1]
+        self.num_M = len(obs_times)
+        if self.dim_d > self.dim_D:                              # :153-157
+            raise RuntimeError(f" {self.__class__.__name__}: System dimensions."
+                               f" {self.dim_d} should be less than, or equal,"
+                               f" to {self.dim_D}.")
+        if self.num_M != self.obs_values.shape[0]:               # :160-164
+            raise RuntimeError(f" {self.__class__.__name__}:  System dimensions."
+                               f" Observation times {self.num_M} should be equal"
+                               f" to observation values {self.obs_values.shape[0]}.")
+        if sum(self.obs_mask) != self.dim_d:
+            raise RuntimeError(f" {self.__class__.__name__}: Observation mask selects"
+                               f" {sum(self.obs_mask)} dimensions, observations have"
+                               f" {self.dim_d}.")
+        self.num_mp = self.dim_D * (3 * self.num_M + 4)          # :168
+        self.num_sp = self.dim_D * (2 * self.num_M + 3)
+        self.num_L = self.num_M - 1                              # :490
+        self.ikm = [3 * i for i in range(1, self.num_M + 1)]
+        self.iks = [2 * i for i in range(1, self.num_M + 1)]
+
+        # ---- device side ------------------------------------------------
+        self._lib = _lib.require_device()
+        self.device = int(device)
+        n0, n1 = (0, -1) if intervals is None else intervals
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.mfvgp_create(ctypes.byref(self._h), _lib.SYS_ID[self.system],
+                                          self.dim_D, self.num_M, self.dim_d, self.device,
+                                          int(n0), int(n1)), "mfvgp_create")
+        self.intervals = (int(n0), self.num_L if n1 < 0 else int(n1))
+        self._sde_sent = None
+        self._prior_sent = None
+        self._push_obs()
+        self._sync_params()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.mfvgp_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- parameter upload (re-read every call: the reference's setters at
+    # free_energy.py:191-279 may replace them between calls) -----------------
+    def _push_obs(self):
+        t = _f64(self.obs_times)
+        y = _f64(self.obs_values).reshape(self.num_M, self.dim_d)
+        r = _f64(np.atleast_1d(self.obs_noise))
+        if r.size == 1 and self.dim_d > 1:
+            r = np.full(self.dim_d, float(r[0]))
+        mask = np.ascontiguousarray(np.asarray(self.obs_mask, dtype=np.uint8))
+        _lib.check(self._lib.mfvgp_set_obs(self._h, _ptr(t), _ptr(y), _ptr(r), _ptr(mask)),
+                   "mfvgp_set_obs")
+
+    def _sync_params(self):
+        sde_key = (self.sigma.tobytes(), self.theta.tobytes())
+        if sde_key != self._sde_sent:
+            s, t = _f64(self.sigma), _f64(self.theta)
+            _lib.check(self._lib.mfvgp_set_sde(self._h, _ptr(s), _ptr(t), t.size),
+                       "mfvgp_set_sde")
+            self._sde_sent = sde_key
+        mu0 = _f64(np.broadcast_to(self._mu0, (self.dim_D,)))
+        tau0 = _f64(np.broadcast_to(self._tau0, (self.dim_D,)))
+        prior_key = (mu0.tobytes(), tau0.tobytes())
+        if prior_key != self._prior_sent:
+            _lib.check(self._lib.mfvgp_set_prior(self._h, _ptr(mu0), _ptr(tau0)),
+                       "mfvgp_set_prior")
+            self._prior_sent = prior_key
+
+    # ---- accessors, free_energy.py:181-279 ---------------------------------
+    @property
+    def prior_mu0(self):
+        return self._mu0
+
+    @prior_mu0.setter
+    def prior_mu0(self, new_value):
+        self._mu0 = np.asarray(new_value, dtype=float)
+
+    @property
+    def prior_tau0(self):
+        return self._tau0
+
+    @prior_tau0.setter
+    def prior_tau0(self, new_value):
+        self._tau0 = np.asarray(new_value, dtype=float)
+
+    @property
+    def sde_theta(self):
+        return self.theta
+
+    @sde_theta.setter
+    def sde_theta(self, new_value):
+        self.theta = np.atleast_1d(np.asarray(new_value, dtype=float))
+
+    @property
+    def sde_sigma(self):
+        return self.sigma
+
+    @sde_sigma.setter
+    def sde_sigma(self, new_value):
+        self.sigma = np.atleast_1d(np.asarray(new_value, dtype=float))
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.mfvgp_launch_count(self._h))
+
+    # ---- error convention ----------------------------------------------------
+    def _raise_on_status(self, status, E0=None, Esde=None, Eobs=None):
+        name = self.__class__.__name__
+        if status & _lib.ST_E0:                                   # :313-316
+            raise RuntimeError(f" {name}: E0 is not a finite number: {E0}")
+        if status & _lib.ST_ESDE:                                 # :547-550
+            raise RuntimeError(f" {name}: Esde is not a finite number: {Esde}")
+        if status & _lib.ST_EOBS:                                 # :615-618
+            raise RuntimeError(f" {name}: Eobs is not a finite number: {Eobs}")
+
+    # ---- E_sde, free_energy.py:461-565 ---------------------------------------
+    def E_sde(self, mean_pts, vars_pts, output_gradients=True):
+        self._sync_params()
+        D, L = self.dim_D, self.num_L
+        want = 1 if output_gradients else 0
+        if _is_tensor(mean_pts):
+            import torch
+            mp = mean_pts.contiguous()
+            sp = vars_pts.contiguous()
+            out = torch.empty(1, dtype=torch.float64, device=mp.device)
+            st = torch.empty(1, dtype=torch.int32, device=mp.device)
+            dm = torch.empty((L, D, 4), dtype=torch.float64, device=mp.device) if want else None
+            ds = torch.empty((L, D, 3), dtype=torch.float64, device=mp.device) if want else None
+            stream = torch.cuda.current_stream(mp.device).cuda_stream
+            _lib.check(self._lib.mfvgp_esde(
+                self._h, mp.data_ptr(), mp.shape[1], sp.data_ptr(), sp.shape[1], want,
+                out.data_ptr(), dm.data_ptr() if want else None,
+                ds.data_ptr() if want else None, st.data_ptr(), stream), "mfvgp_esde")
+            self.last_status = int(st.item())
+            Esde = out[0]
+            self._raise_on_status(self.last_status, Esde=float(Esde))
+            return Esde, dm, ds
+        mp = _f64(mean_pts).reshape(D, 3 * self.num_M + 4)
+        sp = _f64(vars_pts).reshape(D, 2 * self.num_M + 3)
+        Esde = ctypes.c_double()
+        status = ctypes.c_int32()
+        dm = np.empty((L, D, 4)) if want else None
+        ds = np.empty((L, D, 3)) if want else None
+        _lib.check(self._lib.mfvgp_esde_host(
+            self._h, _ptr(mp), _ptr(sp), want, ctypes.byref(Esde),
+            _ptr(dm) if want else None, _ptr(ds) if want else None,
+            ctypes.byref(status)), "mfvgp_esde_host")
+        self.last_status = status.value
+        self._raise_on_status(status.value, Esde=Esde.value)
+        if not output_gradients:
+            return Esde.value, None, None
+        return Esde.value, dm, ds
+
+    # ---- E_cost, free_energy.py:651-751 --------------------------------------
+    def E_cost(self, x, output_gradients=True):
+        self._sync_params()
+        n = self.num_mp + self.num_sp
+        want = 1 if output_gradients else 0
+        if _is_tensor(x):
+            import torch
+            xd = x.contiguous()
+            if xd.numel() != n:
+                raise ValueError(f"E_cost: x has {xd.numel()} entries, expected {n}")
+            out = torch.empty(4, dtype=torch.float64, device=xd.device)
+            st = torch.empty(1, dtype=torch.int32, device=xd.device)
+            grad = torch.empty(n, dtype=torch.float64, device=xd.device) if want else None
+            stream = torch.cuda.current_stream(xd.device).cuda_stream
+            _lib.check(self._lib.mfvgp_ecost(self._h, xd.data_ptr(), want, out.data_ptr(),
+                                             grad.data_ptr() if want else None,
+                                             st.data_ptr(), stream), "mfvgp_ecost")
+            self.last_out = out
+            self.last_status_tensor = st
+            return (out[0], grad) if output_gradients else out[0]
+        xh = _f64(x).ravel()
+        if xh.size != n:
+            raise ValueError(f"E_cost: x has {xh.size} entries, expected {n}")
+        out = np.empty(4)
+        status = ctypes.c_int32()
+        grad = np.empty(n) if want else None
+        _lib.check(self._lib.mfvgp_ecost_host(self._h, _ptr(xh), want, _ptr(out),
+                                              _ptr(grad) if want else None,
+                                              ctypes.byref(status)), "mfvgp_ecost_host")
+        self.last_status = status.value
+        self.last_terms = {"F": out[0], "E0": out[1], "Esde": out[2], "Eobs": out[3]}
+        self._raise_on_status(status.value, E0=out[1], Esde=out[2], Eobs=out[3])
+        if not output_gradients:
+            return float(out[0])
+        return float(out[0]), grad
+
+    # ---- find_minimum, free_energy.py:753-862 --------------------------------
+    def find_minimum(self, x0, max_iter=100, x_tol=1.0e-5, f_tol=1.0e-5,
+                     check_gradients=False, verbose=False):
+        self._sync_params()
+
+        def _grad_check(tag, xin):
+            from scipy.optimize import check_grad
+            print(f"Grad-Check |{tag}| minimization ...")
+            err = check_grad(lambda v: self.E_cost(v, output_gradients=False),
+                             lambda v: self.E_cost(v)[1], np.array(xin, dtype=float))
+            print(f" > Error = {err:.3E}")
+            print("------------------------------------\n")
+
+        tensor_in = _is_tensor(x0)
+        if check_gradients:
+            _grad_check("BEFORE", x0.detach().cpu().numpy() if tensor_in else x0)
+        max_iter = max(int(max_iter), 10)                          # :815-817
+        x_tol = max(float(x_tol), 1.0e-20)
+        f_tol = max(float(f_tol), 1.0e-20)
+        fx_hist = np.zeros(max_iter)
+        dfx_hist = np.zeros(max_iter)
+        result = np.zeros(4)
+        n = self.num_mp + self.num_sp
+        if verbose:
+            print("SCG: Optimization started ...")
+        time_t0 = perf_counter()
+        if tensor_in:
+            import torch
+            opt_x = x0.detach().clone().contiguous().reshape(-1)
+            if opt_x.numel() != n:
+                raise ValueError(f"find_minimum: x0 has {opt_x.numel()} entries, expected {n}")
+            stream = torch.cuda.current_stream(opt_x.device).cuda_stream
+            _lib.check(self._lib.mfvgp_scg(self._h, opt_x.data_ptr(), max_iter, x_tol, f_tol,
+                                           _ptr(fx_hist), _ptr(dfx_hist), _ptr(result),
+                                           stream), "mfvgp_scg")
+        else:
+            opt_x = np.array(x0, dtype=np.float64).ravel()
+            if opt_x.size != n:
+                raise ValueError(f"find_minimum: x0 has {opt_x.size} entries, expected {n}")
+            _lib.check(self._lib.mfvgp_scg_host(self._h, _ptr(opt_x), max_iter, x_tol, f_tol,
+                                                _ptr(fx_hist), _ptr(dfx_hist), _ptr(result)),
+                       "mfvgp_scg_host")
+        time_tf = perf_counter()
+        opt_fx, nit, func_eval, status = (float(result[0]), int(result[1]),
+                                          int(result[2]), int(result[3]))
+        self.last_status = status
+        self._raise_on_status(status, E0=opt_fx, Esde=opt_fx, Eobs=opt_fx)
+        stats = {"nit": nit, "fx": fx_hist, "dfx": dfx_hist, "func_eval": func_eval}
+        if verbose:
+            for j in range(0, nit, 50):                           # scaled_cg.py:288-296
+                print(f"It= {j:>5}: F(x)= {fx_hist[j]:.3E} -:- "
+                      f"Sum(|Gradients|)= {dfx_hist[j]:.3E}")
+        print(f"Elapsed time [{nit}]: {(time_tf - time_t0):.2f} seconds.\n")
+        if check_gradients:
+            _grad_check("AFTER", opt_x.detach().cpu().numpy() if tensor_in else opt_x)
+        print("Done!")
+        return opt_x, opt_fx, stats

@@ -1,0 +1,147 @@
+"""
+Parameter holders for the four drift plug-ins, with the constructor signatures
+of the reference's system classes:
+
+  DoubleWell(sigma, theta, r_seed)          double_well.py:17-38
+  OrnsteinUhlenbeck(sigma, theta, r_seed)   ornstein_uhlenbeck.py:15-36
+  Lorenz63(sigma, theta, r_seed)            lorenz_63.py:42-90
+  Lorenz96(sigma, theta, dim_D, r_seed)     lorenz_96.py:42-101
+
+Only what the free-energy path reads is kept (``theta``, ``sigma``,
+``time_window``; stochastic_process.py:58-182).  The energy / gradient
+expressions themselves live in the CUDA kernels (csrc/drift.cuh,
+csrc/kernels.cuh); trajectory simulation is out of scope.
+A reference system object can be passed to ``FreeEnergy`` directly: the
+kernel is selected from the class name.
+"""
+import numpy as np
+
+
+class StochasticProcess(object):
+    system = None
+
+    def __init__(self, r_seed=None):
+        self._rng = np.random.default_rng(r_seed)
+        self.xt = None
+        self.tk = None
+        self._theta = None
+        self._sigma = None
+
+    # stochastic_process.py:58-84
+    @property
+    def theta(self):
+        if self._theta is None:
+            raise NotImplementedError(f" {self.__class__.__name__}:"
+                                      f" Drift theta parameter(s) is not set yet.")
+        return np.atleast_1d(self._theta)
+
+    @theta.setter
+    def theta(self, new_value):
+        self._theta = np.asarray(new_value, dtype=float)
+
+    # stochastic_process.py:86-118
+    @property
+    def sigma(self):
+        if self._sigma is None:
+            raise NotImplementedError(f" {self.__class__.__name__}:"
+                                      f" SDE noise parameters have not set yet.")
+        return np.atleast_1d(self._sigma)
+
+    @sigma.setter
+    def sigma(self, new_value):
+        new_value = np.asarray(new_value, dtype=float)
+        if np.any(new_value <= 0.0):
+            raise ValueError(f" {self.__class__.__name__}:"
+                             f" SDE noise vector {new_value} is not positive.")
+        self._sigma = new_value
+
+    @property
+    def inverse_sigma(self):
+        return 1.0 / self.sigma
+
+    # stochastic_process.py:158-182
+    @property
+    def time_window(self):
+        if self.tk is None:
+            raise NotImplementedError(f" {self.__class__.__name__}:"
+                                      f" Time window has not been created.")
+        return self.tk
+
+    @time_window.setter
+    def time_window(self, new_value):
+        self.tk = new_value
+
+    @property
+    def rng(self):
+        return self._rng
+
+
+class DoubleWell(StochasticProcess):
+    system = "DW"
+
+    def __init__(self, sigma, theta, r_seed=None):
+        super().__init__(r_seed=r_seed)
+        self.sigma = sigma
+        self.theta = theta
+
+
+class OrnsteinUhlenbeck(StochasticProcess):
+    system = "OU"
+
+    def __init__(self, sigma, theta, r_seed=None):
+        super().__init__(r_seed=r_seed)
+        self.sigma = sigma
+        self.theta = theta
+
+
+def _diag_sigma(cls_name, sigma, dim):
+    sigma = np.asarray(sigma, dtype=float)
+    if sigma.ndim == 0:
+        sigma = sigma * np.ones(dim)
+    elif sigma.ndim == 2:
+        sigma = sigma.diagonal()
+    elif sigma.ndim != 1:
+        raise ValueError(f" {cls_name}: Wrong input dimensions: {sigma.ndim}")
+    if len(sigma) != dim:
+        raise ValueError(f" {cls_name}: Wrong matrix dimensions: {sigma.shape}")
+    return sigma
+
+
+class Lorenz63(StochasticProcess):
+    system = "L63"
+
+    def __init__(self, sigma, theta, r_seed=None):
+        super().__init__(r_seed=r_seed)
+        self.sigma = _diag_sigma(self.__class__.__name__, sigma, 3)
+        theta = np.asarray(theta, dtype=float)
+        if theta.size != 3:                       # lorenz_63.py:84-90
+            raise RuntimeError(f" {self.__class__.__name__}: Drift vector"
+                               f" {theta} is not [3 x 1].")
+        self.theta = theta
+
+
+class Lorenz96(StochasticProcess):
+    system = "L96"
+
+    def __init__(self, sigma, theta, dim_D=40, r_seed=None):
+        super().__init__(r_seed=r_seed)
+        if dim_D < 4:                             # lorenz_96.py:60-63
+            raise ValueError(f" {self.__class__.__name__}:"
+                             f" Insufficient state vector dimensions: {dim_D}")
+        self.dim_D = int(dim_D)
+        self.sigma = _diag_sigma(self.__class__.__name__, sigma, self.dim_D)
+        self.theta = np.asarray(theta, dtype=float)
+
+
+_BY_CLASS_NAME = {"DoubleWell": "DW", "OrnsteinUhlenbeck": "OU",
+                  "Lorenz63": "L63", "Lorenz96": "L96"}
+
+
+def system_of(sde):
+    """Kernel family for an sde object (ours or the reference's own class)."""
+    name = getattr(sde, "system", None) or _BY_CLASS_NAME.get(type(sde).__name__)
+    if name is None:
+        raise NotImplementedError(
+            f"no CUDA drift plug-in for {type(sde).__name__}; supported: "
+            f"{sorted(_BY_CLASS_NAME)}")
+    return name

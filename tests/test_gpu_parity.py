@@ -1,0 +1,105 @@
+"""
+GPU parity tests: the CUDA path (through the C ABI and the FreeEnergy drop-in)
+against (a) the committed golden vectors produced by the unmodified reference
+and (b) the numpy oracle on the same seeded inputs.
+
+Tolerance: BASELINE.json north_star -- relative 1e-10 in FP64.
+"""
+import numpy as np
+import pytest
+
+from helpers import (EVAL_CASES, load_golden, make_free_energy, make_oracle, rel_err,
+                     synthetic_l96)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1.0e-10
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_ecost_matches_reference_golden(name):
+    g = load_golden("eval", name)
+    fe = make_free_energy(g)
+    F, grad = fe.E_cost(g["x0"])
+    assert abs(F - g["F"]) <= RTOL * abs(g["F"])
+    assert rel_err(grad, g["grad"]) <= RTOL
+    assert abs(fe.last_terms["E0"] - g["E0"]) <= RTOL * abs(g["F"])
+    assert abs(fe.last_terms["Esde"] - g["Esde"]) <= RTOL * abs(g["F"])
+    assert abs(fe.last_terms["Eobs"] - g["Eobs"]) <= RTOL * abs(g["F"])
+    # free_energy.py:707 -- value-only call
+    assert abs(fe.E_cost(g["x0"], output_gradients=False) - g["F_only"]) <= RTOL * abs(g["F"])
+    assert fe.kernel_launches > 0
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_esde_matches_reference_golden(name):
+    g = load_golden("eval", name)
+    fe = make_free_energy(g)
+    D, M = fe.dim_D, fe.num_M
+    mp = g["x0"][:fe.num_mp].reshape(D, 3 * M + 4)
+    sp = np.exp(g["x0"][fe.num_mp:].reshape(D, 2 * M + 3))
+    Esde, dm, ds = fe.E_sde(mp, sp)
+    assert dm.shape == (M - 1, D, 4) and ds.shape == (M - 1, D, 3)
+    assert abs(Esde - g["Esde"]) <= RTOL * abs(g["Esde"])
+    assert rel_err(dm, g["dEsde_dm"]) <= RTOL
+    assert rel_err(ds, g["dEsde_ds"]) <= RTOL
+    E_only, none_m, none_s = fe.E_sde(mp, sp, output_gradients=False)
+    assert none_m is None and none_s is None
+    assert abs(E_only - g["Esde"]) <= RTOL * abs(g["Esde"])
+
+
+def test_deterministic_bitwise():
+    g = load_golden("eval", "L96_40")
+    fe = make_free_energy(g)
+    F1, g1 = fe.E_cost(g["x0"])
+    F2, g2 = fe.E_cost(g["x0"])
+    assert F1 == F2 and np.array_equal(g1, g2)
+
+
+@pytest.mark.parametrize("D,M", [(4, 2), (5, 3), (26, 4), (27, 5), (58, 3), (59, 6),
+                                 (123, 4), (300, 9)])
+def test_l96_matches_oracle_random_sizes(D, M):
+    """Ragged sizes around the dim-tile edges (TE-6 = 26, 58, 122)."""
+    g = synthetic_l96(D, M, seed=100 + D)
+    fe = make_free_energy(g)
+    F, grad = fe.E_cost(g["x0"])
+    Fo, go = make_oracle(g, adaptive=False).E_cost(g["x0"])
+    assert abs(F - Fo) <= RTOL * abs(Fo)
+    assert rel_err(grad, go) <= RTOL
+
+
+def test_tensor_api_zero_copy():
+    import torch
+    g = load_golden("eval", "L96_40")
+    fe = make_free_energy(g)
+    x = torch.tensor(g["x0"], dtype=torch.float64, device="cuda")
+    F, grad = fe.E_cost(x)
+    assert grad.is_cuda and grad.dtype == torch.float64
+    assert abs(F.item() - g["F"]) <= RTOL * abs(g["F"])
+    assert rel_err(grad.cpu().numpy(), g["grad"]) <= RTOL
+
+
+def test_linearity_in_obs_noise_full_size():
+    """
+    Size-independent property at the north-star size (L96 D=500, M=16):
+    Esde does not depend on the observation model, E_obs does.
+    """
+    g = synthetic_l96(500, 16, seed=5)
+    fe1 = make_free_energy(g)
+    F1, _ = fe1.E_cost(g["x0"])
+    t1 = dict(fe1.last_terms)
+    g2 = dict(g)
+    g2["obs_values"] = g["obs_values"] + 1.0
+    fe2 = make_free_energy(g2)
+    fe2.E_cost(g["x0"])
+    t2 = fe2.last_terms
+    assert t1["Esde"] == t2["Esde"] and t1["E0"] == t2["E0"]
+    assert t1["Eobs"] != t2["Eobs"]
+
+
+def test_nonfinite_raises_like_reference():
+    g = load_golden("eval", "L96_8")
+    fe = make_free_energy(g)
+    x = g["x0"].copy()
+    x[3] = np.nan
+    with pytest.raises(RuntimeError, match="is not a finite number"):
+        fe.E_cost(x)
