@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""
+bench.py -- free-energy + gradient evaluations per second (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one ``E_cost(x)`` with gradient (free_energy.py:651-751) on the
+north-star configuration: Lorenz '96, D=500, d=125 partial observations,
+M=16 observation times (examples/example_500D.ipynb), synthetic state
+(SURVEY.md 8d).  Rank 0 prints ONE JSON line:
+
+  value      evals/s with x resident in HBM (CUDA events, L2 flushed between steps)
+  e2e        evals/s through FreeEnergy.E_cost on HOST numpy buffers (pinned x;
+             H2D of x and D2H of F+gradient inside the timed region)
+  roofline   the dominant kernel (esde_l96_kernel) against the FP64 pipe
+             (DFMA micro-benchmark measured in this run) and HBM
+  cpu_baseline  the numpy/scipy oracle port on the host cores (bounded sample)
+  scg        device SCG iterations per second on the same configuration
+  large      Lorenz '96 D=8192, M=4097 (L=4096 intervals) long horizon: at
+             N ranks the intervals are sharded (strong scaling); this is the
+             configuration on which the roofline fraction is meaningful.
+
+With N > 1 (torchrun, one rank per GPU) the D=500 evaluation is far below one
+wave of one GPU, so it does not shard: ``value`` is N independent replicas
+("replicas only"); the sharded multi-GPU path is the ``large`` entry.
+
+``--impl reference`` times the CPU implementation of the same path (the oracle
+port: the reference itself is Python under /root/reference and cannot travel
+to the GPU box) with all host threads it can use.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+FLOP_PER_CELL = 4620.0      # 110 FLOP/(dim,node) x 42 nodes
+BYTE_PER_CELL = 96.0        # 40 B read + 56 B written per cell
+METRIC = "free-energy+gradient evals/sec (L96 D=500)"
+WORKLOAD = "L96 D=500 d=125 M=16 (example_500D.ipynb), synthetic state seed 8192"
+
+
+def north_star_problem():
+    from helpers import synthetic_l96
+    return synthetic_l96(500, 16, seed=8192)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                   "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def time_steps(torch, fn, steps, warmup, flush_buf):
+    """CUDA-event time of ``steps`` calls of fn, L2 flushed before each."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(steps)]
+    for e0, e1 in ev:
+        if flush_buf is not None:
+            flush_buf.zero_()
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    return sum(e0.elapsed_time(e1) for e0, e1 in ev)        # ms
+
+
+def kernel_time(fe, lib, fn, reps):
+    """Average duration of the Esde kernel (events recorded inside the library)."""
+    tot, cnt = ctypes.c_double(), ctypes.c_int64()
+    lib.mfvgp_timing(fe._h, 1, ctypes.byref(tot), ctypes.byref(cnt))
+    for _ in range(reps):
+        fn()
+    lib.mfvgp_timing(fe._h, 0, ctypes.byref(tot), ctypes.byref(cnt))
+    return tot.value / max(cnt.value, 1), cnt.value
+
+
+def roofline(D, L, kernel_ms, fp64_peak_tf, hbm_peak_gbs, traffic=None):
+    cells = float(D) * L
+    tf = FLOP_PER_CELL * cells / (kernel_ms * 1e-3) * 1e-12
+    gbs = BYTE_PER_CELL * cells / (kernel_ms * 1e-3) * 1e-9
+    return {"bound": "fp64", "achieved": tf, "peak": fp64_peak_tf, "unit": "TFLOP/s",
+            "frac": tf / fp64_peak_tf, "traffic": traffic,
+            "peak_source": "DFMA micro-benchmark measured in this run (mfvgp_fp64_peak); "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "kernel": "esde_l96_kernel", "kernel_ms": kernel_ms,
+            "algorithmic_flop_per_launch": FLOP_PER_CELL * cells,
+            "algorithmic_bytes_per_launch": BYTE_PER_CELL * cells,
+            "hbm": {"achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s",
+                    "frac": gbs / hbm_peak_gbs, "peak_source": "MEASURED_PEAKS.json hbm_gbs"}}
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.is_file():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def cpu_baseline(g, budget_s=12.0, n_jobs=1):
+    """Oracle port (numpy + scipy.quad_vec, adaptive like the reference)."""
+    from helpers import make_oracle
+    o = make_oracle(g, adaptive=True)
+    o.n_jobs = n_jobs
+    o.E_cost(g["x0"])                     # warm-up (worker spawn)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        o.E_cost(g["x0"])
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 50:
+            break
+    wall = time.perf_counter() - t0
+    return {"value": n / wall, "unit": "evals/s", "cores": n_jobs, "kind": "port",
+            "sample": f"{n} E_cost evaluations of the same workload "
+                      f"(oracle/mfvgp_oracle.py, scipy.quad_vec adaptive GK21, "
+                      f"n_jobs={n_jobs}) in {wall:.1f} s"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g = north_star_problem()
+    cores = os.cpu_count() or 1
+    from helpers import make_oracle
+    o = make_oracle(g, adaptive=True)
+    o.n_jobs = cores
+    for _ in range(max(args.warmup, 1)):
+        o.E_cost(g["x0"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.E_cost(g["x0"])
+    wall = time.perf_counter() - t0
+    val = args.steps / wall
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} E_cost evaluations per run, joblib over "
+                                       f"the 15 intervals, n_jobs={cores}"},
+            "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "note": "oracle port of the reference's CPU path (numpy + scipy.quad_vec); the "
+                    "reference itself (Python under /root/reference) measured 5.59 s/eval "
+                    "with n_jobs=8 on the build container (BASELINE.md)"}
+    print(json.dumps(line), flush=True)
+
+
+def run_large(torch, dist, rank, world, steps, warmup, fp64_peak_tf, hbm_gbs, D=8192, M=4097):
+    """L96 D=8192 long horizon; intervals sharded over the ranks."""
+    from meanfieldvargp_b200 import _lib
+    from meanfieldvargp_b200.parallel import ShardedFreeEnergy
+    from helpers import synthetic_l96_device
+    g = synthetic_l96_device(torch, D, M, seed=8192)
+    fe = ShardedFreeEnergy(g, rank, world)
+    x = g["x0"]
+    L = M - 1
+
+    def step():
+        fe.E_cost(x)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()          # working set (1.3 GB x + 1.3 GB grad + 1.9 GB workspace) >> L2
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / steps
+    lib = _lib.load()
+    k_ms, _ = kernel_time(fe.local, lib, step, 3)
+    Lloc = fe.local.intervals[1] - fe.local.intervals[0]
+    out = {"workload": f"L96 D={D} d={D // 4} M={M} (L={L} intervals), synthetic seed 8192",
+           "value": 1e3 / ms_step, "unit": "evals/s", "ms_per_eval": ms_step,
+           "scaling": "strong", "parallelism": f"time-intervals sharded x{world}",
+           "l2": "inputs larger than L2",
+           "roofline": roofline(D, Lloc, k_ms, fp64_peak_tf, hbm_gbs),
+           "job_tflops_algorithmic": FLOP_PER_CELL * D * L / (ms_step * 1e-3) * 1e-12}
+    del fe, g, x
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-large", action="store_true", help="skip the D=8192 entry")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--large-steps", type=int, default=10)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import meanfieldvargp_b200 as mf
+    from meanfieldvargp_b200 import _lib
+    from helpers import make_free_energy
+    lib = _lib.require_device()
+
+    tf = ctypes.c_double()
+    _lib.check(lib.mfvgp_fp64_peak(local_rank, ctypes.byref(tf)), "mfvgp_fp64_peak")
+    fp64_peak_tf = tf.value
+    hbm_gbs, hbm_src = hbm_peak()
+
+    g = north_star_problem()
+    D, M = 500, 16
+    L = M - 1
+    fe = make_free_energy(g, device=local_rank)
+    n = g["x0"].size
+    x_dev = torch.tensor(g["x0"], dtype=torch.float64, device="cuda")
+    x_pin = torch.tensor(g["x0"], dtype=torch.float64).pin_memory()
+    x_host = x_pin.numpy()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    # ---- value: device-resident evaluations ---------------------------------
+    def step_dev():
+        fe.E_cost(x_dev)
+
+    clocks = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = fe.kernel_launches
+    for _ in range(args.warmup):
+        step_dev()
+    launches_w = fe.kernel_launches
+    clocks.start()
+    ms_total = time_steps(torch, step_dev, args.steps, 0, flush)
+    launches = fe.kernel_launches - launches_w
+    clock_info = clocks.stop()
+    tms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = tms.item() / args.steps
+    value = world * 1e3 / ms_step          # N independent replicas
+
+    # ---- e2e: host buffers through the public API ----------------------------
+    for _ in range(args.warmup):
+        fe.E_cost(x_host)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        F_h, grad_h = fe.E_cost(x_host)
+    wall = time.perf_counter() - t0
+    twall = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(twall, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * args.steps / twall.item(), "unit": "evals/s",
+           "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 8 + 36),
+           "api": "FreeEnergy.E_cost(numpy x) -> (float, numpy grad); wall clock, "
+                  "stream synchronised inside each call"}
+
+    # ---- roofline of the dominant kernel ------------------------------------
+    k_ms, k_cnt = kernel_time(fe, lib, step_dev, 50)
+    roof = roofline(D, L, k_ms, fp64_peak_tf, hbm_gbs)
+    roof["hbm"]["peak_source"] = f"MEASURED_PEAKS.json hbm_gbs ({hbm_src})"
+
+    # ---- SCG iterations per second -------------------------------------------
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        fe.find_minimum(x_dev, max_iter=10)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, fx, stats = fe.find_minimum(x_dev, max_iter=50)
+        torch.cuda.synchronize()
+        scg_wall = time.perf_counter() - t0
+    scg = {"iters_per_s": stats["nit"] / scg_wall, "nit": int(stats["nit"]),
+           "func_eval": int(stats["func_eval"]), "fx_final": float(fx),
+           "note": "mfvgp_scg on device-resident x, max_iter=50, wall clock"}
+
+    large = None
+    if not args.no_large:
+        try:
+            large = run_large(torch, dist, rank, world, args.large_steps, 3, fp64_peak_tf,
+                              hbm_gbs)
+        except Exception as ex:                     # reported, never hidden
+            large = {"error": f"{type(ex).__name__}: {ex}"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(g, n_jobs=1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB write) between steps",
+                           "parallelism": "single GPU" if world == 1 else
+                           f"replicas only x{world} (evaluation is < 1 wave of one GPU)"},
+                "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "scg": scg, "large": large,
+                "fp64_peak_tflops_measured": fp64_peak_tf}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

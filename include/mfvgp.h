@@ -132,6 +132,11 @@ int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x_tol,
 /* counters for benchmarks: number of kernels this handle has launched      */
 int64_t mfvgp_launch_count(const mfvgp_handle *h);
 
+/* Per-launch CUDA-event timing of the dominant (Esde) kernel on the stream it
+ * is launched on.  Returns the accumulated time and launch count since the
+ * last call and then switches recording on (enable != 0) or off.           */
+int mfvgp_timing(mfvgp_handle *h, int enable, double *total_ms, int64_t *count);
+
 /* FP64 FMA micro-benchmark used as the roofline denominator (returns
  * achieved TFLOP/s on the handle's device, FMA = 2 FLOP)                   */
 int mfvgp_fp64_peak(int device, double *tflops_out);

@@ -54,6 +54,9 @@ struct mfvgp_handle {
     int scg_nblk = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    // optional per-launch timing of the dominant (Esde) kernel, for bench.py
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
 };
 
 static int dev_alloc(double **p, size_t n) {
@@ -199,6 +202,12 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
     a.D = h->D; a.n_begin = h->n_begin; a.n_end = h->n_end; a.ntiles = h->ntiles;
     a.log_vars = log_vars;
     const int nl = h->n_end - h->n_begin;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (h->timing) {
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        CK(cudaEventRecord(ev0, st));
+    }
     switch (h->system) {
         case MFVGP_SYS_DW: esde_small_kernel<0><<<nl, 64, 0, st>>>(a); break;
         case MFVGP_SYS_OU: esde_small_kernel<1><<<nl, 64, 0, st>>>(a); break;
@@ -212,6 +221,10 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
     }
     h->launches++;
     CK(cudaGetLastError());
+    if (h->timing) {
+        CK(cudaEventRecord(ev1, st));
+        h->timing_events.emplace_back(ev0, ev1);
+    }
     GuardArgs g;
     g.part = h->part; g.obs_times = h->obs_times; g.esde_n = h->esde_n; g.flags = h->flags;
     g.n_begin = h->n_begin; g.n_end = h->n_end; g.ntiles = h->ntiles;
@@ -342,6 +355,27 @@ extern "C" int mfvgp_esde_host(mfvgp_handle *h, const double *mean_pts_h,
     CK(cudaStreamSynchronize(h->stream));
     *Esde_h = h->pin[0];
     memcpy(status_h, h->pin + 8, sizeof(int32_t));
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_timing(mfvgp_handle *h, int enable, double *total_ms, int64_t *count) {
+    ARG(h != nullptr, "mfvgp_timing: NULL handle");
+    CK(cudaSetDevice(h->device));
+    double tot = 0.0;
+    int64_t cnt = 0;
+    for (auto &pr : h->timing_events) {
+        CK(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms;
+        cnt++;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    h->timing_events.clear();
+    if (total_ms) *total_ms = tot;
+    if (count) *count = cnt;
+    h->timing = enable != 0;
     return MFVGP_OK;
 }
 

@@ -364,7 +364,7 @@ class FreeEnergyOracle(object):
     """
 
     def __init__(self, system, sigma, theta, mu0, tau0, obs_times, obs_values,
-                 obs_noise, obs_mask=None, adaptive=True):
+                 obs_noise, obs_mask=None, adaptive=True, n_jobs=1):
         if system not in SYSTEMS:
             raise ValueError(f"unknown system {system}")
         self.system = system
@@ -385,6 +385,7 @@ class FreeEnergyOracle(object):
         self.ix_ikm = np.ix_(self.obs_mask, ikm)
         self.ix_iks = np.ix_(self.obs_mask, iks)
         self.adaptive = adaptive
+        self.n_jobs = int(n_jobs)        # free_energy.py:130-133 (joblib fan-out)
         self.neval = []
 
     # free_energy.py:281-336
@@ -406,12 +407,22 @@ class FreeEnergyOracle(object):
         dm = np.empty((L, D, 4)) if output_gradients else None
         dsv = np.empty((L, D, 3)) if output_gradients else None
         self.neval = []
-        for n in range(L):
-            e, gm, gs = single_interval(
+        if self.n_jobs > 1:
+            # free_energy.py:497-508 -- one joblib task per interval
+            from joblib import Parallel, delayed
+            results = Parallel(n_jobs=self.n_jobs, backend="loky")(
+                delayed(single_interval)(
+                    self.system, self.obs_times[n], self.obs_times[n + 1],
+                    mean_pts[:, 3 * n:3 * n + 4], vars_pts[:, 2 * n:2 * n + 3],
+                    self.sigma, self.theta, inv_sigma, output_gradients,
+                    adaptive=self.adaptive) for n in range(L))
+        else:
+            results = (single_interval(
                 self.system, self.obs_times[n], self.obs_times[n + 1],
                 mean_pts[:, 3 * n:3 * n + 4], vars_pts[:, 2 * n:2 * n + 3],
                 self.sigma, self.theta, inv_sigma, output_gradients,
-                adaptive=self.adaptive, info=self.neval)
+                adaptive=self.adaptive, info=self.neval) for n in range(L))
+        for n, (e, gm, gs) in enumerate(results):
             Esde += e
             if output_gradients:
                 dm[n], dsv[n] = gm, gs

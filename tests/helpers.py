@@ -70,3 +70,24 @@ def synthetic_l96(D, M, seed, dt_obs=0.25, partial=True):
                 mu0=10.0 * np.ones(D), tau0=4.0 * np.ones(D), obs_times=obs_times,
                 obs_values=obs_values, obs_noise=2.0 * np.ones(d), obs_mask=mask,
                 x0=np.concatenate((mp.ravel(), sp.ravel())))
+
+
+def synthetic_l96_device(torch, D, M, seed, dt_obs=0.25):
+    """Same recipe as synthetic_l96 but x0 is generated on the GPU (large D)."""
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    Nm, Ns = 3 * M + 4, 2 * M + 3
+    raw = 2.3 + 3.6 * torch.randn((D, Nm + 3), dtype=torch.float64, device="cuda",
+                                  generator=gen)
+    mp = (raw[:, :-3] + raw[:, 1:-2] + raw[:, 2:-1] + raw[:, 3:]) / 4.0
+    sp = torch.log(4.0 + 2.0 * torch.rand((D, Ns), dtype=torch.float64, device="cuda",
+                                          generator=gen))
+    x0 = torch.cat((mp.reshape(-1), sp.reshape(-1))).contiguous()
+    rng = np.random.default_rng(seed)
+    mask = [bool(i % 4 == 0) for i in range(D)]
+    d = sum(mask)
+    obs_values = rng.normal(2.3, 3.6, size=(M, d)) + np.sqrt(2.0) * rng.standard_normal((M, d))
+    return dict(system="L96", sigma=40.0 * np.ones(D), theta=np.array([8.0]),
+                mu0=10.0 * np.ones(D), tau0=4.0 * np.ones(D),
+                obs_times=dt_obs * np.arange(1, M + 1), obs_values=obs_values,
+                obs_noise=2.0 * np.ones(d), obs_mask=mask, x0=x0)
