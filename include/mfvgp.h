@@ -132,6 +132,12 @@ int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x_tol,
 /* counters for benchmarks: number of kernels this handle has launched      */
 int64_t mfvgp_launch_count(const mfvgp_handle *h);
 
+/* Diagnostics of the adaptive quadrature of the last evaluation:
+ * info_h [L][2] = number of bisections quad_vec's loop performed for the
+ * energy / dS integrand of each interval (0 = fixed 42-node rule was proven
+ * sufficient; k bisections correspond to quad_vec neval = 21 + 42 k).      */
+int mfvgp_refine_info(mfvgp_handle *h, int32_t *info_h /*[L][2]*/);
+
 /* Per-launch CUDA-event timing of the dominant (Esde) kernel on the stream it
  * is launched on.  Returns the accumulated time and launch count since the
  * last call and then switches recording on (enable != 0) or off.           */

@@ -35,6 +35,7 @@ SIGNATURES = {
     "mfvgp_scg": (c_int, [c_void_p, _P, c_int, c_double, c_double, _P, _P, _P, c_void_p]),
     "mfvgp_scg_host": (c_int, [c_void_p, _P, c_int, c_double, c_double, _P, _P, _P]),
     "mfvgp_launch_count": (c_int64, [c_void_p]),
+    "mfvgp_refine_info": (c_int, [c_void_p, _P]),
     "mfvgp_timing": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),
     "mfvgp_fp64_peak": (c_int, [c_int, POINTER(c_double)]),
 }

@@ -458,6 +458,7 @@ struct FinalArgs {
     const double *apart;      // [D][4] or nullptr (E_sde only)
     double *out;              // [4]
     int32_t *status;          // [1]
+    int32_t *refine_status;   // [1] bits set by refine_kernel, consumed here
     int n_begin, n_end, D;
     int with_e0;
     double eobs_const;        // M (d log 2pi + safe_log(prod R)), 0 on non-owning shards
@@ -505,6 +506,8 @@ final_kernel(const FinalArgs a) {
         if (!isfinite(E0)) st |= 2;
         if (!isfinite(Eobs)) st |= 4;
         if (sh_flag) st |= 8;
+        st |= a.refine_status[0];
+        a.refine_status[0] = 0;
         a.status[0] = st;
     }
 }

@@ -8,6 +8,7 @@
 
 #include "../../include/mfvgp.h"
 #include "kernels.cuh"
+#include "refine.cuh"
 #include "scg.cuh"
 
 using namespace mfvgp;
@@ -45,6 +46,10 @@ struct mfvgp_handle {
     double *dm_ws = nullptr, *ds_ws = nullptr, *part = nullptr, *esde_n = nullptr;
     double *apart = nullptr, *out_ws = nullptr;
     int32_t *flags = nullptr, *status_ws = nullptr;
+    // adaptive refinement (refine.cuh)
+    double *refine_ws = nullptr;
+    int32_t *refine_info = nullptr, *refine_status = nullptr;
+    int refine_grid = 1;
     // host-API staging
     double *x_dev = nullptr, *grad_dev = nullptr;
     double *pin = nullptr;   // pinned: out[4] + status
@@ -109,6 +114,14 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     double tab[kNodes * kTabStride];
     build_fixed_table(tab);
     CK(cudaMemcpyToSymbol(c_tab, tab, sizeof(tab)));
+    {
+        double gx[kNodesPerPanel], gv[kNodesPerPanel], gw[10];
+        for (int r = 0; r < kNodesPerPanel; ++r) { gx[r] = (double)gk21_x(r); gv[r] = (double)gk21_v(r); }
+        for (int i = 0; i < 10; ++i) gw[i] = (double)gk21_w(i);
+        CK(cudaMemcpyToSymbol(c_gk_x, gx, sizeof(gx)));
+        CK(cudaMemcpyToSymbol(c_gk_v, gv, sizeof(gv)));
+        CK(cudaMemcpyToSymbol(c_gk_w, gw, sizeof(gw)));
+    }
     if (dev_alloc(&h->sigma, D) || dev_alloc(&h->theta, 8) || dev_alloc(&h->mu0, D) ||
         dev_alloc(&h->tau0, D) || dev_alloc(&h->obs_times, M) ||
         dev_alloc(&h->obs_values, (size_t)M * d) || dev_alloc(&h->obs_noise, d) ||
@@ -117,6 +130,12 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         dev_alloc(&h->esde_n, L) || dev_alloc(&h->apart, (size_t)D * 4) ||
         dev_alloc(&h->out_ws, 4))
         return MFVGP_ERR_CUDA;
+    h->refine_grid = 2 * nl < 296 ? 2 * nl : 296;
+    if (dev_alloc(&h->refine_ws, (size_t)h->refine_grid * D * kMaxNE)) return MFVGP_ERR_CUDA;
+    CK(cudaMalloc((void **)&h->refine_info, 2 * L * sizeof(int32_t)));
+    CK(cudaMalloc((void **)&h->refine_status, sizeof(int32_t)));
+    CK(cudaMemset(h->refine_info, 0, 2 * L * sizeof(int32_t)));
+    CK(cudaMemset(h->refine_status, 0, sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->obs_idx, D * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->flags, L * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->status_ws, sizeof(int32_t)));
@@ -135,7 +154,8 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->obs_noise, h->obs_idx, h->dm_ws, h->ds_ws, h->part, h->esde_n,
                     h->apart, h->out_ws, h->flags, h->status_ws, h->x_dev, h->grad_dev,
                     h->scg_vec[0], h->scg_vec[1], h->scg_vec[2], h->scg_vec[3], h->scg_vec[4],
-                    h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal};
+                    h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal,
+                    h->refine_ws, h->refine_info, h->refine_status};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
@@ -231,6 +251,22 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
     guard_reduce_kernel<<<(nl * 32 + 255) / 256, 256, 0, st>>>(g);
     h->launches++;
     CK(cudaGetLastError());
+    // adaptive path for the flagged (interval, integrand) pairs; unflagged CTAs exit at once
+    RefineArgs r;
+    r.mean = mean; r.vars = vars; r.ldm = ldm; r.lds = lds;
+    r.obs_times = h->obs_times; r.sigma = h->sigma; r.theta = h->theta;
+    r.flags = h->flags; r.esde_n = h->esde_n; r.ds_out = ds; r.ws = h->refine_ws;
+    r.info = h->refine_info; r.status = h->refine_status;
+    r.D = h->D; r.n_begin = h->n_begin; r.n_end = h->n_end; r.log_vars = log_vars;
+    r.want_grad = ds != nullptr;
+    switch (h->system) {
+        case MFVGP_SYS_DW: refine_kernel<0><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
+        case MFVGP_SYS_OU: refine_kernel<1><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
+        case MFVGP_SYS_L63: refine_kernel<2><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
+        default: refine_kernel<3><<<h->refine_grid, kRefThreads, 0, st>>>(r);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
     return MFVGP_OK;
 }
 
@@ -239,6 +275,7 @@ static int launch_final(mfvgp_handle *h, const double *apart, double *out, int32
     FinalArgs f;
     f.esde_n = h->esde_n; f.flags = h->flags; f.apart = apart; f.out = out; f.status = status;
     f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = h->D;
+    f.refine_status = h->refine_status;
     f.with_e0 = h->n_begin == 0;
     f.eobs_const = h->n_begin == 0 ? h->eobs_const : 0.0;
     final_kernel<<<1, 256, 0, st>>>(f);
@@ -355,6 +392,14 @@ extern "C" int mfvgp_esde_host(mfvgp_handle *h, const double *mean_pts_h,
     CK(cudaStreamSynchronize(h->stream));
     *Esde_h = h->pin[0];
     memcpy(status_h, h->pin + 8, sizeof(int32_t));
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_refine_info(mfvgp_handle *h, int32_t *info_h) {
+    ARG(h && info_h, "mfvgp_refine_info: NULL argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(info_h, h->refine_info, 2 * h->L * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return MFVGP_OK;
 }
 

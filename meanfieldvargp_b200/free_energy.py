@@ -182,6 +182,17 @@ class FreeEnergy(object):
     def kernel_launches(self):
         return int(self._lib.mfvgp_launch_count(self._h))
 
+    def refine_info(self):
+        """
+        Bisections performed by the adaptive quadrature in the last evaluation,
+        array [L, 2] (energy, dS integrand); 0 where the fixed 42-node rule was
+        proven to be quad_vec's answer.  k > 0 corresponds to scipy's
+        ``neval = 21 + 42 k`` (free_energy.py:405-417).
+        """
+        info = np.zeros((self.num_L, 2), dtype=np.int32)
+        _lib.check(self._lib.mfvgp_refine_info(self._h, _ptr(info)), "mfvgp_refine_info")
+        return info
+
     # ---- error convention ----------------------------------------------------
     def _raise_on_status(self, status, E0=None, Esde=None, Eobs=None):
         name = self.__class__.__name__

@@ -78,23 +78,25 @@ def lagrange_basis(t, knots):
     """Return (B[k, ...], dB[k, ...]) for every knot k at times ``t``."""
     t = np.asarray(t, dtype=float)
     K = len(knots)
+    diff = [t - knots[l] for l in range(K)]                  # (t - h_l)
     B = np.empty((K,) + t.shape)
     dB = np.empty((K,) + t.shape)
     for k in range(K):
-        val = np.ones_like(t)
-        for l in range(K):
-            if l != k:
-                val = val * ((t - knots[l]) / (knots[k] - knots[l]))
-        der = np.zeros_like(t)
-        for j in range(K):
-            if j == k:
-                continue
-            term = np.full_like(t, 1.0 / (knots[k] - knots[j]))
-            for l in range(K):
-                if l != k and l != j:
-                    term = term * ((t - knots[l]) / (knots[k] - knots[l]))
+        others = [l for l in range(K) if l != k]
+        den = 1.0
+        for l in others:
+            den *= (knots[k] - knots[l])
+        val = diff[others[0]]
+        for l in others[1:]:
+            val = val * diff[l]
+        der = 0.0
+        for j in others:                                    # product rule
+            rest = [l for l in others if l != j]
+            term = diff[rest[0]] if rest else np.ones_like(t)
+            for l in rest[1:]:
+                term = term * diff[l]
             der = der + term
-        B[k], dB[k] = val, der
+        B[k], dB[k] = val / den, der / den
     return B, dB
 
 
