@@ -115,6 +115,21 @@ int mfvgp_ecost_host(mfvgp_handle *h, const double *x_h, int want_grad,
                      double *out_h /*[4]*/, double *grad_h, int32_t *status_h);
 
 /*
+ * FreeEnergy.E_kl0(m0, s0, output_gradients) (free_energy.py:281-336) and
+ * FreeEnergy.E_obs(mean_pts[d][M], vars_pts[d][M], output_gradients)
+ * (:567-649) as stand-alone calls; E_cost computes both terms itself.
+ * Returned energies carry the reference's 1/2 factor (:335, :648).
+ */
+int mfvgp_ekl0_host(mfvgp_handle *h, const double *m0_h /*[D]*/,
+                    const double *s0_h /*[D]*/, int want_grad, double *E0_h,
+                    double *dE0_dm0_h /*[D]*/, double *dE0_ds0_h /*[D]*/,
+                    int32_t *status_h);
+int mfvgp_eobs_host(mfvgp_handle *h, const double *mean_obs_h /*[d][M]*/,
+                    const double *vars_obs_h /*[d][M]*/, int want_grad,
+                    double *Eobs_h, double *dEobs_dm_h /*[d][M]*/,
+                    double *dEobs_ds_h /*[d][M]*/, int32_t *status_h);
+
+/*
  * SCG.minimize(x0) over E_cost (scaled_cg.py:107-386 as driven by
  * FreeEnergy.find_minimum, free_energy.py:815-830).  Iterates, gradients and
  * the line-search dot products stay on the device; x_d is updated in place.
@@ -128,6 +143,22 @@ int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
 int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x_tol,
                    double f_tol, double *fx_hist_h, double *dfx_hist_h,
                    double *result_h /*[4]*/);
+
+/*
+ * Multi-GPU: one process (rank) per GPU, the L intervals sharded in contiguous
+ * blocks (the reference's own unit of parallelism, free_energy.py:500-508).
+ * Rank 0 calls mfvgp_comm_unique_id and distributes the 128 bytes (any host
+ * channel); every rank then calls mfvgp_comm_init on a handle created with its
+ * interval block [n_begin, n_end).  Afterwards mfvgp_ecost / mfvgp_scg are
+ * collective calls: x_d / grad_d keep the full reference layout, each rank
+ * reads and writes only its own columns (plus the one column it shares with
+ * the next rank), the shared column's gradient is exchanged with
+ * ncclSend/ncclRecv over NVLink, and the scalars (F, E0, Esde, Eobs, status,
+ * SCG dot products) are all-gathered and folded in rank order, so every rank
+ * takes identical SCG branches.  NCCL is bound at run time (dlopen).
+ */
+int mfvgp_comm_unique_id(void *id128_out /*128 bytes*/);
+int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void *id128);
 
 /* counters for benchmarks: number of kernels this handle has launched      */
 int64_t mfvgp_launch_count(const mfvgp_handle *h);

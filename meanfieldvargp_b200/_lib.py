@@ -32,8 +32,12 @@ SIGNATURES = {
     "mfvgp_ecost": (c_int, [c_void_p, _P, c_int, _P, _P, _P, c_void_p]),
     "mfvgp_esde_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P, _P, _P]),
     "mfvgp_ecost_host": (c_int, [c_void_p, _P, c_int, _P, _P, _P]),
+    "mfvgp_ekl0_host": (c_int, [c_void_p, _P, _P, c_int, POINTER(c_double), _P, _P, POINTER(c_int32)]),
+    "mfvgp_eobs_host": (c_int, [c_void_p, _P, _P, c_int, POINTER(c_double), _P, _P, POINTER(c_int32)]),
     "mfvgp_scg": (c_int, [c_void_p, _P, c_int, c_double, c_double, _P, _P, _P, c_void_p]),
     "mfvgp_scg_host": (c_int, [c_void_p, _P, c_int, c_double, c_double, _P, _P, _P]),
+    "mfvgp_comm_unique_id": (c_int, [_P]),
+    "mfvgp_comm_init": (c_int, [c_void_p, c_int, c_int, _P]),
     "mfvgp_launch_count": (c_int64, [c_void_p]),
     "mfvgp_refine_info": (c_int, [c_void_p, _P]),
     "mfvgp_timing": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),

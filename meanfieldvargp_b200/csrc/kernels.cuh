@@ -392,9 +392,14 @@ assemble_kernel(const AssembleArgs a) {
     const double *xs = a.x + (int64_t)a.D * a.Nm + (int64_t)j * a.Ns;
     double *gm = a.grad ? a.grad + (int64_t)j * a.Nm : nullptr;
     double *gs = a.grad ? a.grad + (int64_t)a.D * a.Nm + (int64_t)j * a.Ns : nullptr;
-    // owned column ranges of this shard
-    const int cm0 = 3 * a.n_begin, cm1 = (a.n_end == a.L) ? a.Nm : 3 * a.n_end;
-    const int cs0 = 2 * a.n_begin, cs1 = (a.n_end == a.L) ? a.Ns : 2 * a.n_end;
+    // Column ranges of this shard.  Owned columns [c0, own1) carry the E0 / obs
+    // terms; the active range additionally holds the ghost column shared with
+    // the next shard (its left edge), which only receives this shard's k=3 / k=2
+    // contribution here -- the rest arrives through the edge exchange.
+    const bool last = a.n_end == a.L;
+    const int cm0 = 3 * a.n_begin, own_m1 = last ? a.Nm : 3 * a.n_end;
+    const int cs0 = 2 * a.n_begin, own_s1 = last ? a.Ns : 2 * a.n_end;
+    const int cm1 = last ? a.Nm : own_m1 + 1, cs1 = last ? a.Ns : own_s1 + 1;
     double acc[3] = {0.0, 0.0, 0.0};
 
     for (int c = cm0 + threadIdx.x; c < cm1; c += blockDim.x) {
@@ -412,7 +417,7 @@ assemble_kernel(const AssembleArgs a) {
             g += z0 / a.tau0[j];
             acc[1] += z0 * z0 / a.tau0[j];
         }
-        if (k == 0 && n >= 1 && n <= a.M && jo >= 0) {
+        if (k == 0 && n >= 1 && n <= a.M && jo >= 0 && c < own_m1) {
             const double r = a.obs_values[(int64_t)(n - 1) * a.d + jo] - m;
             g -= Ri * r;
             acc[2] += Ri * r * r;
@@ -435,7 +440,7 @@ assemble_kernel(const AssembleArgs a) {
             acc[0] += log(t0 / s);
             acc[1] += (s - t0) / t0;
         }
-        if (k == 0 && n >= 1 && n <= a.M && jo >= 0) {
+        if (k == 0 && n >= 1 && n <= a.M && jo >= 0 && c < own_s1) {
             g += 0.5 * Ri;
             acc[2] += Ri * s;
         }
@@ -459,6 +464,7 @@ struct FinalArgs {
     double *out;              // [4]
     int32_t *status;          // [1]
     int32_t *refine_status;   // [1] bits set by refine_kernel, consumed here
+    int record9;              // out has 9 slots (multi-GPU record)
     int n_begin, n_end, D;
     int with_e0;
     double eobs_const;        // M (d log 2pi + safe_log(prod R)), 0 on non-owning shards
@@ -497,10 +503,6 @@ final_kernel(const FinalArgs a) {
             }
             Eobs = 0.5 * (acc[3] + a.eobs_const);
         }
-        a.out[0] = E0 + Esde + Eobs;
-        a.out[1] = E0;
-        a.out[2] = Esde;
-        a.out[3] = Eobs;
         int32_t st = 0;
         if (!isfinite(Esde)) st |= 1;
         if (!isfinite(E0)) st |= 2;
@@ -508,7 +510,145 @@ final_kernel(const FinalArgs a) {
         if (sh_flag) st |= 8;
         st |= a.refine_status[0];
         a.refine_status[0] = 0;
+        // record[0..3] = F, E0, Esde, Eobs; record[4..8] = status bits as 0/1 so
+        // that shards can be combined by summation (combine_record_kernel)
+        a.out[0] = E0 + Esde + Eobs;
+        a.out[1] = E0;
+        a.out[2] = Esde;
+        a.out[3] = Eobs;
+        if (a.record9) {
+#pragma unroll
+            for (int b = 0; b < 5; ++b) a.out[4 + b] = (st >> b) & 1 ? 1.0 : 0.0;
+        }
         a.status[0] = st;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU (time intervals sharded, one rank per GPU).  Neighbouring shards
+// share one column of support points (free_energy.py:504-505, 723-724): each
+// computes its part of that column's gradient, the parts are exchanged over
+// NVLink (ncclSend/ncclRecv) and added on both sides, so both hold the same
+// bits.  buf layout: [0] mean left edge, [1] var left edge, [2] mean ghost,
+// [3] var ghost, each [D].
+// ---------------------------------------------------------------------------
+struct EdgeArgs {
+    double *grad;
+    double *buf;              // [4][D]
+    int D, Nm, Ns, n_begin, n_end, has_left, has_right;
+};
+
+__global__ void __launch_bounds__(256)
+pack_edges_kernel(const EdgeArgs a) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.D) return;
+    const double *gm = a.grad + (int64_t)j * a.Nm;
+    const double *gs = a.grad + (int64_t)a.D * a.Nm + (int64_t)j * a.Ns;
+    if (a.has_left) {
+        a.buf[j] = gm[3 * a.n_begin];
+        a.buf[a.D + j] = gs[2 * a.n_begin];
+    }
+    if (a.has_right) {
+        a.buf[2 * a.D + j] = gm[3 * a.n_end];
+        a.buf[3 * a.D + j] = gs[2 * a.n_end];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+add_edges_kernel(const EdgeArgs a) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.D) return;
+    double *gm = a.grad + (int64_t)j * a.Nm;
+    double *gs = a.grad + (int64_t)a.D * a.Nm + (int64_t)j * a.Ns;
+    if (a.has_left) {
+        gm[3 * a.n_begin] += a.buf[j];
+        gs[2 * a.n_begin] += a.buf[a.D + j];
+    }
+    if (a.has_right) {
+        gm[3 * a.n_end] += a.buf[2 * a.D + j];
+        gs[2 * a.n_end] += a.buf[3 * a.D + j];
+    }
+}
+
+// gathered [world][n]: slots < nsum are summed in rank order, the rest max'ed
+__global__ void combine_record_kernel(const double *gathered, int world, int n, int nsum,
+                                      double *out, int32_t *status /*or nullptr*/) {
+    const int i = threadIdx.x;
+    if (i < n) {
+        double v = gathered[i];
+        for (int r = 1; r < world; ++r)
+            v = i < nsum ? v + gathered[r * n + i] : fmax(v, gathered[r * n + i]);
+        out[i] = v;
+    }
+    if (status != nullptr) {
+        __syncthreads();
+        if (i == 0) {
+            int32_t st = 0;
+            for (int b = 0; b < 5; ++b)
+                if (out[4 + b] > 0.0) st |= 1 << b;
+            status[0] = st;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stand-alone E_kl0 (free_energy.py:281-336) and E_obs (:567-649), for callers
+// that use those two methods directly; E_cost fuses them into assemble_kernel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ekl0_kernel(const double *m0, const double *s0, const double *mu0, const double *tau0, int D,
+            double *out /*[1]*/, double *dm0, double *ds0, int32_t *status) {
+    __shared__ double sh_red[2 * 8];
+    double acc[2] = {0.0, 0.0};
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+        const double z0 = m0[j] - mu0[j], t0 = tau0[j], s = s0[j];
+        acc[0] += log(t0 / s);
+        acc[1] += (z0 * z0 + s - t0) / t0;
+        if (dm0 != nullptr) {
+            dm0[j] = z0 / t0;
+            ds0[j] = 0.5 * (1.0 / t0 - 1.0 / s);
+        }
+    }
+    block_sum<2, 256>(acc, sh_red);
+    if (threadIdx.x == 0) {
+        const double lg = fmin(fmax(acc[0], -690.77552789821368), 690.77552789821368);
+        const double E0 = lg + acc[1];
+        out[0] = 0.5 * E0;
+        status[0] = isfinite(E0) ? 0 : 2;
+    }
+}
+
+// one CTA per observed dimension; mean/vars are the [d][M] slices the reference
+// passes (mean_points[ix_ikm], vars_points[ix_iks]); row partials -> rowsum[d]
+__global__ void __launch_bounds__(256)
+eobs_rows_kernel(const double *mean, const double *vars, const double *obs_values,
+                 const double *obs_noise, int d, int M, double *rowsum, double *dm, double *ds) {
+    __shared__ double sh_red[8];
+    const int jo = blockIdx.x;
+    const double Ri = 1.0 / obs_noise[jo];
+    double acc[1] = {0.0};
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+        const double r = obs_values[(int64_t)k * d + jo] - mean[(int64_t)jo * M + k];
+        acc[0] += Ri * r * r + Ri * vars[(int64_t)jo * M + k];
+        if (dm != nullptr) {
+            dm[(int64_t)jo * M + k] = -Ri * r;
+            ds[(int64_t)jo * M + k] = 0.5 * Ri;
+        }
+    }
+    block_sum<1, 256>(acc, sh_red);
+    if (threadIdx.x == 0) rowsum[jo] = acc[0];
+}
+
+__global__ void __launch_bounds__(256)
+eobs_final_kernel(const double *rowsum, int d, double eobs_const, double *out, int32_t *status) {
+    __shared__ double sh_red[8];
+    double acc[1] = {0.0};
+    for (int j = threadIdx.x; j < d; j += blockDim.x) acc[0] += rowsum[j];
+    block_sum<1, 256>(acc, sh_red);
+    if (threadIdx.x == 0) {
+        const double Eobs = acc[0] + eobs_const;
+        out[0] = 0.5 * Eobs;
+        status[0] = isfinite(Eobs) ? 0 : 4;
     }
 }
 

@@ -8,6 +8,7 @@
 
 #include "../../include/mfvgp.h"
 #include "kernels.cuh"
+#include "nccl_dyn.h"
 #include "refine.cuh"
 #include "scg.cuh"
 
@@ -57,6 +58,12 @@ struct mfvgp_handle {
     double *scg_vec[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *scg_part = nullptr, *scg_scal = nullptr;
     int scg_nblk = 0;
+    // multi-GPU: one rank per GPU, intervals [n_begin, n_end) of this handle
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    double *edge_send = nullptr, *edge_recv = nullptr;   // [4][D] each
+    double *gather = nullptr;                            // [world][16]
+    double *rec_ws = nullptr;                            // [16] local record before combine
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     // optional per-launch timing of the dominant (Esde) kernel, for bench.py
@@ -128,7 +135,7 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         dev_alloc(&h->dm_ws, (size_t)L * D * 4) || dev_alloc(&h->ds_ws, (size_t)L * D * 3) ||
         dev_alloc(&h->part, (size_t)nl * h->ntiles * kPartStride) ||
         dev_alloc(&h->esde_n, L) || dev_alloc(&h->apart, (size_t)D * 4) ||
-        dev_alloc(&h->out_ws, 4))
+        dev_alloc(&h->out_ws, 16) || dev_alloc(&h->rec_ws, 16))
         return MFVGP_ERR_CUDA;
     h->refine_grid = 2 * nl < 296 ? 2 * nl : 296;
     if (dev_alloc(&h->refine_ws, (size_t)h->refine_grid * D * kMaxNE)) return MFVGP_ERR_CUDA;
@@ -155,9 +162,11 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->apart, h->out_ws, h->flags, h->status_ws, h->x_dev, h->grad_dev,
                     h->scg_vec[0], h->scg_vec[1], h->scg_vec[2], h->scg_vec[3], h->scg_vec[4],
                     h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal,
-                    h->refine_ws, h->refine_info, h->refine_status};
+                    h->refine_ws, h->refine_info, h->refine_status, h->edge_send, h->edge_recv,
+                    h->gather, h->rec_ws};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -270,17 +279,100 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
     return MFVGP_OK;
 }
 
+#define NCK(call)                                                             \
+    do {                                                                      \
+        int r_ = (call);                                                      \
+        if (r_ != kNcclSuccess) {                                             \
+            g_err = std::string(#call) + ": " + nccl().GetErrorString(r_);    \
+            return MFVGP_ERR_CUDA;                                            \
+        }                                                                     \
+    } while (0)
+
+// all-gather `n` doubles from every rank and fold them in rank order
+static int combine_over_ranks(mfvgp_handle *h, const double *local, int n, int nsum,
+                              double *out, int32_t *status, cudaStream_t st) {
+    NCK(nccl().AllGather(local, h->gather, n, kNcclFloat64, h->comm, st));
+    combine_record_kernel<<<1, 32, 0, st>>>(h->gather, h->world, n, nsum, out, status);
+    h->launches++;
+    CK(cudaGetLastError());
+    return MFVGP_OK;
+}
+
 static int launch_final(mfvgp_handle *h, const double *apart, double *out, int32_t *status,
                         cudaStream_t st) {
     FinalArgs f;
-    f.esde_n = h->esde_n; f.flags = h->flags; f.apart = apart; f.out = out; f.status = status;
-    f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = h->D;
+    const bool multi = h->world > 1;
+    f.esde_n = h->esde_n; f.flags = h->flags; f.apart = apart;
+    f.out = multi ? h->rec_ws : out; f.status = status;
     f.refine_status = h->refine_status;
+    f.record9 = multi ? 1 : 0;
+    f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = h->D;
     f.with_e0 = h->n_begin == 0;
     f.eobs_const = h->n_begin == 0 ? h->eobs_const : 0.0;
     final_kernel<<<1, 256, 0, st>>>(f);
     h->launches++;
     CK(cudaGetLastError());
+    if (multi) {
+        // scalar free energy: every rank ends up with the same F, E0, Esde, Eobs
+        int rc = combine_over_ranks(h, h->rec_ws, 9, 9, h->rec_ws, status, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out, h->rec_ws, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    return MFVGP_OK;
+}
+
+// gradient of the column shared with each neighbour: exchange the two partial
+// sums over NVLink and add (both sides then hold identical bits)
+static int exchange_edges(mfvgp_handle *h, double *grad, cudaStream_t st) {
+    EdgeArgs e;
+    e.grad = grad; e.buf = h->edge_send; e.D = h->D; e.Nm = h->Nm; e.Ns = h->Ns;
+    e.n_begin = h->n_begin; e.n_end = h->n_end;
+    e.has_left = h->rank > 0; e.has_right = h->rank < h->world - 1;
+    const int nb = (h->D + 255) / 256;
+    pack_edges_kernel<<<nb, 256, 0, st>>>(e);
+    h->launches++;
+    CK(cudaGetLastError());
+    const size_t cnt = 2 * (size_t)h->D;
+    NCK(nccl().GroupStart());
+    if (e.has_left) {
+        NCK(nccl().Send(h->edge_send, cnt, kNcclFloat64, h->rank - 1, h->comm, st));
+        NCK(nccl().Recv(h->edge_recv, cnt, kNcclFloat64, h->rank - 1, h->comm, st));
+    }
+    if (e.has_right) {
+        NCK(nccl().Send(h->edge_send + cnt, cnt, kNcclFloat64, h->rank + 1, h->comm, st));
+        NCK(nccl().Recv(h->edge_recv + cnt, cnt, kNcclFloat64, h->rank + 1, h->comm, st));
+    }
+    NCK(nccl().GroupEnd());
+    e.buf = h->edge_recv;
+    add_edges_kernel<<<nb, 256, 0, st>>>(e);
+    h->launches++;
+    CK(cudaGetLastError());
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_comm_unique_id(void *id128_out) {
+    ARG(id128_out != nullptr, "mfvgp_comm_unique_id: NULL argument");
+    if (!nccl().load()) { g_err = "NCCL (libnccl.so.2) could not be loaded"; return MFVGP_ERR_CUDA; }
+    ncclUniqueId id;
+    NCK(nccl().GetUniqueId(&id));
+    memcpy(id128_out, &id, sizeof(id));
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void *id128) {
+    ARG(h && id128 && world >= 1 && rank >= 0 && rank < world, "mfvgp_comm_init: bad argument");
+    if (world == 1) return MFVGP_OK;
+    if (!nccl().load()) { g_err = "NCCL (libnccl.so.2) could not be loaded"; return MFVGP_ERR_CUDA; }
+    ARG((rank == 0) == (h->n_begin == 0) && (rank == world - 1) == (h->n_end == h->L),
+        "mfvgp_comm_init: the handle's interval range does not match its rank");
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NCK(nccl().CommInitRank(&h->comm, world, id, rank));
+    h->rank = rank; h->world = world;
+    if (dev_alloc(&h->edge_send, 4 * (size_t)h->D) || dev_alloc(&h->edge_recv, 4 * (size_t)h->D) ||
+        dev_alloc(&h->gather, 16 * (size_t)world))
+        return MFVGP_ERR_CUDA;
     return MFVGP_OK;
 }
 
@@ -330,6 +422,10 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
     assemble_kernel<<<h->D, 256, 0, st>>>(a);
     h->launches++;
     CK(cudaGetLastError());
+    if (h->world > 1 && want_grad) {
+        rc = exchange_edges(h, grad_d, st);
+        if (rc) return rc;
+    }
     return launch_final(h, h->apart, out_d, status_d, st);
 }
 
@@ -391,6 +487,75 @@ extern "C" int mfvgp_esde_host(mfvgp_handle *h, const double *mean_pts_h,
                        h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *Esde_h = h->pin[0];
+    memcpy(status_h, h->pin + 8, sizeof(int32_t));
+    return MFVGP_OK;
+}
+
+// E_kl0 / E_obs as stand-alone calls on host buffers (free_energy.py:281-336, 567-649)
+extern "C" int mfvgp_ekl0_host(mfvgp_handle *h, const double *m0_h, const double *s0_h,
+                               int want_grad, double *E0_h, double *dm0_h, double *ds0_h,
+                               int32_t *status_h) {
+    ARG(h && m0_h && s0_h && E0_h && status_h, "mfvgp_ekl0_host: NULL argument");
+    ARG(!want_grad || (dm0_h && ds0_h), "mfvgp_ekl0_host: gradient buffers are NULL");
+    if (!h->have_prior) { g_err = "mfvgp_ekl0_host: set_prior not called"; return MFVGP_ERR_STATE; }
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const int D = h->D;
+    double *buf = h->x_dev, *gbuf = h->grad_dev;          // [m0 | s0], [dm0 | ds0]
+    CK(cudaMemcpyAsync(buf, m0_h, D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(buf + D, s0_h, D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    ekl0_kernel<<<1, 256, 0, h->stream>>>(buf, buf + D, h->mu0, h->tau0, D, h->out_ws,
+                                          want_grad ? gbuf : nullptr,
+                                          want_grad ? gbuf + D : nullptr, h->status_ws);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (want_grad) {
+        CK(cudaMemcpyAsync(dm0_h, gbuf, D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(ds0_h, gbuf + D, D * sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+    }
+    CK(cudaMemcpyAsync(h->pin, h->out_ws, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin + 8, h->status_ws, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *E0_h = h->pin[0];
+    memcpy(status_h, h->pin + 8, sizeof(int32_t));
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_eobs_host(mfvgp_handle *h, const double *mean_obs_h,
+                               const double *vars_obs_h, int want_grad, double *Eobs_h,
+                               double *dm_h, double *ds_h, int32_t *status_h) {
+    ARG(h && mean_obs_h && vars_obs_h && Eobs_h && status_h, "mfvgp_eobs_host: NULL argument");
+    ARG(!want_grad || (dm_h && ds_h), "mfvgp_eobs_host: gradient buffers are NULL");
+    if (!h->have_obs) { g_err = "mfvgp_eobs_host: set_obs not called"; return MFVGP_ERR_STATE; }
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const size_t dm_n = (size_t)h->d * h->M;               // <= D*Nm/3, fits the staging
+    double *buf = h->x_dev, *gbuf = h->grad_dev;
+    CK(cudaMemcpyAsync(buf, mean_obs_h, dm_n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(buf + dm_n, vars_obs_h, dm_n * sizeof(double), cudaMemcpyHostToDevice,
+                       h->stream));
+    eobs_rows_kernel<<<h->d, 256, 0, h->stream>>>(buf, buf + dm_n, h->obs_values, h->obs_noise,
+                                                  h->d, h->M, h->apart,
+                                                  want_grad ? gbuf : nullptr,
+                                                  want_grad ? gbuf + dm_n : nullptr);
+    eobs_final_kernel<<<1, 256, 0, h->stream>>>(h->apart, h->d, h->eobs_const, h->out_ws,
+                                                h->status_ws);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    if (want_grad) {
+        CK(cudaMemcpyAsync(dm_h, gbuf, dm_n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(ds_h, gbuf + dm_n, dm_n * sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+    }
+    CK(cudaMemcpyAsync(h->pin, h->out_ws, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin + 8, h->status_ws, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *Eobs_h = h->pin[0];
     memcpy(status_h, h->pin + 8, sizeof(int32_t));
     return MFVGP_OK;
 }
@@ -464,13 +629,15 @@ namespace {
 struct ScgRun {
     mfvgp_handle *h;
     cudaStream_t st;
-    int64_t n;
+    VecMap n;          // index map of this rank's part of x (named n: it replaces the length)
     int status_or = 0;
 
     int fold() {
         scg_fold_kernel<<<1, kRedBlock, 0, st>>>(h->scg_part, h->scg_nblk, h->scg_scal);
         h->launches++;
         CK(cudaGetLastError());
+        // sharded: the dot products of all ranks, folded in rank order (sum, sum, sum, max)
+        if (h->world > 1) return combine_over_ranks(h, h->scg_scal, 4, 3, h->scg_scal, nullptr, st);
         return MFVGP_OK;
     }
     // reads scal[0..3] (fold output), scal[4..7] (E_cost output) and the status
@@ -531,6 +698,20 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int64_t n = (int64_t)h->D * (h->Nm + h->Ns);
+    VecMap vm;
+    vm.num_mp = (int64_t)h->D * h->Nm;
+    vm.D = h->D; vm.Nm = h->Nm; vm.Ns = h->Ns;
+    vm.full = h->world == 1 ? 1 : 0;
+    {
+        const bool last = h->n_end == h->L;
+        vm.cm0 = 3 * h->n_begin; vm.cs0 = 2 * h->n_begin;
+        vm.own_wm = (last ? h->Nm : 3 * h->n_end) - vm.cm0;
+        vm.own_ws = (last ? h->Ns : 2 * h->n_end) - vm.cs0;
+        vm.wm = vm.own_wm + (last ? 0 : 1);          // + ghost column shared with the next rank
+        vm.ws = vm.own_ws + (last ? 0 : 1);
+        vm.n = vm.full ? n : (int64_t)h->D * (vm.wm + vm.ws);
+    }
+    const int64_t n_total = n;       // SCG restarts after dim_x successes (scaled_cg.py:361)
     if (!h->scg_vec[0]) {
         for (int i = 0; i < 7; ++i)
             if (dev_alloc(&h->scg_vec[i], n)) return MFVGP_ERR_CUDA;
@@ -540,13 +721,15 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
             dev_alloc(&h->scg_scal, 8))
             return MFVGP_ERR_CUDA;
     }
-    ScgRun R{h, st, n};
+    ScgRun R{h, st, vm};
     double *x = h->scg_vec[0], *xt = h->scg_vec[1], *d = h->scg_vec[2];
     double *gnew = h->scg_vec[3], *gold = h->scg_vec[4], *gnow = h->scg_vec[5];
     double *gp = h->scg_vec[6];
     double s8[8];
     for (int i = 0; i < max_it; ++i) fx_hist_h[i] = dfx_hist_h[i] = 0.0;   // :123-124
     CK(cudaMemcpyAsync(x, x_d, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (!vm.full)   // columns of other ranks are never written: keep them defined in both iterates
+        CK(cudaMemcpyAsync(xt, x_d, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
 
     int nit = max_it, func_eval = 0;
     double fx = 0.0;
@@ -628,7 +811,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         }
         if (Delta < 0.25) beta = fmin(4.0 * beta, beta_max);      // :350-356
         if (Delta > 0.75) beta = fmax(0.5 * beta, beta_min);
-        if (count_success == n) {                                 // :361-369
+        if (count_success == n_total) {                           // :361-369
             RC(R.direction(d, gnew, 0.0, 1));
             RC(R.read(s8));
             mu = s8[0]; kappa = s8[1];

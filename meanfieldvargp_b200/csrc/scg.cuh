@@ -13,6 +13,33 @@ namespace mfvgp {
 constexpr int kRedBlock = 256;
 constexpr int kRedSlots = 4;
 
+// Index map of the optimisation vector a rank works on.  Single GPU: the whole
+// x.  Sharded: the rank's active columns of the mean block [D][Nm] and of the
+// log-variance block [D][Ns]; the last active column may be a ghost column
+// shared with the next rank -- it is updated here too (both ranks hold the same
+// bits) but only its owner counts it in reductions.
+struct VecMap {
+    int64_t n;        // number of local entries
+    int64_t num_mp;   // D*Nm
+    int full;         // 1: identity map
+    int D, Nm, Ns, cm0, cs0, wm, ws, own_wm, own_ws;
+    __device__ __forceinline__ int64_t at(int64_t idx, bool &owned) const {
+        if (full) { owned = true; return idx; }
+        const int64_t nm = (int64_t)D * wm;
+        if (idx < nm) {
+            const int64_t j = idx / wm;
+            const int c = (int)(idx - j * wm);
+            owned = c < own_wm;
+            return j * Nm + cm0 + c;
+        }
+        const int64_t r = idx - nm;
+        const int64_t j = r / ws;
+        const int c = (int)(r - j * ws);
+        owned = c < own_ws;
+        return num_mp + j * Ns + cs0 + c;
+    }
+};
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -52,35 +79,46 @@ __device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part) 
 // d = gamma*d - g (gamma = 0 and d arbitrary gives the restart d = -g);
 // partials: [0] mu = d.g, [1] kappa = d.d     (scaled_cg.py:192-200, 361-369)
 __global__ void __launch_bounds__(kRedBlock)
-scg_direction_kernel(double *d, const double *g, double gamma, int restart, int64_t n,
+scg_direction_kernel(double *d, const double *g, double gamma, int restart, const VecMap vm,
                      double *part) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        bool own;
+        const int64_t i = vm.at(t, own);
         const double gi = g[i];
         const double di = restart ? -gi : gamma * d[i] - gi;
         d[i] = di;
-        v[0] = fma(di, gi, v[0]);
-        v[1] = fma(di, di, v[1]);
+        if (own) {
+            v[0] = fma(di, gi, v[0]);
+            v[1] = fma(di, di, v[1]);
+        }
     }
     red_store(v, part);
 }
 
 // y = x + a*d                                   (scaled_cg.py:222, :242)
 __global__ void __launch_bounds__(kRedBlock)
-scg_axpy_kernel(double *y, const double *x, const double *d, double a, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x)
+scg_axpy_kernel(double *y, const double *x, const double *d, double a, const VecMap vm) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        bool own;
+        const int64_t i = vm.at(t, own);
         y[i] = x[i] + a * d[i];
+    }
 }
 
 // partial [0] = d.(gp - g)                      (scaled_cg.py:228)
 __global__ void __launch_bounds__(kRedBlock)
-scg_theta_kernel(const double *d, const double *gp, const double *g, int64_t n, double *part) {
+scg_theta_kernel(const double *d, const double *gp, const double *g, const VecMap vm,
+                 double *part) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x)
-        v[0] = fma(d[i], gp[i] - g[i], v[0]);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        bool own;
+        const int64_t i = vm.at(t, own);
+        if (own) v[0] = fma(d[i], gp[i] - g[i], v[0]);
+    }
     red_store(v, part);
 }
 
@@ -89,11 +127,14 @@ scg_theta_kernel(const double *d, const double *gp, const double *g, int64_t n, 
 // (Polak-Ribiere numerator once g_now becomes grad_new and g_new grad_old,
 // :367), [3] max |d| (:306).
 __global__ void __launch_bounds__(kRedBlock)
-scg_stats_kernel(const double *g_now, const double *g_new, const double *d, int64_t n,
+scg_stats_kernel(const double *g_now, const double *g_new, const double *d, const VecMap vm,
                  double *part) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        bool own;
+        const int64_t i = vm.at(t, own);
+        if (!own) continue;
         const double a = g_now[i];
         v[0] += fabs(a);
         v[1] = fma(a, a, v[1]);

@@ -182,6 +182,26 @@ class FreeEnergy(object):
     def kernel_launches(self):
         return int(self._lib.mfvgp_launch_count(self._h))
 
+    def attach_communicator(self, rank, world):
+        """
+        Join this object (created with ``intervals=`` = the rank's block) to the
+        ``world`` ranks of a torch.distributed job: rank 0 creates the NCCL id,
+        it is broadcast through torch.distributed, and the C library opens its
+        own communicator (mfvgp_comm_init).  E_cost / find_minimum then become
+        collective calls.
+        """
+        import torch
+        import torch.distributed as dist
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.check(self._lib.mfvgp_comm_unique_id(_ptr(ident)), "mfvgp_comm_unique_id")
+        box = [ident.tobytes()]
+        dist.broadcast_object_list(box, src=0)
+        ident = np.frombuffer(box[0], dtype=np.uint8).copy()
+        _lib.check(self._lib.mfvgp_comm_init(self._h, int(rank), int(world), _ptr(ident)),
+                   "mfvgp_comm_init")
+        self.rank, self.world = int(rank), int(world)
+
     def refine_info(self):
         """
         Bisections performed by the adaptive quadrature in the last evaluation,
@@ -202,6 +222,46 @@ class FreeEnergy(object):
             raise RuntimeError(f" {name}: Esde is not a finite number: {Esde}")
         if status & _lib.ST_EOBS:                                 # :615-618
             raise RuntimeError(f" {name}: Eobs is not a finite number: {Eobs}")
+
+    # ---- E_kl0, free_energy.py:281-336 ---------------------------------------
+    def E_kl0(self, m0, s0, output_gradients=True):
+        self._sync_params()
+        tensor_in = _is_tensor(m0)
+        m0h = _f64(m0.detach().cpu().numpy() if tensor_in else m0).reshape(self.dim_D)
+        s0h = _f64(s0.detach().cpu().numpy() if tensor_in else s0).reshape(self.dim_D)
+        want = 1 if output_gradients else 0
+        E0, status = ctypes.c_double(), ctypes.c_int32()
+        dm0 = np.empty(self.dim_D) if want else None
+        ds0 = np.empty(self.dim_D) if want else None
+        _lib.check(self._lib.mfvgp_ekl0_host(self._h, _ptr(m0h), _ptr(s0h), want,
+                                             ctypes.byref(E0), _ptr(dm0) if want else None,
+                                             _ptr(ds0) if want else None,
+                                             ctypes.byref(status)), "mfvgp_ekl0_host")
+        self._raise_on_status(status.value, E0=2.0 * E0.value)
+        if not output_gradients:
+            return E0.value, None, None
+        return E0.value, dm0, ds0
+
+    # ---- E_obs, free_energy.py:567-649 ----------------------------------------
+    def E_obs(self, mean_pts, vars_pts, output_gradients=True):
+        self._sync_params()
+        d, M = self.dim_d, self.num_M
+        mo = _f64(mean_pts).reshape(d, M)
+        so = _f64(vars_pts).reshape(d, M)
+        want = 1 if output_gradients else 0
+        Eobs, status = ctypes.c_double(), ctypes.c_int32()
+        dm = np.empty((d, M)) if want else None
+        ds = np.empty((d, M)) if want else None
+        _lib.check(self._lib.mfvgp_eobs_host(self._h, _ptr(mo), _ptr(so), want,
+                                             ctypes.byref(Eobs), _ptr(dm) if want else None,
+                                             _ptr(ds) if want else None,
+                                             ctypes.byref(status)), "mfvgp_eobs_host")
+        self._raise_on_status(status.value, Eobs=2.0 * Eobs.value)
+        if not output_gradients:
+            return Eobs.value, None, None
+        if d == 1:                                                # :637-642
+            return Eobs.value, dm.squeeze(), ds.squeeze()
+        return Eobs.value, dm, ds
 
     # ---- E_sde, free_energy.py:461-565 ---------------------------------------
     def E_sde(self, mean_pts, vars_pts, output_gradients=True):

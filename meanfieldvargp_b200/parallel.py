@@ -15,6 +15,21 @@ def shard_intervals(L, rank, world):
     return n0, n0 + base + (1 if rank < rem else 0)
 
 
+def owned_columns(M, n0, n1):
+    """
+    Columns of the mean block [D][3M+4] and of the variance block [D][2M+3]
+    whose entries of x and of the gradient rank ``[n0, n1)`` owns.  The column
+    shared by two neighbouring blocks (3*n1 / 2*n1) belongs to the right-hand
+    block; the last block also owns the columns the reference never integrates
+    (free_energy.py:168, 490, 719).
+    """
+    L = M - 1
+    last = n1 == L
+    cm = np.arange(3 * n0, (3 * M + 4) if last else 3 * n1)
+    cs = np.arange(2 * n0, (2 * M + 3) if last else 2 * n1)
+    return cm, cs
+
+
 class ShardedFreeEnergy(object):
     """E_cost of one problem evaluated by ``world`` ranks, intervals sharded."""
 

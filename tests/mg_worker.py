@@ -1,0 +1,71 @@
+"""
+Worker for the multi-GPU tests (launched by torchrun, one rank per GPU):
+sharded E_cost / find_minimum against the single-GPU evaluation of the same
+problem on the same device.  Prints "MG_OK" on success.
+"""
+import contextlib
+import io
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+from helpers import make_free_energy, rel_err, synthetic_l96  # noqa: E402
+from meanfieldvargp_b200.parallel import ShardedFreeEnergy  # noqa: E402
+
+
+def active_columns(fe, D, M):
+    n0, n1 = fe.intervals
+    L = M - 1
+    last = n1 == L
+    Nm, Ns = 3 * M + 4, 2 * M + 3
+    cm = np.arange(3 * n0, Nm if last else 3 * n1 + 1)
+    cs = np.arange(2 * n0, Ns if last else 2 * n1 + 1)
+    idx = np.concatenate([(np.arange(D)[:, None] * Nm + cm[None, :]).ravel(),
+                          D * Nm + (np.arange(D)[:, None] * Ns + cs[None, :]).ravel()])
+    return idx
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    for D, M in ((67, 9), (130, 13)):
+        g = synthetic_l96(D, M, seed=77 + D)
+        single = make_free_energy(g, device=local)
+        x = torch.tensor(g["x0"], dtype=torch.float64, device="cuda")
+        F1, g1 = single.E_cost(x)
+        sh = ShardedFreeEnergy(g, rank, world, device=local)
+        Fs, gs = sh.E_cost(x)
+        idx = active_columns(sh.local, D, M)
+        assert abs(Fs.item() - F1.item()) <= 1e-13 * abs(F1.item()), (Fs.item(), F1.item())
+        err = rel_err(gs.cpu().numpy()[idx], g1.cpu().numpy()[idx])
+        assert err <= 1e-13, err
+        # value only
+        Fv = sh.E_cost(x, output_gradients=False)
+        assert abs(Fv.item() - F1.item()) <= 1e-13 * abs(F1.item())
+        # SCG: same branch sequence and iterates on the rank's own columns
+        with contextlib.redirect_stdout(io.StringIO()):
+            x1, fx1, st1 = single.find_minimum(x, max_iter=12)
+            xs, fxs, sts = sh.local.find_minimum(x, max_iter=12)
+        assert st1["nit"] == sts["nit"] and st1["func_eval"] == sts["func_eval"]
+        assert abs(fx1 - fxs) <= 1e-10 * abs(fx1), (fx1, fxs)
+        assert rel_err(sts["fx"], st1["fx"]) <= 1e-10
+        e2 = rel_err(xs.cpu().numpy()[idx], x1.cpu().numpy()[idx])
+        assert e2 <= 1e-8, e2
+        dist.barrier()
+    if rank == 0:
+        print("MG_OK", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -103,3 +103,25 @@ def test_nonfinite_raises_like_reference():
     x[3] = np.nan
     with pytest.raises(RuntimeError, match="is not a finite number"):
         fe.E_cost(x)
+
+
+@pytest.mark.parametrize("name", ["DW", "L63", "L96_67p"])
+def test_ekl0_and_eobs_standalone(name):
+    """free_energy.py:281-336 and :567-649 as separate calls, vs the oracle."""
+    g = load_golden("eval", name)
+    fe = make_free_energy(g)
+    o = make_oracle(g)
+    D, M = fe.dim_D, fe.num_M
+    mp = g["x0"][:fe.num_mp].reshape(D, 3 * M + 4)
+    sp = np.exp(g["x0"][fe.num_mp:].reshape(D, 2 * M + 3))
+    E0, dm0, ds0 = fe.E_kl0(mp[:, 0], sp[:, 0])
+    E0o, dm0o, ds0o = o.E_kl0(mp[:, 0], sp[:, 0])
+    assert abs(E0 - g["E0"]) <= RTOL * abs(g["F"]) and abs(E0 - E0o) <= RTOL * abs(g["F"])
+    assert rel_err(dm0, dm0o) <= RTOL and rel_err(ds0, ds0o) <= RTOL
+    assert fe.E_kl0(mp[:, 0], sp[:, 0], output_gradients=False)[1] is None
+    Eobs, dm, ds = fe.E_obs(mp[o.ix_ikm], sp[o.ix_iks])
+    Eobso, dmo, dso = o.E_obs(mp[o.ix_ikm], sp[o.ix_iks])
+    assert abs(Eobs - g["Eobs"]) <= RTOL * abs(g["F"])
+    assert rel_err(np.atleast_2d(dm), dmo) <= RTOL and rel_err(np.atleast_2d(ds), dso) <= RTOL
+    if fe.dim_d == 1:
+        assert dm.ndim == 1           # squeezed like the reference (:637-642)
