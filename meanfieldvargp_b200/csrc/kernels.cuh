@@ -25,6 +25,10 @@ namespace mfvgp {
 // [42][16] table of the fixed 42-node rule (tables.h)
 __constant__ double c_tab[kNodes * kTabStride];
 
+// split rule (tables.h): rational part on the 42 GK nodes, polynomial part on 7 GL nodes
+__constant__ double c_rat[kNodes * kTabStride];
+__constant__ double c_gl[kGL * kTabStride];
+
 constexpr int kPartStride = 8;   // doubles per (interval, dim-tile) partial
 // partial slots (raw sums; scaled by h = dt/4 in guard_reduce_kernel)
 //  0: sum_i sum_r v_r E_i / Sigma_i         (weighted energy)
@@ -192,6 +196,191 @@ esde_l96_kernel(const EsdeArgs a) {
     const double KE = accE * Sig;                              // raw sum_r v_r E_i
     double red[7] = {accE, KE * KE, eE1, kgE * kgE, eS1,
                      kgS[0] * kgS[0] + kgS[1] * kgS[1] + kgS[2] * kgS[2], ownS1 * ownS1};
+    if (!is_out)
+#pragma unroll
+        for (int i = 0; i < 7; ++i) red[i] = 0.0;
+    block_sum<7, TE>(red, sh_red);
+    if (threadIdx.x == 0) {
+        double *p = a.part + (int64_t)blockIdx.x * kPartStride;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) p[i] = red[i];
+        p[7] = 0.0;
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// Lorenz 96, split rule (default).  Same cell/tile mapping and same outputs as
+// esde_l96_kernel, about 3.5x fewer FP64 instructions:
+//   E_i = [R^2 + sb u^2 + b^2 su + su sb]  coupled polynomial, degree <= 12
+//       + [s_i + q_i]                      own polynomial, integrated in closed form
+//       + q_i^2/(4 s_i)                    rational, own dimension only
+// (A) the rational part and its d/dS run over scipy's 42 Kronrod nodes with no
+//     neighbour traffic; they also carry quad_vec's Kronrod-minus-Gauss error
+//     estimate (the polynomial parts contribute nothing to it);
+// (B) the coupled polynomial part runs over 7 Gauss-Legendre nodes (exact to
+//     degree 13) with the shared-memory neighbour exchange of the 42-node kernel.
+// GK21 integrates those polynomials exactly as well, so both kernels return the
+// reference's value up to rounding (tests/test_gpu_parity.py compares them).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp3(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);          // |e| <= 2^-20
+    const double t = fma(e, e, e);             // e + e^2  -> error e^3 = 2^-60
+    return fma(r, t, r);                       // measured max rel. error 2.2e-16 (tools/rcp_test.cu)
+}
+
+template <int TE>
+__global__ void __launch_bounds__(TE)
+esde_l96_split_kernel(const EsdeArgs a) {
+    constexpr int TD = TE - 6;
+    __shared__ double sh_m[TE], sh_s[TE];
+    __shared__ double sh_A[TE], sh_B[TE], sh_C[TE], sh_Dv[TE];
+    __shared__ double sh_red[7 * (TE / 32)];
+
+    const int e = threadIdx.x;
+    const int tile = blockIdx.x % a.ntiles;
+    const int n = a.n_begin + blockIdx.x / a.ntiles;
+    const int d0 = tile * TD;
+    const int D = a.D;
+    int j = (d0 - 3 + e) % D;
+    if (j < 0) j += D;
+    const bool has_energy = (e >= 2) && (e <= TE - 2);
+    const bool is_out = (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
+
+    const double ti = a.obs_times[n], tj = a.obs_times[n + 1];
+    const double dt = fabs(tj - ti);
+    const double inv_dt = 1.0 / dt;
+
+    const double *mp = a.mean + (int64_t)j * a.ldm + 3 * (int64_t)n;
+    const double *sp = a.vars + (int64_t)j * a.lds + 2 * (int64_t)n;
+    const double P0 = mp[0], P1 = mp[1], P2 = mp[2], P3 = mp[3];
+    double S0 = sp[0], S1 = sp[1], S2 = sp[2];
+    if (a.log_vars) { S0 = exp(S0); S1 = exp(S1); S2 = exp(S2); }
+    const double Sig = a.sigma[j];
+    const double inv_sig = 1.0 / Sig;
+    const double theta = a.theta[0];
+
+    // ---- (A) rational part, own dimension, 42 Kronrod nodes -------------------
+    // Per panel: Kronrod sums K (all 21 nodes) and embedded Gauss sums G (the 10
+    // odd nodes); quad_vec's raw error estimate is |K - G| (its absolute accuracy
+    // here, ~1e-16 |K|, is far below the ~1e-9 |K| level the guard decides at).
+    // Fully unrolled so every table entry is a constant-bank operand of its FMA.
+    double aE = 0.0, eE1 = 0.0, eE2 = 0.0, eS1 = 0.0, eS2 = 0.0;
+    double aSv[3] = {0, 0, 0}, aSd[3] = {0, 0, 0};
+    if (is_out) {
+        // s(tau) = a0 + a1 tau + a2 tau^2 ; q(tau) = ds/dt - Sigma = b0 + b1 tau
+        const double a0 = S0, a1 = -3.0 * S0 + 4.0 * S1 - S2, a2 = 2.0 * (S0 - 2.0 * S1 + S2);
+        const double b0 = a1 * inv_dt - Sig, b1 = 2.0 * a2 * inv_dt;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            double kE = 0.0, gE = 0.0;
+            double kSv[3] = {0, 0, 0}, kSd[3] = {0, 0, 0}, gSv[3] = {0, 0, 0}, gSd[3] = {0, 0, 0};
+#pragma unroll
+            for (int r = 0; r < kNodesPerPanel; ++r) {
+                const double *T = c_rat + (p * kNodesPerPanel + r) * kTabStride;
+                const double tau = T[R_TAU];
+                const double s = fma(fma(a2, tau, a1), tau, a0);
+                const double qq = fma(b1, tau, b0);
+                const double qi = qq * fast_rcp3(s);   // q / s
+                const double t = qq * qi;              // q^2 / s   (= 4 rat)
+                const double qi2 = qi * qi;            // (q/s)^2   (= -4 d rat/d s)
+                kE = fma(T[R_V], t, kE);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    kSv[k] = fma(T[R_VB + k], qi2, kSv[k]);
+                    kSd[k] = fma(T[R_VD + k], qi, kSd[k]);
+                }
+                if (r & 1) {
+                    gE = fma(T[R_W], t, gE);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        gSv[k] = fma(T[R_WB + k], qi2, gSv[k]);
+                        gSd[k] = fma(T[R_WD + k], qi, gSd[k]);
+                    }
+                }
+            }
+            const double dE = 0.25 * (kE - gE);
+            double eS = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double kg = fma(0.5 * inv_dt, kSd[k] - gSd[k], -0.25 * (kSv[k] - gSv[k]));
+                eS = fma(kg, kg, eS);
+                aSv[k] += kSv[k];
+                aSd[k] += kSd[k];
+            }
+            aE += kE;
+            if (p == 0) { eE1 = dE * dE; eS1 = eS; } else { eE2 = dE * dE; eS2 = eS; }
+        }
+    }
+
+    // ---- (B) coupled polynomial part, 7 Gauss-Legendre nodes -------------------
+    double accM[4] = {0, 0, 0, 0}, accS[3] = {0, 0, 0}, accE = 0.0;
+#pragma unroll
+    for (int g = 0; g < kGL; ++g) {
+        const double *T = c_gl + g * kTabStride;
+        const double m = P0 * T[T_B3] + P1 * T[T_B3 + 1] + P2 * T[T_B3 + 2] + P3 * T[T_B3 + 3];
+        const double dm = (P0 * T[T_DB3] + P1 * T[T_DB3 + 1] + P2 * T[T_DB3 + 2]
+                           + P3 * T[T_DB3 + 3]) * inv_dt;
+        const double s = S0 * T[T_B2] + S1 * T[T_B2 + 1] + S2 * T[T_B2 + 2];
+        sh_m[e] = m;
+        sh_s[e] = s;
+        __syncthreads();
+        double own_m = 0.0;
+        if (has_energy) {
+            const double ma = sh_m[e + 1], mb = sh_m[e - 1], mc = sh_m[e - 2];
+            const double sa = sh_s[e + 1], sb = sh_s[e - 1], sc = sh_s[e - 2];
+            const double u = ma - mc, su = sa + sc;
+            const double R = fma(u, mb, theta - m) - dm;
+            const double t1 = sb * u, t2 = mb * su;
+            const double Ec = fma(R, R, fma(t1, u, fma(t2, mb, su * sb)));
+            const double w = T[T_V] * inv_sig, w2 = w + w;
+            const double wR2 = w2 * R;
+            sh_A[e] = fma(wR2, mb, w2 * t1);
+            sh_B[e] = fma(wR2, u, w2 * t2);
+            sh_C[e] = w * fma(mb, mb, sb);
+            sh_Dv[e] = w * fma(u, u, su);
+            own_m = -wR2;
+            accE = fma(w, Ec, accE);
+        }
+        __syncthreads();
+        if (is_out) {
+            const double Gm = own_m + sh_A[e - 1] + sh_B[e + 1] - sh_A[e + 2];
+            const double Gs = sh_C[e - 1] + sh_Dv[e + 1] + sh_C[e + 2];
+            const double Hm = own_m * inv_dt;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                accM[k] += Gm * T[T_B3 + k] + Hm * T[T_DB3 + k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) accS[k] = fma(Gs, T[T_B2 + k], accS[k]);
+        }
+    }
+
+    // ---- epilogue: closed-form own polynomial, scaling, outputs ----------------
+    // All "K-sums" below use the normalisation of the 42-node kernel
+    // (integral = (dt/4) * Ksum) so guard_reduce_kernel serves both.
+    const double four_inv_dt = 4.0 * inv_dt;
+    // int (s_i + q_i) dt = dt (S0 + 4 S1 + S2)/6 + (S2 - S0) - Sigma dt
+    const double own_poly = dt * (S0 + 4.0 * S1 + S2) * (1.0 / 6.0) + (S2 - S0) - Sig * dt;
+    const double ksum_E = 0.25 * aE + 4.0 * accE * Sig + four_inv_dt * own_poly;   // raw, this i
+    double kS[3];                         // rational d/dS K-sums of the own slot
+#pragma unroll
+    for (int k = 0; k < 3; ++k) kS[k] = fma(0.5 * inv_dt, aSd[k], -0.25 * aSv[k]);
+    if (is_out && a.dm_out != nullptr) {
+        double *om = a.dm_out + ((int64_t)n * D + j) * 4;
+        double *os = a.ds_out + ((int64_t)n * D + j) * 3;
+        const double sc_gl = 0.5 * dt;                 // 1/2 * interval length (GL weights sum to 1)
+        const double sc_gk = 0.5 * 0.25 * dt * inv_sig;
+        const double polyS[3] = {dt * (1.0 / 6.0) - 1.0, dt * (4.0 / 6.0), dt * (1.0 / 6.0) + 1.0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) om[k] = sc_gl * accM[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            os[k] = sc_gl * accS[k] + sc_gk * kS[k] + 0.5 * inv_sig * polyS[k];
+    }
+    const double own1 = kS[1] + four_inv_dt * (dt * (4.0 / 6.0));    // own-slot k=1 K-sum
+    double red[7] = {ksum_E * inv_sig, ksum_E * ksum_E, eE1, eE2, eS1, eS2, own1 * own1};
     if (!is_out)
 #pragma unroll
         for (int i = 0; i < 7; ++i) red[i] = 0.0;

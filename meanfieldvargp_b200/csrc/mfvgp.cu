@@ -2,6 +2,7 @@
 // Pure CUDA runtime: no torch types cross this boundary.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -37,6 +38,7 @@ struct mfvgp_handle {
     int system = 0, D = 0, M = 0, d = 0, device = 0;
     int L = 0, n_begin = 0, n_end = 0, Nm = 0, Ns = 0, ntheta = 0;
     int te = 64, ntiles = 1;
+    int rule = 1;     // 1: split rule (default), 0: 42-node coupled rule (MFVGP_RULE=gk42)
     bool have_sde = false, have_prior = false, have_obs = false;
     double eobs_const = 0.0;
     // problem data (device)
@@ -121,6 +123,15 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     double tab[kNodes * kTabStride];
     build_fixed_table(tab);
     CK(cudaMemcpyToSymbol(c_tab, tab, sizeof(tab)));
+    build_rational_table(tab);
+    CK(cudaMemcpyToSymbol(c_rat, tab, sizeof(tab)));
+    {
+        double gl[kGL * kTabStride];
+        build_gl_table(gl);
+        CK(cudaMemcpyToSymbol(c_gl, gl, sizeof(gl)));
+        const char *rule = getenv("MFVGP_RULE");
+        h->rule = (rule && std::string(rule) == "gk42") ? 0 : 1;
+    }
     {
         double gx[kNodesPerPanel], gv[kNodesPerPanel], gw[10];
         for (int r = 0; r < kNodesPerPanel; ++r) { gx[r] = (double)gk21_x(r); gv[r] = (double)gk21_v(r); }
@@ -243,9 +254,15 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         case MFVGP_SYS_L63: esde_small_kernel<2><<<nl, 64, 0, st>>>(a); break;
         default: {
             const unsigned grid = (unsigned)nl * h->ntiles;
-            if (h->te == 32) esde_l96_kernel<32><<<grid, 32, 0, st>>>(a);
-            else if (h->te == 64) esde_l96_kernel<64><<<grid, 64, 0, st>>>(a);
-            else esde_l96_kernel<128><<<grid, 128, 0, st>>>(a);
+            if (h->rule == 0) {
+                if (h->te == 32) esde_l96_kernel<32><<<grid, 32, 0, st>>>(a);
+                else if (h->te == 64) esde_l96_kernel<64><<<grid, 64, 0, st>>>(a);
+                else esde_l96_kernel<128><<<grid, 128, 0, st>>>(a);
+            } else {
+                if (h->te == 32) esde_l96_split_kernel<32><<<grid, 32, 0, st>>>(a);
+                else if (h->te == 64) esde_l96_split_kernel<64><<<grid, 64, 0, st>>>(a);
+                else esde_l96_split_kernel<128><<<grid, 128, 0, st>>>(a);
+            }
         }
     }
     h->launches++;

@@ -12,6 +12,8 @@
 // are universal constants; d/dt = (1/dt) d/dtau.
 #pragma once
 
+#include <cmath>
+
 namespace mfvgp {
 
 constexpr int kNodesPerPanel = 21;
@@ -101,6 +103,74 @@ inline void build_fixed_table(double *tab /*[42][16]*/) {
             long double c = (r & 1) ? v - gk21_w((r - 1) / 2) : v;
             fill_row(tab + (p * kNodesPerPanel + r) * kTabStride, tau, v, c);
         }
+}
+
+// ---------------------------------------------------------------------------
+// Split rule (kernels.cuh, esde_l96_split_kernel).  Every integrand of the
+// path is  polynomial(t) + terms in q/s and (q/s)^2  with q linear and s
+// quadratic in t.  GK21 (degree 31) and its embedded Gauss-10
+// (degree 19) integrate the polynomial part (degree <= 12 for L96) exactly, so
+// that part may be integrated by ANY exact rule -- here 7-point Gauss-Legendre
+// on the whole interval (exact to degree 13) -- while the rational part keeps
+// scipy's 42 Kronrod nodes, which is what fixes the result to the reference's.
+// ---------------------------------------------------------------------------
+constexpr int kGL = 7;
+
+// table of the rational part, per GK node: tau, v, v*B2[3], v*dB2[3], and -- on the
+// odd nodes, which carry the embedded Gauss-10 rule -- w, w*B2[3], w*dB2[3]
+constexpr int R_TAU = 0, R_V = 1, R_VB = 2, R_VD = 5, R_W = 8, R_WB = 9, R_WD = 12;
+
+inline void build_rational_table(double *tab /*[42][16]*/) {
+    for (int p = 0; p < 2; ++p)
+        for (int r = 0; r < kNodesPerPanel; ++r) {
+            long double tau = 0.25L + 0.5L * p + 0.25L * gk21_x(r);
+            long double v = gk21_v(r);
+            long double w = (r & 1) ? gk21_w((r - 1) / 2) : 0.0L;
+            double *row = tab + (p * kNodesPerPanel + r) * kTabStride;
+            row[R_TAU] = (double)tau;
+            row[R_V] = (double)v;
+            row[R_W] = (double)w;
+            for (int k = 0; k < 3; ++k) {
+                long double b, d;
+                lagrange_unit(3, k, tau, &b, &d);
+                row[R_VB + k] = (double)(v * b);
+                row[R_VD + k] = (double)(v * d);
+                row[R_WB + k] = (double)(w * b);
+                row[R_WD + k] = (double)(w * d);
+            }
+            row[15] = 0.0;
+        }
+}
+
+// n-point Gauss-Legendre on [-1,1] by Newton iteration in long double
+inline void gauss_legendre(int n, long double *x, long double *w) {
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int i = 0; i < n; ++i) {
+        long double z = cosl(pi * (i + 0.75L) / (n + 0.5L));
+        long double pp = 0.0L;
+        for (int it = 0; it < 100; ++it) {
+            long double p1 = 1.0L, p2 = 0.0L;
+            for (int j = 1; j <= n; ++j) {
+                long double p3 = p2;
+                p2 = p1;
+                p1 = ((2.0L * j - 1.0L) * z * p2 - (j - 1.0L) * p3) / j;
+            }
+            pp = n * (z * p1 - p2) / (z * z - 1.0L);
+            long double dz = p1 / pp;
+            z -= dz;
+            if (fabsl(dz) < 1e-19L) break;
+        }
+        x[i] = z;
+        w[i] = 2.0L / ((1.0L - z * z) * pp * pp);
+    }
+}
+
+// table of the polynomial part: same columns as the fixed table, T_V = weight on [0,1]
+inline void build_gl_table(double *tab /*[kGL][16]*/) {
+    long double x[kGL], w[kGL];
+    gauss_legendre(kGL, x, w);
+    for (int g = 0; g < kGL; ++g)
+        fill_row(tab + g * kTabStride, 0.5L + 0.5L * x[g], 0.5L * w[g], 0.0L);
 }
 
 }  // namespace mfvgp

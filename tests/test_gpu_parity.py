@@ -125,3 +125,22 @@ def test_ekl0_and_eobs_standalone(name):
     assert rel_err(np.atleast_2d(dm), dmo) <= RTOL and rel_err(np.atleast_2d(ds), dso) <= RTOL
     if fe.dim_d == 1:
         assert dm.ndim == 1           # squeezed like the reference (:637-642)
+
+
+def test_split_rule_equals_42_node_rule(monkeypatch):
+    """
+    The default L96 kernel integrates the polynomial part of the integrands on 7
+    Gauss-Legendre nodes and the rational part on scipy's 42 Kronrod nodes; the
+    node-for-node 42-point kernel (MFVGP_RULE=gk42) must give the same numbers.
+    """
+    for name in ("L96_40", "L96_67p", "L96_5_irregular"):
+        g = load_golden("eval", name)
+        monkeypatch.setenv("MFVGP_RULE", "gk42")
+        fe42 = make_free_energy(g)
+        F42, g42 = fe42.E_cost(g["x0"])
+        monkeypatch.delenv("MFVGP_RULE")
+        fes = make_free_energy(g)
+        Fs, gs = fes.E_cost(g["x0"])
+        assert abs(Fs - F42) <= 1e-13 * abs(F42)
+        assert rel_err(gs, g42) <= 1e-12
+        assert abs(F42 - g["F"]) <= RTOL * abs(g["F"]) and rel_err(g42, g["grad"]) <= RTOL
