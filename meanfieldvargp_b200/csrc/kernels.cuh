@@ -29,13 +29,17 @@ __constant__ double c_tab[kNodes * kTabStride];
 __constant__ double c_rat[kNodes * kTabStride];
 __constant__ double c_gl[kGL * kTabStride];
 
-constexpr int kPartStride = 8;   // doubles per (interval, dim-tile) partial
+__constant__ double c_gkx_main[kNodesPerPanel];     // Kronrod abscissae (descending)
+__constant__ double c_vxB[kNodes], c_vxD[kNodes], c_m1poly[4];   // tables.h build_moment_table
+
+constexpr int kPartStride = 12;  // doubles per (interval, dim-tile) partial
 // partial slots (raw sums; scaled by h = dt/4 in guard_reduce_kernel)
 //  0: sum_i sum_r v_r E_i / Sigma_i         (weighted energy)
 //  1: sum_i (sum_r v_r E_i)^2               (|I_E|^2 for quad_vec's tol)
 //  2,3: sum_i (sum_r c_r E_i)^2, panels 1,2 (Kronrod - Gauss, quad_vec's err)
 //  4,5: sum_i sum_k (sum_r c_r dS_own_ik)^2, panels 1,2
-//  6: sum_i (sum_r v_r dS_own_i1)^2         (lower bound of |I_dS|^2)
+//  6: sum_i sum_k (sum_r v_r dS_own_ik)^2   (own-slot part: lower bound of |I_dS|^2)
+//  7,8: sum_i (sum_r v_r x_r dS_own_i0)^2, panels 1,2 (lower bound of scipy's dabs^2)
 
 struct EsdeArgs {
     const double *mean;     // [D][ldm]
@@ -237,7 +241,7 @@ esde_l96_split_kernel(const EsdeArgs a) {
     constexpr int TD = TE - 6;
     __shared__ double sh_m[TE], sh_s[TE];
     __shared__ double sh_A[TE], sh_B[TE], sh_C[TE], sh_Dv[TE];
-    __shared__ double sh_red[7 * (TE / 32)];
+    __shared__ double sh_red[9 * (TE / 32)];
 
     const int e = threadIdx.x;
     const int tile = blockIdx.x % a.ntiles;
@@ -267,7 +271,7 @@ esde_l96_split_kernel(const EsdeArgs a) {
     // odd nodes); quad_vec's raw error estimate is |K - G| (its absolute accuracy
     // here, ~1e-16 |K|, is far below the ~1e-9 |K| level the guard decides at).
     // Fully unrolled so every table entry is a constant-bank operand of its FMA.
-    double aE = 0.0, eE1 = 0.0, eE2 = 0.0, eS1 = 0.0, eS2 = 0.0;
+    double aE = 0.0, eE1 = 0.0, eE2 = 0.0, eS1 = 0.0, eS2 = 0.0, m1S1 = 0.0, m1S2 = 0.0;
     double aSv[3] = {0, 0, 0}, aSd[3] = {0, 0, 0};
     if (is_out) {
         // s(tau) = a0 + a1 tau + a2 tau^2 ; q(tau) = ds/dt - Sigma = b0 + b1 tau
@@ -275,7 +279,7 @@ esde_l96_split_kernel(const EsdeArgs a) {
         const double b0 = a1 * inv_dt - Sig, b1 = 2.0 * a2 * inv_dt;
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            double kE = 0.0, gE = 0.0;
+            double kE = 0.0, gE = 0.0, mSv = 0.0, mSd = 0.0;
             double kSv[3] = {0, 0, 0}, kSd[3] = {0, 0, 0}, gSv[3] = {0, 0, 0}, gSd[3] = {0, 0, 0};
 #pragma unroll
             for (int r = 0; r < kNodesPerPanel; ++r) {
@@ -292,6 +296,8 @@ esde_l96_split_kernel(const EsdeArgs a) {
                     kSv[k] = fma(T[R_VB + k], qi2, kSv[k]);
                     kSd[k] = fma(T[R_VD + k], qi, kSd[k]);
                 }
+                mSv = fma(c_vxB[p * kNodesPerPanel + r], qi2, mSv);
+                mSd = fma(c_vxD[p * kNodesPerPanel + r], qi, mSd);
                 if (r & 1) {
                     gE = fma(T[R_W], t, gE);
 #pragma unroll
@@ -311,7 +317,11 @@ esde_l96_split_kernel(const EsdeArgs a) {
                 aSd[k] += kSd[k];
             }
             aE += kE;
-            if (p == 0) { eE1 = dE * dE; eS1 = eS; } else { eE2 = dE * dE; eS2 = eS; }
+            // first moment of the own-slot k=0 element of dS about the panel centre
+            const double m1 = fma(0.5 * inv_dt, mSd, -0.25 * mSv)
+                              + fma(c_m1poly[2 * p + 1], inv_dt, c_m1poly[2 * p]);
+            if (p == 0) { eE1 = dE * dE; eS1 = eS; m1S1 = m1 * m1; }
+            else { eE2 = dE * dE; eS2 = eS; m1S2 = m1 * m1; }
         }
     }
 
@@ -379,17 +389,25 @@ esde_l96_split_kernel(const EsdeArgs a) {
         for (int k = 0; k < 3; ++k)
             os[k] = sc_gl * accS[k] + sc_gk * kS[k] + 0.5 * inv_sig * polyS[k];
     }
-    const double own1 = kS[1] + four_inv_dt * (dt * (4.0 / 6.0));    // own-slot k=1 K-sum
-    double red[7] = {ksum_E * inv_sig, ksum_E * ksum_E, eE1, eE2, eS1, eS2, own1 * own1};
+    double own2 = 0.0;                                    // own-slot K-sums, k = 0..2
+    {
+        const double polyK[3] = {four_inv_dt * (dt * (1.0 / 6.0) - 1.0), four_inv_dt * dt * (4.0 / 6.0),
+                                 four_inv_dt * (dt * (1.0 / 6.0) + 1.0)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double o = kS[k] + polyK[k];
+            own2 = fma(o, o, own2);
+        }
+    }
+    double red[9] = {ksum_E * inv_sig, ksum_E * ksum_E, eE1, eE2, eS1, eS2, own2, m1S1, m1S2};
     if (!is_out)
 #pragma unroll
-        for (int i = 0; i < 7; ++i) red[i] = 0.0;
-    block_sum<7, TE>(red, sh_red);
+        for (int i = 0; i < 9; ++i) red[i] = 0.0;
+    block_sum<9, TE>(red, sh_red);
     if (threadIdx.x == 0) {
         double *p = a.part + (int64_t)blockIdx.x * kPartStride;
 #pragma unroll
-        for (int i = 0; i < 7; ++i) p[i] = red[i];
-        p[7] = 0.0;
+        for (int i = 0; i < 9; ++i) p[i] = red[i];
     }
 }
 
@@ -407,7 +425,7 @@ esde_small_kernel(const EsdeArgs a) {
     constexpr int V_E = 0, V_DM = 1, V_DS = V_DM + 4 * D, V_RE = V_DS + 3 * D,
                   V_RS = V_RE + D;
     __shared__ double vals[NV][kNodes];
-    __shared__ double sums[NV][4];                       // K1, K2, KG1, KG2
+    __shared__ double sums[NV][6];                       // K1, K2, KG1, KG2, M1 (panels 1, 2)
 
     const int n = a.n_begin + blockIdx.x;
     const int q = threadIdx.x;
@@ -465,7 +483,7 @@ esde_small_kernel(const EsdeArgs a) {
     }
     __syncthreads();
     if (q < NV) {
-        double K1 = 0.0, K2 = 0.0, G1 = 0.0, G2 = 0.0;
+        double K1 = 0.0, K2 = 0.0, G1 = 0.0, G2 = 0.0, M1 = 0.0, M2 = 0.0;
         for (int r = 0; r < kNodesPerPanel; ++r) {
             const double v = c_tab[r * kTabStride + T_V], c = c_tab[r * kTabStride + T_C];
             const double f1 = vals[q][r], f2 = vals[q][kNodesPerPanel + r];
@@ -473,8 +491,12 @@ esde_small_kernel(const EsdeArgs a) {
             K2 = fma(v, f2, K2);
             G1 = fma(c, f1, G1);
             G2 = fma(c, f2, G2);
+            const double vx = v * c_gkx_main[r];          // first moment about the panel centre
+            M1 = fma(vx, f1, M1);
+            M2 = fma(vx, f2, M2);
         }
         sums[q][0] = K1; sums[q][1] = K2; sums[q][2] = G1; sums[q][3] = G2;
+        sums[q][4] = M1; sums[q][5] = M2;
         const double scale = 0.5 * (0.25 * dt);
         if (a.dm_out != nullptr) {
             if (q >= V_DM && q < V_DS)
@@ -485,7 +507,7 @@ esde_small_kernel(const EsdeArgs a) {
     }
     __syncthreads();
     if (q == 0) {
-        double p[kPartStride] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double p[kPartStride] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         p[0] = sums[V_E][0] + sums[V_E][1];
         for (int i = 0; i < D; ++i) {
             const double KE = sums[V_RE + i][0] + sums[V_RE + i][1];
@@ -497,8 +519,12 @@ esde_small_kernel(const EsdeArgs a) {
                 p[4] += sv[2] * sv[2];
                 p[5] += sv[3] * sv[3];
             }
-            const double KS = sums[V_RS + 3 * i + 1][0] + sums[V_RS + 3 * i + 1][1];
-            p[6] += KS * KS;
+            for (int k = 0; k < 3; ++k) {
+                const double KS = sums[V_RS + 3 * i + k][0] + sums[V_RS + 3 * i + k][1];
+                p[6] += KS * KS;
+            }
+            p[7] += sums[V_RS + 3 * i][4] * sums[V_RS + 3 * i][4];
+            p[8] += sums[V_RS + 3 * i][5] * sums[V_RS + 3 * i][5];
         }
         double *out = a.part + (int64_t)blockIdx.x * kPartStride;
         for (int i = 0; i < kPartStride; ++i) out[i] = p[i];
@@ -527,22 +553,30 @@ guard_reduce_kernel(const GuardArgs a) {
     const int lane = threadIdx.x & 31;
     const int n = a.n_begin + warp;
     if (n >= a.n_end) return;
-    double p[7] = {0, 0, 0, 0, 0, 0, 0};
+    double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int t = lane; t < a.ntiles; t += 32) {
         const double *src = a.part + ((int64_t)warp * a.ntiles + t) * kPartStride;
 #pragma unroll
-        for (int i = 0; i < 7; ++i) p[i] += src[i];
+        for (int i = 0; i < 9; ++i) p[i] += src[i];
     }
 #pragma unroll
-    for (int i = 0; i < 7; ++i) p[i] = warp_sum(p[i]);
+    for (int i = 0; i < 9; ++i) p[i] = warp_sum(p[i]);
     if (lane == 0) {
         const double dt = fabs(a.obs_times[n + 1] - a.obs_times[n]);
         const double h = 0.25 * dt;
         a.esde_n[n] = 0.5 * h * p[0];
         const double tolE = fmax(1.0e-6, 1.0e-6 * h * sqrt(p[1]));
         const double tolS = fmax(1.0e-6, 1.0e-6 * h * sqrt(p[6]));
-        const double ubE = 202.0 * h * (sqrt(p[2]) + sqrt(p[3]));
-        const double ubS = 202.0 * h * (sqrt(p[4]) + sqrt(p[5]));
+        // scipy: err_p = dabs_p min(1, (200 e_p/dabs_p)^1.5), e_p = |(K-G) h|.  It never
+        // exceeds 200 e_p, and with a lower bound dl_p <= dabs_p it never exceeds
+        // (200 e_p)^1.5 / sqrt(dl_p) once 200 e_p <= dl_p.  2 % margin on e_p.
+        const double ubE = 204.0 * h * (sqrt(p[2]) + sqrt(p[3]));
+        double ubS = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const double e200 = 204.0 * h * sqrt(p[4 + k]), dl = h * sqrt(p[7 + k]);
+            ubS += (e200 <= dl && dl > 0.0) ? e200 * sqrt(e200 / dl) : e200;
+        }
         int32_t f = 0;
         if (!(ubE < 0.125 * tolE)) f |= 1;
         if (!(ubS < 0.125 * tolS)) f |= 2;

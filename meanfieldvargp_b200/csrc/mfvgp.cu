@@ -129,6 +129,13 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         double gl[kGL * kTabStride];
         build_gl_table(gl);
         CK(cudaMemcpyToSymbol(c_gl, gl, sizeof(gl)));
+        double vxB[kNodes], vxD[kNodes], m1poly[4], gkx[kNodesPerPanel];
+        build_moment_table(vxB, vxD, m1poly);
+        for (int r = 0; r < kNodesPerPanel; ++r) gkx[r] = (double)gk21_x(r);
+        CK(cudaMemcpyToSymbol(c_vxB, vxB, sizeof(vxB)));
+        CK(cudaMemcpyToSymbol(c_vxD, vxD, sizeof(vxD)));
+        CK(cudaMemcpyToSymbol(c_m1poly, m1poly, sizeof(m1poly)));
+        CK(cudaMemcpyToSymbol(c_gkx_main, gkx, sizeof(gkx)));
         const char *rule = getenv("MFVGP_RULE");
         h->rule = (rule && std::string(rule) == "gk42") ? 0 : 1;
     }

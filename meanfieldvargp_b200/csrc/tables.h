@@ -118,7 +118,28 @@ constexpr int kGL = 7;
 
 // table of the rational part, per GK node: tau, v, v*B2[3], v*dB2[3], and -- on the
 // odd nodes, which carry the embedded Gauss-10 rule -- w, w*B2[3], w*dB2[3]
+// [15]: unused.  A second small table carries v*x*B2_0 and v*x*dB2_0 (x = node
+// position in [-1,1] within its panel), used for the lower bound of scipy's
+// "dabs" (sum_r v_r |f_r - mean| >= |sum_r v_r x_r f_r| because sum v_r x_r = 0).
 constexpr int R_TAU = 0, R_V = 1, R_VB = 2, R_VD = 5, R_W = 8, R_WB = 9, R_WD = 12;
+
+inline void build_moment_table(double *vxB /*[42]*/, double *vxD /*[42]*/,
+                               double *poly /*[2][2]: per panel sum vxB, sum vxD*/) {
+    for (int p = 0; p < 2; ++p) {
+        long double s1 = 0.0L, s2 = 0.0L;
+        for (int r = 0; r < kNodesPerPanel; ++r) {
+            long double x = gk21_x(r), tau = 0.25L + 0.5L * p + 0.25L * x, b, d;
+            lagrange_unit(3, 0, tau, &b, &d);
+            long double v = gk21_v(r);
+            vxB[p * kNodesPerPanel + r] = (double)(v * x * b);
+            vxD[p * kNodesPerPanel + r] = (double)(v * x * d);
+            s1 += v * x * b;
+            s2 += v * x * d;
+        }
+        poly[2 * p] = (double)s1;
+        poly[2 * p + 1] = (double)s2;
+    }
+}
 
 inline void build_rational_table(double *tab /*[42][16]*/) {
     for (int p = 0; p < 2; ++p)
