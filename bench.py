@@ -46,6 +46,10 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 FLOP_PER_CELL = 4620.0      # 110 FLOP/(dim,node) x 42 nodes
 BYTE_PER_CELL = 96.0        # 40 B read + 56 B written per cell
+# What the split-rule kernel actually executes per cell (static SASS count of the fully
+# unrolled esde_l96_split_kernel, `cuobjdump -sass`: 1054 DFMA + 291 DMUL + 222 DADD):
+EXEC_FP64_INST_PER_CELL = 1567.0
+EXEC_FLOP_PER_CELL = 2.0 * 1054.0 + 291.0 + 222.0
 METRIC = "free-energy+gradient evals/sec (L96 D=500)"
 WORKLOAD = "L96 D=500 d=125 M=16 (example_500D.ipynb), synthetic state seed 8192"
 
@@ -143,9 +147,18 @@ def roofline(D, L, kernel_ms, fp64_peak_tf, hbm_peak_gbs, traffic=None):
             "frac": tf / fp64_peak_tf, "traffic": traffic,
             "peak_source": "DFMA micro-benchmark measured in this run (mfvgp_fp64_peak); "
                            "MEASURED_PEAKS.json has no FP64 entry",
-            "kernel": "esde_l96_kernel", "kernel_ms": kernel_ms,
+            "kernel": "esde_l96_split_kernel", "kernel_ms": kernel_ms,
             "algorithmic_flop_per_launch": FLOP_PER_CELL * cells,
             "algorithmic_bytes_per_launch": BYTE_PER_CELL * cells,
+            "executed": {
+                "note": "frac is on the ALGORITHMIC FLOPs of SURVEY 8(d) (42-node rule); the "
+                        "split-rule kernel executes fewer (DESIGN.md 4), so frac may exceed 1. "
+                        "fp64_pipe_frac = executed FP64 instructions / (time x measured DFMA "
+                        "issue rate) is the utilisation of the pipe that bounds the kernel.",
+                "flop_per_launch": EXEC_FLOP_PER_CELL * cells,
+                "tflops": EXEC_FLOP_PER_CELL * cells / (kernel_ms * 1e-3) * 1e-12,
+                "fp64_pipe_frac": EXEC_FP64_INST_PER_CELL * cells / (kernel_ms * 1e-3)
+                                  / (fp64_peak_tf * 0.5e12)},
             "hbm": {"achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s",
                     "frac": gbs / hbm_peak_gbs, "peak_source": "MEASURED_PEAKS.json hbm_gbs"}}
 
@@ -311,7 +324,6 @@ def main():
     clocks.start()
     ms_total = time_steps(torch, step_dev, args.steps, 0, flush)
     launches = fe.kernel_launches - launches_w
-    clock_info = clocks.stop()
     tms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -331,6 +343,7 @@ def main():
     twall = torch.tensor([wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(twall, op=dist.ReduceOp.MAX)
+    clock_info = clocks.stop()          # sampled over the device-timed and the e2e regions
     e2e = {"value": world * args.steps / twall.item(), "unit": "evals/s",
            "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 8 + 36),
            "api": "FreeEnergy.E_cost(numpy x) -> (float, numpy grad); wall clock, "

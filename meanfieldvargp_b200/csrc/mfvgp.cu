@@ -39,6 +39,9 @@ struct mfvgp_handle {
     int L = 0, n_begin = 0, n_end = 0, Nm = 0, Ns = 0, ntheta = 0;
     int te = 64, ntiles = 1;
     int rule = 1;     // 1: split rule (default), 0: 42-node coupled rule (MFVGP_RULE=gk42)
+    // fused E_cost kernel (L96, split rule): TE x TN tile, grid = fntn * fntiles
+    int fte = 64, ftn = 1, fntiles = 1, fntn = 1, fused = 0;
+    double *fedge_m = nullptr, *fedge_s = nullptr, *fapart = nullptr;
     bool have_sde = false, have_prior = false, have_obs = false;
     double eobs_const = 0.0;
     // problem data (device)
@@ -120,6 +123,16 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         h->ntiles = (D + h->te - 7) / (h->te - 6);
     }
     const int nl = n_end - n_begin;
+    if (system == MFVGP_SYS_L96) {
+        h->fte = D <= 26 ? 32 : 64;
+        h->ftn = (h->fte == 64 && cells > 148 * 512) ? 4 : 1;
+        if (const char *ft = getenv("MFVGP_FTILE")) {       // experiments: "TE,TN"
+            int te = 0, tn = 0;
+            if (sscanf(ft, "%d,%d", &te, &tn) == 2) { h->fte = te; h->ftn = tn; }
+        }
+        h->fntiles = (D + h->fte - 7) / (h->fte - 6);
+        h->fntn = (nl + h->ftn - 1) / h->ftn;
+    }
     double tab[kNodes * kTabStride];
     build_fixed_table(tab);
     CK(cudaMemcpyToSymbol(c_tab, tab, sizeof(tab)));
@@ -138,6 +151,11 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         CK(cudaMemcpyToSymbol(c_gkx_main, gkx, sizeof(gkx)));
         const char *rule = getenv("MFVGP_RULE");
         h->rule = (rule && std::string(rule) == "gk42") ? 0 : 1;
+        // The fused E_cost kernel is parity-tested but measured ~2 % slower end to end than
+        // split kernel + assemble_kernel at D=8192 (profiles/r1_fused_experiment.md), so it
+        // stays opt-in (MFVGP_FUSE=1) until its prologue and edge fix-up are tuned.
+        const char *fuse = getenv("MFVGP_FUSE");
+        h->fused = (system == MFVGP_SYS_L96 && h->rule == 1 && fuse && fuse[0] == '1') ? 1 : 0;
     }
     {
         double gx[kNodesPerPanel], gv[kNodesPerPanel], gw[10];
@@ -151,12 +169,15 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         dev_alloc(&h->tau0, D) || dev_alloc(&h->obs_times, M) ||
         dev_alloc(&h->obs_values, (size_t)M * d) || dev_alloc(&h->obs_noise, d) ||
         dev_alloc(&h->dm_ws, (size_t)L * D * 4) || dev_alloc(&h->ds_ws, (size_t)L * D * 3) ||
-        dev_alloc(&h->part, (size_t)nl * h->ntiles * kPartStride) ||
+        dev_alloc(&h->part, (size_t)nl * (h->ntiles > h->fntiles ? h->ntiles : h->fntiles) *
+                                kPartStride) ||
+        dev_alloc(&h->fedge_m, (size_t)h->fntn * D) || dev_alloc(&h->fedge_s, (size_t)h->fntn * D) ||
+        dev_alloc(&h->fapart, (size_t)h->fntn * h->fntiles * 4) ||
         dev_alloc(&h->esde_n, L) || dev_alloc(&h->apart, (size_t)D * 4) ||
         dev_alloc(&h->out_ws, 16) || dev_alloc(&h->rec_ws, 16))
         return MFVGP_ERR_CUDA;
     h->refine_grid = 2 * nl < 296 ? 2 * nl : 296;
-    if (dev_alloc(&h->refine_ws, (size_t)h->refine_grid * D * kMaxNE)) return MFVGP_ERR_CUDA;
+    if (dev_alloc(&h->refine_ws, (size_t)h->refine_grid * 2 * D * kMaxNE)) return MFVGP_ERR_CUDA;
     CK(cudaMalloc((void **)&h->refine_info, 2 * L * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->refine_status, sizeof(int32_t)));
     CK(cudaMemset(h->refine_info, 0, 2 * L * sizeof(int32_t)));
@@ -181,7 +202,7 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->scg_vec[0], h->scg_vec[1], h->scg_vec[2], h->scg_vec[3], h->scg_vec[4],
                     h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal,
                     h->refine_ws, h->refine_info, h->refine_status, h->edge_send, h->edge_recv,
-                    h->gather, h->rec_ws};
+                    h->gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
@@ -240,6 +261,36 @@ extern "C" int mfvgp_set_obs(mfvgp_handle *h, const double *obs_times_h,
 }
 
 // ---- launch helpers ---------------------------------------------------------
+static int launch_guard_refine(mfvgp_handle *h, const double *mean, int64_t ldm,
+                               const double *vars, int64_t lds, int log_vars, double *ds,
+                               int ntiles, int delta_mode, cudaStream_t st) {
+    const int nl = h->n_end - h->n_begin;
+    GuardArgs g;
+    g.part = h->part; g.obs_times = h->obs_times; g.esde_n = h->esde_n; g.flags = h->flags;
+    g.n_begin = h->n_begin; g.n_end = h->n_end; g.ntiles = ntiles;
+    guard_reduce_kernel<<<(nl * 32 + 255) / 256, 256, 0, st>>>(g);
+    h->launches++;
+    CK(cudaGetLastError());
+    // adaptive path for the flagged (interval, integrand) pairs; unflagged CTAs exit at once
+    RefineArgs r;
+    r.mean = mean; r.vars = vars; r.ldm = ldm; r.lds = lds;
+    r.obs_times = h->obs_times; r.sigma = h->sigma; r.theta = h->theta;
+    r.flags = h->flags; r.esde_n = h->esde_n; r.ds_out = ds; r.ws = h->refine_ws;
+    r.delta_mode = delta_mode;
+    r.info = h->refine_info; r.status = h->refine_status;
+    r.D = h->D; r.n_begin = h->n_begin; r.n_end = h->n_end; r.log_vars = log_vars;
+    r.want_grad = ds != nullptr;
+    switch (h->system) {
+        case MFVGP_SYS_DW: refine_kernel<0><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
+        case MFVGP_SYS_OU: refine_kernel<1><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
+        case MFVGP_SYS_L63: refine_kernel<2><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
+        default: refine_kernel<3><<<h->refine_grid, kRefThreads, 0, st>>>(r);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return MFVGP_OK;
+}
+
 static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const double *vars,
                        int64_t lds, int log_vars, double *dm, double *ds, cudaStream_t st) {
     EsdeArgs a;
@@ -278,28 +329,86 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         CK(cudaEventRecord(ev1, st));
         h->timing_events.emplace_back(ev0, ev1);
     }
-    GuardArgs g;
-    g.part = h->part; g.obs_times = h->obs_times; g.esde_n = h->esde_n; g.flags = h->flags;
-    g.n_begin = h->n_begin; g.n_end = h->n_end; g.ntiles = h->ntiles;
-    guard_reduce_kernel<<<(nl * 32 + 255) / 256, 256, 0, st>>>(g);
-    h->launches++;
-    CK(cudaGetLastError());
-    // adaptive path for the flagged (interval, integrand) pairs; unflagged CTAs exit at once
-    RefineArgs r;
-    r.mean = mean; r.vars = vars; r.ldm = ldm; r.lds = lds;
-    r.obs_times = h->obs_times; r.sigma = h->sigma; r.theta = h->theta;
-    r.flags = h->flags; r.esde_n = h->esde_n; r.ds_out = ds; r.ws = h->refine_ws;
-    r.info = h->refine_info; r.status = h->refine_status;
-    r.D = h->D; r.n_begin = h->n_begin; r.n_end = h->n_end; r.log_vars = log_vars;
-    r.want_grad = ds != nullptr;
-    switch (h->system) {
-        case MFVGP_SYS_DW: refine_kernel<0><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
-        case MFVGP_SYS_OU: refine_kernel<1><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
-        case MFVGP_SYS_L63: refine_kernel<2><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
-        default: refine_kernel<3><<<h->refine_grid, kRefThreads, 0, st>>>(r);
+    return launch_guard_refine(h, mean, ldm, vars, lds, log_vars, ds, h->ntiles, 0, st);
+}
+
+template <int TE, int TN>
+static int launch_fused_kernel(const EsdeArgs &a, const FusedArgs &f, unsigned grid,
+                               cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = sizeof(FusedSmem<TE, TN>);
+    if (!configured) {
+        CK(cudaFuncSetAttribute(esde_l96_fused_kernel<TE, TN>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
     }
+    esde_l96_fused_kernel<TE, TN><<<grid, dim3(TE, TN), smem, st>>>(a, f);
+    return MFVGP_OK;
+}
+
+// L96, split rule: E_cost in one main kernel (esde_l96_fused_kernel) + small follow-ups
+static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStream_t st) {
+    const double *lvar = x + (int64_t)h->D * h->Nm;
+    EsdeArgs a;
+    a.mean = x; a.vars = lvar; a.ldm = h->Nm; a.lds = h->Ns;
+    a.obs_times = h->obs_times; a.sigma = h->sigma; a.theta = h->theta;
+    a.dm_out = nullptr; a.ds_out = nullptr; a.part = h->part;
+    a.D = h->D; a.n_begin = h->n_begin; a.n_end = h->n_end; a.ntiles = h->fntiles;
+    a.log_vars = 1;
+    FusedArgs f;
+    f.gm = grad; f.gs = grad ? grad + (int64_t)h->D * h->Nm : nullptr;
+    f.mu0 = h->mu0; f.tau0 = h->tau0; f.obs_values = h->obs_values; f.obs_noise = h->obs_noise;
+    f.obs_idx = h->obs_idx; f.edge_m = h->fedge_m; f.edge_s = h->fedge_s; f.apart = h->fapart;
+    f.M = h->M; f.d = h->d; f.Nm = h->Nm; f.Ns = h->Ns; f.L = h->L; f.ntn = h->fntn;
+    f.with_e0 = h->n_begin == 0;
+    const unsigned grid = (unsigned)h->fntn * h->fntiles;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (h->timing) {
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        CK(cudaEventRecord(ev0, st));
+    }
+    int rc;
+    const int key = h->fte * 100 + h->ftn;
+    switch (key) {
+        case 3201: rc = launch_fused_kernel<32, 1>(a, f, grid, st); break;
+        case 3204: rc = launch_fused_kernel<32, 4>(a, f, grid, st); break;
+        case 3208: rc = launch_fused_kernel<32, 8>(a, f, grid, st); break;
+        case 6401: rc = launch_fused_kernel<64, 1>(a, f, grid, st); break;
+        case 6402: rc = launch_fused_kernel<64, 2>(a, f, grid, st); break;
+        case 6404: rc = launch_fused_kernel<64, 4>(a, f, grid, st); break;
+        case 12801: rc = launch_fused_kernel<128, 1>(a, f, grid, st); break;
+        case 12802: rc = launch_fused_kernel<128, 2>(a, f, grid, st); break;
+        default: g_err = "unsupported fused tile"; return MFVGP_ERR_ARG;
+    }
+    if (rc) return rc;
     h->launches++;
     CK(cudaGetLastError());
+    if (h->timing) {
+        CK(cudaEventRecord(ev1, st));
+        h->timing_events.emplace_back(ev0, ev1);
+    }
+    // refined dS integrals come back as (refined - fixed) in ds_ws and are applied below
+    rc = launch_guard_refine(h, x, h->Nm, lvar, h->Ns, 1, grad ? h->ds_ws : nullptr,
+                             h->fntiles, 1, st);
+    if (rc) return rc;
+    if (grad != nullptr) {
+        if (h->fntn > 1) {
+            FixupArgs fx;
+            fx.x = x; fx.gm = f.gm; fx.gs = f.gs; fx.edge_m = h->fedge_m; fx.edge_s = h->fedge_s;
+            fx.D = h->D; fx.Nm = h->Nm; fx.Ns = h->Ns; fx.n_begin = h->n_begin; fx.ntn = h->fntn;
+            fx.TN = h->ftn;
+            edge_fixup_kernel<<<dim3((h->D + 255) / 256, h->fntn - 1), 256, 0, st>>>(fx);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
+        ApplyRefineArgs ar;
+        ar.flags = h->flags; ar.delta = h->ds_ws; ar.x = x; ar.gs = f.gs;
+        ar.D = h->D; ar.Nm = h->Nm; ar.Ns = h->Ns; ar.n_begin = h->n_begin; ar.n_end = h->n_end;
+        apply_refine_kernel<<<h->n_end - h->n_begin + 1, 256, 0, st>>>(ar);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     return MFVGP_OK;
 }
 
@@ -322,15 +431,15 @@ static int combine_over_ranks(mfvgp_handle *h, const double *local, int n, int n
     return MFVGP_OK;
 }
 
-static int launch_final(mfvgp_handle *h, const double *apart, double *out, int32_t *status,
-                        cudaStream_t st) {
+static int launch_final(mfvgp_handle *h, const double *apart, int napart, double *out,
+                        int32_t *status, cudaStream_t st) {
     FinalArgs f;
     const bool multi = h->world > 1;
     f.esde_n = h->esde_n; f.flags = h->flags; f.apart = apart;
     f.out = multi ? h->rec_ws : out; f.status = status;
     f.refine_status = h->refine_status;
     f.record9 = multi ? 1 : 0;
-    f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = h->D;
+    f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = napart;
     f.with_e0 = h->n_begin == 0;
     f.eobs_const = h->n_begin == 0 ? h->eobs_const : 0.0;
     final_kernel<<<1, 256, 0, st>>>(f);
@@ -416,7 +525,7 @@ extern "C" int mfvgp_esde(mfvgp_handle *h, const double *mean_pts_d, int64_t ldm
                          want_grad ? dEsde_dm_d : nullptr, want_grad ? dEsde_ds_d : nullptr, st);
     if (rc) return rc;
     // E_sde alone: out[0] = Esde (reported through the F slot as well)
-    rc = launch_final(h, nullptr, h->out_ws, status_d, st);
+    rc = launch_final(h, nullptr, 0, h->out_ws, status_d, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out_d, h->out_ws + 2, sizeof(double), cudaMemcpyDeviceToDevice, st));
     return MFVGP_OK;
@@ -434,8 +543,18 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const double *mean = x_d;
     const double *lvar = x_d + (int64_t)h->D * h->Nm;
-    int rc = launch_esde(h, mean, h->Nm, lvar, h->Ns, 1, want_grad ? h->dm_ws : nullptr,
-                         want_grad ? h->ds_ws : nullptr, st);
+    int rc;
+    if (h->fused) {
+        rc = launch_fused(h, x_d, want_grad ? grad_d : nullptr, st);
+        if (rc) return rc;
+        if (h->world > 1 && want_grad) {
+            rc = exchange_edges(h, grad_d, st);
+            if (rc) return rc;
+        }
+        return launch_final(h, h->fapart, h->fntn * h->fntiles, out_d, status_d, st);
+    }
+    rc = launch_esde(h, mean, h->Nm, lvar, h->Ns, 1, want_grad ? h->dm_ws : nullptr,
+                     want_grad ? h->ds_ws : nullptr, st);
     if (rc) return rc;
     AssembleArgs a;
     a.x = x_d; a.dm = want_grad ? h->dm_ws : nullptr; a.ds = want_grad ? h->ds_ws : nullptr;
@@ -450,7 +569,7 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
         rc = exchange_edges(h, grad_d, st);
         if (rc) return rc;
     }
-    return launch_final(h, h->apart, out_d, status_d, st);
+    return launch_final(h, h->apart, h->D, out_d, status_d, st);
 }
 
 static int ensure_host_staging(mfvgp_handle *h) {

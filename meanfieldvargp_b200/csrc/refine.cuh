@@ -42,7 +42,9 @@ struct RefineArgs {
     const int32_t *flags;      // [L] bit0: energy, bit1: dS
     double *esde_n;            // [L]   overwritten for refined energy integrals
     double *ds_out;            // [L][D][3] overwritten for refined dS integrals (or nullptr)
-    double *ws;                // [gridDim.x][D*kMaxNE] scratch: elementwise integral
+    double *ws;                // [gridDim.x][2][D*kMaxNE] scratch: elementwise integral, and
+                               // (delta mode) the fixed-rule value s1+s2 of the first bisection
+    int delta_mode;            // 1: ds_out receives (refined - fixed rule), for the fused E_cost path
     int32_t *info;             // [L][2] number of bisections done (0 = not refined)
     int32_t *status;           // OR-ed MFVGP_ST_REFINE_LIMIT
     int D, n_begin, n_end, log_vars, want_grad;
@@ -229,7 +231,7 @@ __device__ __forceinline__ void gk_error(double n_kg2, double n_dabs2, double n_
 }
 
 template <int SYS, bool ENERGY>
-__device__ void refine_item(const RefineArgs &a, int n, double *ws) {
+__device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_fixed) {
     using RE = RowEval<SYS>;
     constexpr int NE = ENERGY ? 1 : RE::NJ * 3;
     __shared__ double h_err[kHeapCap], h_a[kHeapCap], h_b[kHeapCap];
@@ -314,6 +316,8 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws) {
                 for (int e = 0; e < NE; ++e) {
                     const double dint = i_l[e] + i_r[e] - i_old[e];
                     ws[(int64_t)i * NE + e] += dint;
+                    // the root panel's two halves are the fixed 42-node rule
+                    if (!ENERGY && pa == 0.0 && pb == 1.0) ws_fixed[(int64_t)i * NE + e] = i_l[e] + i_r[e];
                 }
             }
             block_sum<7, kRefThreads>(acc, sh_red);
@@ -374,14 +378,19 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws) {
                     const int i = src[slot];      // row whose `slot` neighbour is j
                     const double is = 1.0 / a.sigma[i];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        o[k] += is * ws[(int64_t)i * NE + slot * 3 + k];
+                    for (int k = 0; k < 3; ++k) {
+                        const int64_t q = (int64_t)i * NE + slot * 3 + k;
+                        o[k] += is * (a.delta_mode ? ws[q] - ws_fixed[q] : ws[q]);
+                    }
                 }
             } else {
                 for (int i = 0; i < D; ++i) {
                     const double is = 1.0 / a.sigma[i];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) o[k] += is * ws[(int64_t)i * NE + j * 3 + k];
+                    for (int k = 0; k < 3; ++k) {
+                        const int64_t q = (int64_t)i * NE + j * 3 + k;
+                        o[k] += is * (a.delta_mode ? ws[q] - ws_fixed[q] : ws[q]);
+                    }
                 }
             }
 #pragma unroll
@@ -396,14 +405,44 @@ template <int SYS>
 __global__ void __launch_bounds__(kRefThreads)
 refine_kernel(const RefineArgs a) {
     const int nl = a.n_end - a.n_begin;
-    double *ws = a.ws + (int64_t)blockIdx.x * a.D * kMaxNE;
+    double *ws = a.ws + (int64_t)blockIdx.x * 2 * a.D * kMaxNE;
+    double *ws_fixed = ws + (int64_t)a.D * kMaxNE;
     for (int w = blockIdx.x; w < 2 * nl; w += gridDim.x) {
         const int n = a.n_begin + (w >> 1);
         const int which = w & 1;
         const int f = a.flags[n];
         if (threadIdx.x == 0) a.info[2 * n + which] = 0;
-        if (which == 0 && (f & 1)) refine_item<SYS, true>(a, n, ws);
-        if (which == 1 && (f & 2) && a.want_grad) refine_item<SYS, false>(a, n, ws);
+        if (which == 0 && (f & 1)) refine_item<SYS, true>(a, n, ws, ws_fixed);
+        if (which == 1 && (f & 2) && a.want_grad) refine_item<SYS, false>(a, n, ws, ws_fixed);
+    }
+}
+
+// Fused E_cost path: the gradient has already been assembled from the fixed rule;
+// add (refined - fixed) dS integrals of the flagged intervals, times exp(x)
+// (free_energy.py:743).  CTA n owns columns 2n and 2n+1, so every column has one
+// writer and a fixed order of its (at most two) addends.
+struct ApplyRefineArgs {
+    const int32_t *flags;      // [L]
+    const double *delta;       // [L][D][3]  (refined - fixed), already * 1/2 / Sigma
+    const double *x;           // optimisation vector (log-variances after D*Nm)
+    double *gs;                // gradient, variance block [D][Ns]
+    int D, Nm, Ns, n_begin, n_end;
+};
+
+__global__ void __launch_bounds__(256)
+apply_refine_kernel(const ApplyRefineArgs a) {
+    const int n = a.n_begin + blockIdx.x;             // n_end itself: last shared column only
+    const bool f_own = n < a.n_end && (a.flags[n] & 2);
+    const bool f_prev = n > a.n_begin && (a.flags[n - 1] & 2);
+    if (!f_own && !f_prev) return;
+    for (int j = threadIdx.x; j < a.D; j += blockDim.x) {
+        const int64_t base = (int64_t)j * a.Ns + 2 * n;
+        const double *xs = a.x + (int64_t)a.D * a.Nm;
+        double d0 = 0.0;
+        if (f_prev) d0 += a.delta[((int64_t)(n - 1) * a.D + j) * 3 + 2];
+        if (f_own) d0 += a.delta[((int64_t)n * a.D + j) * 3 + 0];
+        a.gs[base] += d0 * exp(xs[base]);
+        if (f_own) a.gs[base + 1] += a.delta[((int64_t)n * a.D + j) * 3 + 1] * exp(xs[base + 1]);
     }
 }
 

@@ -144,3 +144,36 @@ def test_split_rule_equals_42_node_rule(monkeypatch):
         assert abs(Fs - F42) <= 1e-13 * abs(F42)
         assert rel_err(gs, g42) <= 1e-12
         assert abs(F42 - g["F"]) <= RTOL * abs(g["F"]) and rel_err(g42, g["grad"]) <= RTOL
+
+
+@pytest.mark.parametrize("D,M,rough", [(40, 7, False), (67, 12, True), (300, 300, False),
+                                       (300, 290, True), (64, 1500, True)])
+def test_fused_ecost_equals_unfused(D, M, rough, monkeypatch):
+    """
+    The opt-in fused kernel (MFVGP_FUSE=1: esde_l96_fused_kernel + edge fix-up +
+    refine deltas) against the default split kernel + assemble_kernel, which the
+    golden tests pin to the reference.  `rough` makes some variance triples steep so intervals get refined.
+    """
+    g = synthetic_l96(D, M, seed=D + M)
+    x = g["x0"].copy()
+    if rough:
+        rng = np.random.default_rng(M)
+        sp = x[D * (3 * M + 4):].reshape(D, 2 * M + 3)
+        cols = rng.choice(2 * M + 3, size=max(2, M // 6), replace=False)
+        sp[:, cols] = np.log(10.0 ** rng.uniform(-1.7, -0.7, size=(D, cols.size)))
+    fe0 = make_free_energy(g)
+    F0, g0 = fe0.E_cost(x)
+    info0 = fe0.refine_info()
+    monkeypatch.setenv("MFVGP_FUSE", "1")
+    fe1 = make_free_energy(g)
+    monkeypatch.delenv("MFVGP_FUSE")
+    F1, g1 = fe1.E_cost(x)
+    assert np.array_equal(fe1.refine_info(), info0)
+    if rough:
+        assert info0.max() > 0
+    assert abs(F1 - F0) <= 1e-13 * abs(F0)
+    assert rel_err(g1, g0) <= 1e-12
+    assert abs(fe1.E_cost(x, output_gradients=False) - F0) <= 1e-13 * abs(F0)
+    if D * (M - 1) < 20000 and info0.max() < 90:      # limit=100 hit => not comparable (DESIGN.md 4)
+        Fo, go = make_oracle(g, adaptive=True).E_cost(x)
+        assert abs(F1 - Fo) <= RTOL * abs(Fo) and rel_err(g1, go) <= RTOL
