@@ -236,7 +236,7 @@ __device__ __forceinline__ double fast_rcp3(double x) {
 }
 
 template <int TE>
-__global__ void __launch_bounds__(TE)
+__global__ void __launch_bounds__(TE, 640 / TE)
 esde_l96_split_kernel(const EsdeArgs a) {
     constexpr int TD = TE - 6;
     __shared__ double sh_m[TE], sh_s[TE];
@@ -325,7 +325,7 @@ esde_l96_split_kernel(const EsdeArgs a) {
         }
     }
 
-    // ---- (B) coupled polynomial part, 7 Gauss-Legendre nodes -------------------
+// ---- (B) coupled polynomial part, 7 Gauss-Legendre nodes -------------------
     double accM[4] = {0, 0, 0, 0}, accS[3] = {0, 0, 0}, accE = 0.0;
 #pragma unroll
     for (int g = 0; g < kGL; ++g) {
