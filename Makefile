@@ -6,7 +6,7 @@ LIB = meanfieldvargp_b200/lib/libmfvgp.so
 
 all: $(LIB)
 
-$(LIB): $(CSRC)/mfvgp.cu $(CSRC)/kernels.cuh $(CSRC)/scg.cuh $(CSRC)/drift.cuh $(CSRC)/tables.h include/mfvgp.h
+$(LIB): $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.h) include/mfvgp.h
 	mkdir -p meanfieldvargp_b200/lib
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/mfvgp.cu
 

@@ -1,0 +1,440 @@
+// Lorenz 96 E_cost in one main kernel: "walk" layout.
+//
+// Replaces, for Lorenz 96, the reference's E_sde + gradient assembly of E_cost
+// (src/var_bayes/free_energy.py:461-565 and :711-743; drift expressions
+// src/dynamical_systems/lorenz_96.py:187-381).
+//
+// A CTA owns TE "extended" state dimensions (TE-6 output rows plus the
+// wrap-around halo of 3 per side that the circular i-2/i-1/i+1 coupling needs,
+// lorenz_96.py:232-235) and WALKS along a run of TN consecutive time intervals:
+// thread e keeps row j's support points in registers, the end point of one
+// interval is the start point of the next (free_energy.py:504-505), so
+//   * every support point is loaded and exp()'d once,
+//   * the loads of interval n+1 are issued before the arithmetic of interval n,
+//   * the gradient is stitched in registers (:715-728: shared end points add),
+//     gets dE0 (:733-734), dEobs (:737-738) and the log-variance chain rule
+//     (:743) and is written straight into the gradient of x -- no per-interval
+//     workspace, no assembly pass.
+// Only the one column a run shares with the NEXT run needs another CTA: it goes
+// to a small edge buffer and edge_fixup_kernel adds it (one writer per element,
+// fixed order: deterministic).
+//
+// Quadrature = the split rule of esde_l96_split_kernel (kernels.cuh):
+//   (A) rational part q^2/(4s) and its d/dS on scipy's 2 x 21 Kronrod nodes, plus
+//       the embedded Gauss-10 sums (quad_vec's error estimate) -- here in
+//       panel-local coordinates with symmetric node pairs and moment sums
+//       (tables.h build_pair_table): 66 node constants instead of 560, ~20 % fewer
+//       FP64 instructions;
+//   (B) coupled polynomial part on 7 Gauss-Legendre nodes with the shared-memory
+//       neighbour exchange.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace mfvgp {
+
+__constant__ double c_pair[kPairs * kPairStride];
+__constant__ double c_vcentre;
+
+constexpr int kWalkMaxTN = 64;
+
+// Sums of one Kronrod panel in panel-local coordinates x in [-1, 1].
+struct PanelSums {
+    double kE, N0, N1, N2, N3, L0, L1, L2;     // Kronrod:  sum v x^j {t, qi2, qi}
+    double gE, GN0, GN1, GN2, GL0, GL1;        // Gauss-10: sum w x^j {t, qi2, qi}
+};
+
+// s(x) = al0 + al1 x + al2 x^2, q(x) = be0 + be1 x on the panel.
+__device__ __forceinline__ void panel_sums(double al0, double al1, double al2, double be0,
+                                           double be1, PanelSums &o) {
+    double kE = 0.0, N0 = 0.0, N1 = 0.0, N2 = 0.0, N3 = 0.0, L0 = 0.0, L1 = 0.0, L2 = 0.0;
+    double gE = 0.0, GN0 = 0.0, GN1 = 0.0, GN2 = 0.0, GL0 = 0.0, GL1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+        const double *T = c_pair + i * kPairStride;
+        const double x = T[PR_X];
+        const double sp = fma(fma(al2, x, al1), x, al0);
+        const double sm = fma(fma(al2, -x, al1), -x, al0);
+        const double qp = fma(be1, x, be0), qm = fma(-be1, x, be0);
+        const double ip = qp * fast_rcp3(sp), im = qm * fast_rcp3(sm);   // q / s
+        const double tE = fma(qp, ip, qm * im);                          // sum of q^2 / s
+        const double p2 = ip * ip, m2 = im * im;                         // (q/s)^2
+        const double ue = p2 + m2, uo = p2 - m2, le = ip + im, lo = ip - im;
+        kE = fma(T[PR_V], tE, kE);
+        N0 = fma(T[PR_V], ue, N0);
+        N2 = fma(T[PR_VX2], ue, N2);
+        N1 = fma(T[PR_VX], uo, N1);
+        N3 = fma(T[PR_VX3], uo, N3);
+        L0 = fma(T[PR_V], le, L0);
+        L2 = fma(T[PR_VX2], le, L2);
+        L1 = fma(T[PR_VX], lo, L1);
+        if (i & 1) {
+            gE = fma(T[PR_W], tE, gE);
+            GN0 = fma(T[PR_W], ue, GN0);
+            GN2 = fma(T[PR_WX2], ue, GN2);
+            GN1 = fma(T[PR_WX], uo, GN1);
+            GL0 = fma(T[PR_W], le, GL0);
+            GL1 = fma(T[PR_WX], lo, GL1);
+        }
+    }
+    {   // centre node x = 0 (Kronrod only)
+        const double ic = be0 * fast_rcp3(al0), vc = c_vcentre;
+        kE = fma(vc, be0 * ic, kE);
+        N0 = fma(vc, ic * ic, N0);
+        L0 = fma(vc, ic, L0);
+    }
+    o.kE = kE; o.N0 = N0; o.N1 = N1; o.N2 = N2; o.N3 = N3; o.L0 = L0; o.L1 = L1; o.L2 = L2;
+    o.gE = gE; o.GN0 = GN0; o.GN1 = GN1; o.GN2 = GN2; o.GL0 = GL0; o.GL1 = GL1;
+}
+
+// Rational part of one cell: K-sums in the normalisation of the split kernel
+// (integral = (dt/4) x sum) and the guard quantities.
+struct RatOut {
+    double aE;            // sum_42 v q^2/s
+    double kS[3];         // own-slot K-sums of the rational d/dS part
+    double eE[2], eS[2];  // per panel: (Kronrod - Gauss)^2 of E, of the 3 dS elements
+    double m1S[2];        // per panel: squared first moment of the k = 0 dS element
+};
+
+// Quadratic Lagrange basis on knots 0, 1/2, 1 expanded about the panel centre c
+// (tau = c + x/4):  sum v B2_k(tau) f = B2_k(c) M0 + B2_k'(c)/4 M1 + B2_k''/32 M2,
+//                   sum v B2_k'(tau) f = B2_k'(c) M0 + B2_k''/4 M1.
+// c = 1/4: B2 = (3/8, 3/4, -1/8), B2' = (-2, 2, 0);  c = 3/4: B2 = (-1/8, 3/4, 3/8),
+// B2' = (0, -2, 2);  B2'' = (4, -8, 4).
+template <int P>
+__device__ __forceinline__ void sv3(double M0, double M1, double M2, double *o) {
+    if (P == 0) {
+        o[0] = fma(0.375, M0, fma(-0.5, M1, 0.125 * M2));
+        o[1] = fma(0.75, M0, fma(0.5, M1, -0.25 * M2));
+        o[2] = 0.125 * (M2 - M0);
+    } else {
+        o[0] = 0.125 * (M2 - M0);
+        o[1] = fma(0.75, M0, fma(-0.5, M1, -0.25 * M2));
+        o[2] = fma(0.375, M0, fma(0.5, M1, 0.125 * M2));
+    }
+}
+template <int P>
+__device__ __forceinline__ void sd3(double M0, double M1, double *o) {
+    if (P == 0) {
+        o[0] = fma(-2.0, M0, M1);
+        o[1] = 2.0 * (M0 - M1);
+        o[2] = M1;
+    } else {
+        o[0] = M1;
+        o[1] = -2.0 * (M0 + M1);
+        o[2] = fma(2.0, M0, M1);
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void panel_post(const PanelSums &s, double hid /*0.5/dt*/,
+                                           double inv_dt, RatOut &o) {
+    double sv[3], sd[3];
+    sv3<P>(s.N0, s.N1, s.N2, sv);
+    sd3<P>(s.L0, s.L1, sd);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.kS[k] += fma(hid, sd[k], -0.25 * sv[k]);
+    o.aE += s.kE;
+    const double dE = 0.25 * (s.kE - s.gE);
+    o.eE[P] = dE * dE;
+    sv3<P>(s.N0 - s.GN0, s.N1 - s.GN1, s.N2 - s.GN2, sv);
+    sd3<P>(s.L0 - s.GL0, s.L1 - s.GL1, sd);
+    double eS = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double kg = fma(hid, sd[k], -0.25 * sv[k]);
+        eS = fma(kg, kg, eS);
+    }
+    o.eS[P] = eS;
+    // first moment of the k = 0 element: sum v x [(1 - qi2/4) B2_0 + (1 + qi/2) B2_0'/dt]
+    double mv, md;
+    if (P == 0) {
+        mv = fma(0.375, s.N1, fma(-0.5, s.N2, 0.125 * s.N3));
+        md = fma(-2.0, s.L1, s.L2);
+    } else {
+        mv = 0.125 * (s.N3 - s.N1);
+        md = s.L2;
+    }
+    const double m1 = fma(hid, md, -0.25 * mv) + fma(c_m1poly[2 * P + 1], inv_dt, c_m1poly[2 * P]);
+    o.m1S[P] = m1 * m1;
+}
+
+__device__ __forceinline__ void rational_part(double S0, double S1, double S2, double Sig,
+                                              double inv_dt, RatOut &o) {
+    // s(tau) = a0 + a1 tau + a2 tau^2 ; q(tau) = ds/dt - Sigma = b0 + b1 tau
+    const double a0 = S0, a1 = -3.0 * S0 + 4.0 * S1 - S2, a2 = 2.0 * (S0 - 2.0 * S1 + S2);
+    const double b0 = fma(a1, inv_dt, -Sig), b1 = 2.0 * a2 * inv_dt;
+    const double al2 = 0.0625 * a2, be1 = 0.25 * b1, hid = 0.5 * inv_dt;
+    o.aE = 0.0;
+    o.kS[0] = o.kS[1] = o.kS[2] = 0.0;
+    PanelSums s;
+    panel_sums(fma(fma(a2, 0.25, a1), 0.25, a0), 0.25 * fma(0.5, a2, a1), al2,
+               fma(b1, 0.25, b0), be1, s);
+    panel_post<0>(s, hid, inv_dt, o);
+    panel_sums(fma(fma(a2, 0.75, a1), 0.75, a0), 0.25 * fma(1.5, a2, a1), al2,
+               fma(b1, 0.75, b0), be1, s);
+    panel_post<1>(s, hid, inv_dt, o);
+}
+
+struct WalkArgs {
+    // inputs: x = [means [D][Nm] | log-variances [D][Ns]]
+    const double *x;
+    const double *obs_times, *sigma, *theta;
+    const double *mu0, *tau0, *obs_values, *obs_noise;
+    const int32_t *obs_idx;      // [D] index into the observed dims or -1
+    double *gm, *gs;             // gradient blocks [D][Nm], [D][Ns] (nullptr: value only)
+    double *edge_m, *edge_s;     // [nruns][D]: k=3 / k=2 part of each run's last interval
+    double *part;                // [(n_end-n_begin)*ntiles][kPartStride] guard partials
+    double *apart;               // [gridDim.x][4]: sum log(tau0/s0), kl0 quad, obs, -
+    int D, M, d, Nm, Ns, L;
+    int n_begin, n_end;          // intervals of this shard
+    int ntiles, nruns, TN;       // dim tiles, runs, intervals per run
+    int with_e0;
+};
+
+template <int TE>
+__global__ void __launch_bounds__(TE, 512 / TE)
+esde_l96_walk_kernel(const WalkArgs a) {
+    constexpr int TD = TE - 6, NW = TE / 32;
+    __shared__ double sh_m[TE], sh_s[TE];
+    __shared__ double sh_A[TE], sh_B[TE], sh_C[TE], sh_Dv[TE];
+    __shared__ double sh_red[9][NW];
+    __shared__ double sh_dt[kWalkMaxTN], sh_idt[kWalkMaxTN];
+
+    const int e = threadIdx.x;
+    const int tile = blockIdx.x % a.ntiles, run = blockIdx.x / a.ntiles;
+    const int n0 = a.n_begin + run * a.TN;
+    const int tnv = min(a.TN, a.n_end - n0);            // intervals in this run
+    const int d0 = tile * TD, D = a.D;
+    int j = (d0 - 3 + e) % D;
+    if (j < 0) j += D;
+    const bool has_energy = (e >= 2) && (e <= TE - 2);
+    const bool is_out = (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
+    const bool last_run = n0 + tnv == a.n_end;           // last run of this shard
+    const bool last_shard = a.n_end == a.L;
+    const bool want_grad = a.gm != nullptr;
+
+    for (int i = e; i < tnv; i += TE) {
+        const double dt = fabs(a.obs_times[n0 + i + 1] - a.obs_times[n0 + i]);
+        sh_dt[i] = dt;
+        sh_idt[i] = 1.0 / dt;
+    }
+
+    const double *mp = a.x + (int64_t)j * a.Nm + 3 * (int64_t)n0;
+    const double *sp = a.x + (int64_t)D * a.Nm + (int64_t)j * a.Ns + 2 * (int64_t)n0;
+    double P0 = mp[0], P1 = mp[1], P2 = mp[2], P3 = mp[3];
+    double S0 = sp[0], S1 = sp[1], S2 = sp[2];
+    const double Sig = a.sigma[j];
+    const double theta = a.theta[0];
+    const int jo = is_out ? a.obs_idx[j] : -1;
+    double Ri = 0.0, y0 = 0.0;
+    if (jo >= 0) {
+        Ri = a.obs_noise[jo];
+        if (n0 >= 1) y0 = a.obs_values[(int64_t)(n0 - 1) * a.d + jo];     // obs at column 3 n0
+    }
+    double *gmp = want_grad ? a.gm + (int64_t)j * a.Nm + 3 * (int64_t)n0 : nullptr;
+    double *gsp = want_grad ? a.gs + (int64_t)j * a.Ns + 2 * (int64_t)n0 : nullptr;
+    S0 = exp(S0); S1 = exp(S1); S2 = exp(S2);
+    if (jo >= 0) Ri = 1.0 / Ri;
+    const double inv_sig = 1.0 / Sig;
+    double carry_m = 0.0, carry_s = 0.0;                 // k=3 / k=2 part of the previous interval
+    double acc[3] = {0.0, 0.0, 0.0};
+    __syncthreads();
+
+    for (int nl = 0; nl < tnv; ++nl) {
+        const int n = n0 + nl;
+        // ---- loads of the next interval, consumed at the bottom of this iteration ----
+        double nP1 = 0.0, nP2 = 0.0, nP3 = 0.0, nS1 = 0.0, nS2 = 0.0, ny = 0.0;
+        const bool more = nl + 1 < tnv;
+        if (more) {
+            nP1 = mp[3 * nl + 4]; nP2 = mp[3 * nl + 5]; nP3 = mp[3 * nl + 6];
+            nS1 = sp[2 * nl + 3]; nS2 = sp[2 * nl + 4];
+            if (jo >= 0) ny = a.obs_values[(int64_t)n * a.d + jo];
+        }
+        const double dt = sh_dt[nl], inv_dt = sh_idt[nl];
+
+        // ---- (A) rational part, own dimension ---------------------------------------------
+        RatOut ro;
+        ro.aE = 0.0;
+        ro.kS[0] = ro.kS[1] = ro.kS[2] = 0.0;
+        ro.eE[0] = ro.eE[1] = ro.eS[0] = ro.eS[1] = ro.m1S[0] = ro.m1S[1] = 0.0;
+        if (is_out) rational_part(S0, S1, S2, Sig, inv_dt, ro);
+
+        // ---- (B) coupled polynomial part, 7 Gauss-Legendre nodes ---------------------------
+        double accM[4] = {0, 0, 0, 0}, accS[3] = {0, 0, 0}, accE = 0.0;
+#pragma unroll
+        for (int g = 0; g < kGL; ++g) {
+            const double *T = c_gl + g * kTabStride;
+            const double m = P0 * T[T_B3] + P1 * T[T_B3 + 1] + P2 * T[T_B3 + 2] + P3 * T[T_B3 + 3];
+            const double dm = (P0 * T[T_DB3] + P1 * T[T_DB3 + 1] + P2 * T[T_DB3 + 2]
+                               + P3 * T[T_DB3 + 3]) * inv_dt;
+            const double s = S0 * T[T_B2] + S1 * T[T_B2 + 1] + S2 * T[T_B2 + 2];
+            sh_m[e] = m;
+            sh_s[e] = s;
+            __syncthreads();
+            double own_m = 0.0;
+            if (has_energy) {
+                const double ma = sh_m[e + 1], mb = sh_m[e - 1], mc = sh_m[e - 2];
+                const double sa = sh_s[e + 1], sb = sh_s[e - 1], sc = sh_s[e - 2];
+                const double u = ma - mc, su = sa + sc;
+                const double R = fma(u, mb, theta - m) - dm;
+                const double t1 = sb * u, t2 = mb * su;
+                const double Ec = fma(R, R, fma(t1, u, fma(t2, mb, su * sb)));
+                const double w = T[T_V] * inv_sig, w2 = w + w;
+                const double wR2 = w2 * R;
+                sh_A[e] = fma(wR2, mb, w2 * t1);
+                sh_B[e] = fma(wR2, u, w2 * t2);
+                sh_C[e] = w * fma(mb, mb, sb);
+                sh_Dv[e] = w * fma(u, u, su);
+                own_m = -wR2;
+                accE = fma(w, Ec, accE);
+            }
+            __syncthreads();
+            if (is_out) {
+                const double Gm = own_m + sh_A[e - 1] + sh_B[e + 1] - sh_A[e + 2];
+                const double Gs = sh_C[e - 1] + sh_Dv[e + 1] + sh_C[e + 2];
+                const double Hm = own_m * inv_dt;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    accM[k] += Gm * T[T_B3 + k] + Hm * T[T_DB3 + k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) accS[k] = fma(Gs, T[T_B2 + k], accS[k]);
+            }
+        }
+
+        // ---- per-interval results (same algebra as esde_l96_split_kernel) -------------------
+        const double four_inv_dt = 4.0 * inv_dt;
+        const double own_poly = dt * (S0 + 4.0 * S1 + S2) * (1.0 / 6.0) + (S2 - S0) - Sig * dt;
+        const double ksum_E = 0.25 * ro.aE + 4.0 * accE * Sig + four_inv_dt * own_poly;
+        const double polyS[3] = {dt * (1.0 / 6.0) - 1.0, dt * (4.0 / 6.0), dt * (1.0 / 6.0) + 1.0};
+        double dsv[3], own2 = 0.0;
+        {
+            const double sc_gl = 0.5 * dt, sc_gk = 0.125 * dt * inv_sig, hsig = 0.5 * inv_sig;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                dsv[k] = fma(sc_gl, accS[k], fma(sc_gk, ro.kS[k], hsig * polyS[k]));
+                const double o = fma(four_inv_dt, polyS[k], ro.kS[k]);
+                own2 = fma(o, o, own2);
+            }
+        }
+        // guard partials of this (interval, tile)
+        {
+            double red[9] = {ksum_E * inv_sig, ksum_E * ksum_E, ro.eE[0], ro.eE[1], ro.eS[0],
+                             ro.eS[1], own2, ro.m1S[0], ro.m1S[1]};
+            const int lane = e & 31, w = e >> 5;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const double v = warp_sum(is_out ? red[i] : 0.0);
+                if (lane == 0) sh_red[i][w] = v;
+            }
+        }
+        __syncthreads();
+        if (e < 9) {
+            double v = sh_red[e][0];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) v += sh_red[e][w];
+            a.part[((int64_t)(n - a.n_begin) * a.ntiles + tile) * kPartStride + e] = v;
+        }
+
+        // ---- gradient columns 3n..3n+2 / 2n..2n+1 (free_energy.py:715-743) -------------------
+        if (is_out) {
+            const double sc_gl = 0.5 * dt;
+            double gm0 = fma(sc_gl, accM[0], carry_m), gs0 = dsv[0] + carry_s;
+            if (n == 0 && a.with_e0) {                           // :733-734 and E_kl0 :309-310
+                const double mu = a.mu0[j], t0 = a.tau0[j];
+                const double z0 = P0 - mu, it0 = 1.0 / t0;
+                gm0 = fma(z0, it0, gm0);
+                gs0 += 0.5 * (it0 - 1.0 / S0);
+                acc[0] += log(t0 / S0);
+                acc[1] += (z0 * z0 + S0 - t0) * it0;
+            }
+            if (jo >= 0 && n >= 1) {                             // :737-738 and E_obs :594-612
+                const double rr = y0 - P0;
+                gm0 = fma(-Ri, rr, gm0);
+                gs0 = fma(0.5, Ri, gs0);
+                acc[2] = fma(Ri, fma(rr, rr, S0), acc[2]);
+            }
+            if (want_grad) {
+                gmp[3 * nl] = gm0;
+                gmp[3 * nl + 1] = sc_gl * accM[1];
+                gmp[3 * nl + 2] = sc_gl * accM[2];
+                gsp[2 * nl] = gs0 * S0;                          // :743
+                gsp[2 * nl + 1] = dsv[1] * S1;
+            }
+            carry_m = sc_gl * accM[3];
+            carry_s = dsv[2];
+        }
+        if (more) {
+            P0 = P3; P1 = nP1; P2 = nP2; P3 = nP3;
+            S0 = S2; S1 = exp(nS1); S2 = exp(nS2);
+            y0 = ny;
+        }
+    }
+
+    // ---- the column this run shares with the next one ------------------------------------
+    if (is_out) {
+        if (!last_run) {
+            if (want_grad) {
+                a.edge_m[(int64_t)run * D + j] = carry_m;
+                a.edge_s[(int64_t)run * D + j] = carry_s;
+            }
+        } else {
+            // end column of the shard, 3 n_end / 2 n_end.  On the last shard observation
+            // M-1 sits on it, observation M three (two) columns further on, and the
+            // remaining columns are never touched by the reference (:711-712): zeros.
+            double gme = carry_m, gse = carry_s;
+            if (last_shard && jo >= 0) {
+                const int64_t M = a.M;
+                const double y1 = a.obs_values[(M - 2) * a.d + jo];
+                const double y2 = a.obs_values[(M - 1) * a.d + jo];
+                const double mT = a.x[(int64_t)j * a.Nm + 3 * M];
+                const double sT = exp(a.x[(int64_t)D * a.Nm + (int64_t)j * a.Ns + 2 * M]);
+                const double rr = y1 - P3, r2 = y2 - mT;
+                gme = fma(-Ri, rr, gme);
+                gse = fma(0.5, Ri, gse);
+                acc[2] = fma(Ri, fma(rr, rr, S2), acc[2]);
+                acc[2] = fma(Ri, fma(r2, r2, sT), acc[2]);
+                if (want_grad) {
+                    gmp[3 * tnv + 3] = -Ri * r2;
+                    gsp[2 * tnv + 2] = 0.5 * Ri * sT;
+                }
+            } else if (last_shard && want_grad) {
+                gmp[3 * tnv + 3] = 0.0;
+                gsp[2 * tnv + 2] = 0.0;
+            }
+            if (want_grad) {
+                gmp[3 * tnv] = gme;
+                gsp[2 * tnv] = gse * S2;
+                if (last_shard) {
+                    gmp[3 * tnv + 1] = 0.0; gmp[3 * tnv + 2] = 0.0;
+                    gmp[3 * tnv + 4] = 0.0; gmp[3 * tnv + 5] = 0.0; gmp[3 * tnv + 6] = 0.0;
+                    gsp[2 * tnv + 1] = 0.0;
+                    gsp[2 * tnv + 3] = 0.0; gsp[2 * tnv + 4] = 0.0;
+                }
+            }
+        }
+    }
+
+    // ---- E_kl0 / E_obs energy partials of this CTA ------------------------------------------
+    {
+        const int lane = e & 31, w = e >> 5;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double v = warp_sum(acc[i]);
+            if (lane == 0) sh_red[i][w] = v;
+        }
+        __syncthreads();
+        if (e < 4) {
+            double v = 0.0;
+            if (e < 3) {
+                v = sh_red[e][0];
+#pragma unroll
+                for (int w2 = 1; w2 < NW; ++w2) v += sh_red[e][w2];
+            }
+            a.apart[(int64_t)blockIdx.x * 4 + e] = v;
+        }
+    }
+}
+
+}  // namespace mfvgp

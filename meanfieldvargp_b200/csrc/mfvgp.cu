@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include "nccl_dyn.h"
 #include "refine.cuh"
+#include "l96_walk.cuh"
 #include "scg.cuh"
 
 using namespace mfvgp;
@@ -40,6 +41,7 @@ struct mfvgp_handle {
     int te = 64, ntiles = 1;
     int rule = 1;     // 1: split rule (default), 0: 42-node coupled rule (MFVGP_RULE=gk42)
     // fused E_cost kernel (L96, split rule): TE x TN tile, grid = fntn * fntiles
+    // (fused = 2: walk kernel, l96_walk.cuh -- a CTA walks along ftn consecutive intervals)
     int fte = 64, ftn = 1, fntiles = 1, fntn = 1, fused = 0;
     double *fedge_m = nullptr, *fedge_s = nullptr, *fapart = nullptr;
     bool have_sde = false, have_prior = false, have_obs = false;
@@ -123,12 +125,44 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         h->ntiles = (D + h->te - 7) / (h->te - 6);
     }
     const int nl = n_end - n_begin;
+    // E_cost path for L96 (MFVGP_PATH=split|fused|walk; MFVGP_FUSE=1 = fused):
+    //   split: esde_l96_split_kernel + assemble_kernel   (default for small problems)
+    //   walk : esde_l96_walk_kernel, gradient written directly (default for large ones)
+    //   fused: esde_l96_fused_kernel (round-1 experiment, kept for comparison)
+    const char *path_env = getenv("MFVGP_PATH");
+    const char *fuse_env = getenv("MFVGP_FUSE");
+    const char *rule_env = getenv("MFVGP_RULE");
+    h->rule = (rule_env && std::string(rule_env) == "gk42") ? 0 : 1;
+    if (system == MFVGP_SYS_L96 && h->rule == 1) {
+        std::string path = path_env ? path_env : (fuse_env && fuse_env[0] == '1' ? "fused" : "");
+        if (path.empty()) path = cells > 148 * 512 ? "walk" : "split";
+        h->fused = path == "walk" ? 2 : (path == "fused" ? 1 : 0);
+    }
     if (system == MFVGP_SYS_L96) {
-        h->fte = D <= 26 ? 32 : 64;
-        h->ftn = (h->fte == 64 && cells > 148 * 512) ? 4 : 1;
+        if (h->fused == 2) {
+            // dim tile: the TE in {32, 64, 128} that wastes the fewest threads on halo / padding
+            int best = 128;
+            int64_t best_thr = (int64_t)((D + 121) / 122) * 128;
+            for (int te : {64, 32}) {
+                const int64_t thr = (int64_t)((D + te - 7) / (te - 6)) * te;
+                if (thr < best_thr) { best = te; best_thr = thr; }
+            }
+            h->fte = best;
+            const int nt = (D + h->fte - 7) / (h->fte - 6);
+            const int64_t target = 148LL * (512 / h->fte) * 8;       // ~8 waves of resident CTAs
+            int64_t tn = (int64_t)nl * nt / target;
+            h->ftn = (int)(tn < 1 ? 1 : (tn > 32 ? 32 : tn));
+        } else {
+            h->fte = D <= 26 ? 32 : 64;
+            h->ftn = (h->fte == 64 && cells > 148 * 512) ? 4 : 1;
+        }
         if (const char *ft = getenv("MFVGP_FTILE")) {       // experiments: "TE,TN"
             int te = 0, tn = 0;
             if (sscanf(ft, "%d,%d", &te, &tn) == 2) { h->fte = te; h->ftn = tn; }
+        }
+        if (h->fused == 2) {
+            ARG(h->fte == 32 || h->fte == 64 || h->fte == 128, "MFVGP_FTILE: walk TE must be 32|64|128");
+            ARG(h->ftn >= 1 && h->ftn <= kWalkMaxTN, "MFVGP_FTILE: walk TN must be 1..64");
         }
         h->fntiles = (D + h->fte - 7) / (h->fte - 6);
         h->fntn = (nl + h->ftn - 1) / h->ftn;
@@ -149,13 +183,10 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         CK(cudaMemcpyToSymbol(c_vxD, vxD, sizeof(vxD)));
         CK(cudaMemcpyToSymbol(c_m1poly, m1poly, sizeof(m1poly)));
         CK(cudaMemcpyToSymbol(c_gkx_main, gkx, sizeof(gkx)));
-        const char *rule = getenv("MFVGP_RULE");
-        h->rule = (rule && std::string(rule) == "gk42") ? 0 : 1;
-        // The fused E_cost kernel is parity-tested but measured ~2 % slower end to end than
-        // split kernel + assemble_kernel at D=8192 (profiles/r1_fused_experiment.md), so it
-        // stays opt-in (MFVGP_FUSE=1) until its prologue and edge fix-up are tuned.
-        const char *fuse = getenv("MFVGP_FUSE");
-        h->fused = (system == MFVGP_SYS_L96 && h->rule == 1 && fuse && fuse[0] == '1') ? 1 : 0;
+        double pair[kPairs * kPairStride], vc;
+        build_pair_table(pair, &vc);
+        CK(cudaMemcpyToSymbol(c_pair, pair, sizeof(pair)));
+        CK(cudaMemcpyToSymbol(c_vcentre, &vc, sizeof(vc)));
     }
     {
         double gx[kNodesPerPanel], gv[kNodesPerPanel], gw[10];
@@ -368,7 +399,22 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
         CK(cudaEventCreate(&ev1));
         CK(cudaEventRecord(ev0, st));
     }
-    int rc;
+    int rc = MFVGP_OK;
+    if (h->fused == 2) {
+        WalkArgs w;
+        w.x = x; w.obs_times = h->obs_times; w.sigma = h->sigma; w.theta = h->theta;
+        w.mu0 = h->mu0; w.tau0 = h->tau0; w.obs_values = h->obs_values;
+        w.obs_noise = h->obs_noise; w.obs_idx = h->obs_idx;
+        w.gm = f.gm; w.gs = f.gs; w.edge_m = h->fedge_m; w.edge_s = h->fedge_s;
+        w.part = h->part; w.apart = h->fapart;
+        w.D = h->D; w.M = h->M; w.d = h->d; w.Nm = h->Nm; w.Ns = h->Ns; w.L = h->L;
+        w.n_begin = h->n_begin; w.n_end = h->n_end;
+        w.ntiles = h->fntiles; w.nruns = h->fntn; w.TN = h->ftn;
+        w.with_e0 = h->n_begin == 0;
+        if (h->fte == 32) esde_l96_walk_kernel<32><<<grid, 32, 0, st>>>(w);
+        else if (h->fte == 64) esde_l96_walk_kernel<64><<<grid, 64, 0, st>>>(w);
+        else esde_l96_walk_kernel<128><<<grid, 128, 0, st>>>(w);
+    } else {
     const int key = h->fte * 100 + h->ftn;
     switch (key) {
         case 3201: rc = launch_fused_kernel<32, 1>(a, f, grid, st); break;
@@ -380,6 +426,7 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
         case 12801: rc = launch_fused_kernel<128, 1>(a, f, grid, st); break;
         case 12802: rc = launch_fused_kernel<128, 2>(a, f, grid, st); break;
         default: g_err = "unsupported fused tile"; return MFVGP_ERR_ARG;
+    }
     }
     if (rc) return rc;
     h->launches++;

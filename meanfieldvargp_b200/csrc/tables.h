@@ -163,6 +163,36 @@ inline void build_rational_table(double *tab /*[42][16]*/) {
         }
 }
 
+// ---------------------------------------------------------------------------
+// Pair table of the rational part in PANEL-LOCAL coordinates (l96_walk.cuh).
+// GK21 nodes are symmetric, x and -x; with s and q re-expanded about the panel
+// centre the node constants are the same for both panels, and every weighted
+// basis sum becomes a moment sum  sum_r v_r x_r^j f(x_r): even moments see
+// f(x)+f(-x), odd ones f(x)-f(-x).  Row i = 0..9 (x descending, i odd = node of
+// the embedded Gauss-10 rule): x, v, v x, v x^2, v x^3, w, w x, w x^2.
+// ---------------------------------------------------------------------------
+constexpr int kPairs = 10;
+constexpr int kPairStride = 8;
+constexpr int PR_X = 0, PR_V = 1, PR_VX = 2, PR_VX2 = 3, PR_VX3 = 4, PR_W = 5, PR_WX = 6,
+              PR_WX2 = 7;
+
+inline void build_pair_table(double *tab /*[10][8]*/, double *v_centre) {
+    for (int i = 0; i < kPairs; ++i) {
+        const long double x = gk21_x(i), v = gk21_v(i);
+        const long double w = (i & 1) ? gk21_w((i - 1) / 2) : 0.0L;
+        double *row = tab + i * kPairStride;
+        row[PR_X] = (double)x;
+        row[PR_V] = (double)v;
+        row[PR_VX] = (double)(v * x);
+        row[PR_VX2] = (double)(v * x * x);
+        row[PR_VX3] = (double)(v * x * x * x);
+        row[PR_W] = (double)w;
+        row[PR_WX] = (double)(w * x);
+        row[PR_WX2] = (double)(w * x * x);
+    }
+    *v_centre = (double)gk21_v(10);
+}
+
 // n-point Gauss-Legendre on [-1,1] by Newton iteration in long double
 inline void gauss_legendre(int n, long double *x, long double *w) {
     const long double pi = 3.14159265358979323846264338327950288L;

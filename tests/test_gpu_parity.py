@@ -146,27 +146,29 @@ def test_split_rule_equals_42_node_rule(monkeypatch):
         assert abs(F42 - g["F"]) <= RTOL * abs(g["F"]) and rel_err(g42, g["grad"]) <= RTOL
 
 
-@pytest.mark.parametrize("D,M,rough", [(40, 7, False), (67, 12, True), (300, 300, False),
-                                       (300, 290, True), (64, 1500, True)])
-def test_fused_ecost_equals_unfused(D, M, rough, monkeypatch):
-    """
-    The opt-in fused kernel (MFVGP_FUSE=1: esde_l96_fused_kernel + edge fix-up +
-    refine deltas) against the default split kernel + assemble_kernel, which the
-    golden tests pin to the reference.  `rough` makes some variance triples steep so intervals get refined.
-    """
-    g = synthetic_l96(D, M, seed=D + M)
+def _roughen(g, D, M, rough):
     x = g["x0"].copy()
     if rough:
         rng = np.random.default_rng(M)
         sp = x[D * (3 * M + 4):].reshape(D, 2 * M + 3)
         cols = rng.choice(2 * M + 3, size=max(2, M // 6), replace=False)
         sp[:, cols] = np.log(10.0 ** rng.uniform(-1.7, -0.7, size=(D, cols.size)))
+    return x
+
+
+def _check_path_equals_split(path, D, M, rough, monkeypatch, ftile=None):
+    g = synthetic_l96(D, M, seed=D + M)
+    x = _roughen(g, D, M, rough)
+    monkeypatch.setenv("MFVGP_PATH", "split")
     fe0 = make_free_energy(g)
     F0, g0 = fe0.E_cost(x)
     info0 = fe0.refine_info()
-    monkeypatch.setenv("MFVGP_FUSE", "1")
+    monkeypatch.setenv("MFVGP_PATH", path)
+    if ftile:
+        monkeypatch.setenv("MFVGP_FTILE", ftile)
     fe1 = make_free_energy(g)
-    monkeypatch.delenv("MFVGP_FUSE")
+    monkeypatch.delenv("MFVGP_PATH")
+    monkeypatch.delenv("MFVGP_FTILE", raising=False)
     F1, g1 = fe1.E_cost(x)
     assert np.array_equal(fe1.refine_info(), info0)
     if rough:
@@ -177,3 +179,44 @@ def test_fused_ecost_equals_unfused(D, M, rough, monkeypatch):
     if D * (M - 1) < 20000 and info0.max() < 90:      # limit=100 hit => not comparable
         Fo, go = make_oracle(g, adaptive=True).E_cost(x)
         assert abs(F1 - Fo) <= RTOL * abs(Fo) and rel_err(g1, go) <= RTOL
+
+
+@pytest.mark.parametrize("D,M,rough", [(40, 7, False), (67, 12, True), (300, 300, False),
+                                       (300, 290, True), (64, 1500, True)])
+def test_fused_ecost_equals_unfused(D, M, rough, monkeypatch):
+    """
+    The fused kernel (MFVGP_PATH=fused: esde_l96_fused_kernel + edge fix-up + refine
+    deltas) against the split kernel + assemble_kernel, which the golden tests pin to
+    the reference.  `rough` makes some variance triples steep so intervals get refined.
+    """
+    _check_path_equals_split("fused", D, M, rough, monkeypatch)
+
+
+@pytest.mark.parametrize("D,M,rough,ftile", [
+    (4, 2, False, None), (5, 3, False, "32,1"), (26, 9, False, "32,3"), (27, 5, True, None),
+    (40, 7, False, "64,2"), (67, 12, True, "64,5"), (123, 40, True, "128,7"),
+    (300, 300, False, None), (300, 290, True, "128,64"), (64, 1500, True, None),
+    (500, 16, False, "128,1"), (1000, 130, True, "128,16")])
+def test_walk_ecost_equals_split(D, M, rough, ftile, monkeypatch):
+    """
+    The walk kernel (MFVGP_PATH=walk, l96_walk.cuh: a CTA walks along a run of
+    intervals, moment form of the rational part, gradient written directly) against
+    the split kernel + assemble_kernel; run lengths chosen to hit ragged last runs,
+    single-interval runs and the maximum run length.
+    """
+    _check_path_equals_split("walk", D, M, rough, monkeypatch, ftile)
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_walk_matches_reference_golden(name, monkeypatch):
+    g = load_golden("eval", name)
+    if g["system"] != "L96":
+        pytest.skip("walk kernel is the Lorenz 96 path")
+    monkeypatch.setenv("MFVGP_PATH", "walk")
+    fe = make_free_energy(g)
+    monkeypatch.delenv("MFVGP_PATH")
+    F, grad = fe.E_cost(g["x0"])
+    assert abs(F - g["F"]) <= RTOL * abs(g["F"])
+    assert rel_err(grad, g["grad"]) <= RTOL
+    for k in ("E0", "Esde", "Eobs"):
+        assert abs(fe.last_terms[k] - g[k]) <= RTOL * abs(g["F"])
