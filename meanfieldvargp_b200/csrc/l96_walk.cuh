@@ -38,6 +38,15 @@ __constant__ double c_vcentre;
 
 constexpr int kWalkMaxTN = 64;
 
+// tuning knobs (tools/build_variant.sh builds variants with -D overrides)
+#ifndef MFVGP_WALK_B_UNROLL
+#define MFVGP_WALK_B_UNROLL 7
+#endif
+#ifndef MFVGP_WALK_THREADS_PER_SM
+#define MFVGP_WALK_THREADS_PER_SM 512
+#endif
+constexpr int kWalkBUnroll = MFVGP_WALK_B_UNROLL;
+
 // Sums of one Kronrod panel in panel-local coordinates x in [-1, 1].
 struct PanelSums {
     double kE, N0, N1, N2, N3, L0, L1, L2;     // Kronrod:  sum v x^j {t, qi2, qi}
@@ -49,32 +58,37 @@ __device__ __forceinline__ void panel_sums(double al0, double al1, double al2, d
                                            double be1, PanelSums &o) {
     double kE = 0.0, N0 = 0.0, N1 = 0.0, N2 = 0.0, N3 = 0.0, L0 = 0.0, L1 = 0.0, L2 = 0.0;
     double gE = 0.0, GN0 = 0.0, GN1 = 0.0, GN2 = 0.0, GL0 = 0.0, GL1 = 0.0;
+    // two pairs per trip (even pair: Kronrod only; odd pair: also a Gauss-10 node); the loop
+    // is kept rolled so the live ranges of the reciprocals stay short (no spills)
+#pragma unroll 1
+    for (int ii = 0; ii < kPairs / 2; ++ii) {
 #pragma unroll
-    for (int i = 0; i < kPairs; ++i) {
-        const double *T = c_pair + i * kPairStride;
-        const double x = T[PR_X];
-        const double sp = fma(fma(al2, x, al1), x, al0);
-        const double sm = fma(fma(al2, -x, al1), -x, al0);
-        const double qp = fma(be1, x, be0), qm = fma(-be1, x, be0);
-        const double ip = qp * fast_rcp3(sp), im = qm * fast_rcp3(sm);   // q / s
-        const double tE = fma(qp, ip, qm * im);                          // sum of q^2 / s
-        const double p2 = ip * ip, m2 = im * im;                         // (q/s)^2
-        const double ue = p2 + m2, uo = p2 - m2, le = ip + im, lo = ip - im;
-        kE = fma(T[PR_V], tE, kE);
-        N0 = fma(T[PR_V], ue, N0);
-        N2 = fma(T[PR_VX2], ue, N2);
-        N1 = fma(T[PR_VX], uo, N1);
-        N3 = fma(T[PR_VX3], uo, N3);
-        L0 = fma(T[PR_V], le, L0);
-        L2 = fma(T[PR_VX2], le, L2);
-        L1 = fma(T[PR_VX], lo, L1);
-        if (i & 1) {
-            gE = fma(T[PR_W], tE, gE);
-            GN0 = fma(T[PR_W], ue, GN0);
-            GN2 = fma(T[PR_WX2], ue, GN2);
-            GN1 = fma(T[PR_WX], uo, GN1);
-            GL0 = fma(T[PR_W], le, GL0);
-            GL1 = fma(T[PR_WX], lo, GL1);
+        for (int h = 0; h < 2; ++h) {
+            const double *T = c_pair + (2 * ii + h) * kPairStride;
+            const double x = T[PR_X];
+            const double sp = fma(fma(al2, x, al1), x, al0);
+            const double sm = fma(fma(al2, -x, al1), -x, al0);
+            const double qp = fma(be1, x, be0), qm = fma(-be1, x, be0);
+            const double ip = qp * fast_rcp3(sp), im = qm * fast_rcp3(sm);   // q / s
+            const double tE = fma(qp, ip, qm * im);                          // sum of q^2 / s
+            const double p2 = ip * ip, m2 = im * im;                         // (q/s)^2
+            const double ue = p2 + m2, uo = p2 - m2, le = ip + im, lo = ip - im;
+            kE = fma(T[PR_V], tE, kE);
+            N0 = fma(T[PR_V], ue, N0);
+            N2 = fma(T[PR_VX2], ue, N2);
+            N1 = fma(T[PR_VX], uo, N1);
+            N3 = fma(T[PR_VX3], uo, N3);
+            L0 = fma(T[PR_V], le, L0);
+            L2 = fma(T[PR_VX2], le, L2);
+            L1 = fma(T[PR_VX], lo, L1);
+            if (h == 1) {
+                gE = fma(T[PR_W], tE, gE);
+                GN0 = fma(T[PR_W], ue, GN0);
+                GN2 = fma(T[PR_WX2], ue, GN2);
+                GN1 = fma(T[PR_WX], uo, GN1);
+                GL0 = fma(T[PR_W], le, GL0);
+                GL1 = fma(T[PR_WX], lo, GL1);
+            }
         }
     }
     {   // centre node x = 0 (Kronrod only)
@@ -193,7 +207,7 @@ struct WalkArgs {
 };
 
 template <int TE>
-__global__ void __launch_bounds__(TE, 512 / TE)
+__global__ void __launch_bounds__(TE, MFVGP_WALK_THREADS_PER_SM / TE)
 esde_l96_walk_kernel(const WalkArgs a) {
     constexpr int TD = TE - 6, NW = TE / 32;
     __shared__ double sh_m[TE], sh_s[TE];
@@ -262,7 +276,7 @@ esde_l96_walk_kernel(const WalkArgs a) {
 
         // ---- (B) coupled polynomial part, 7 Gauss-Legendre nodes ---------------------------
         double accM[4] = {0, 0, 0, 0}, accS[3] = {0, 0, 0}, accE = 0.0;
-#pragma unroll
+#pragma unroll kWalkBUnroll
         for (int g = 0; g < kGL; ++g) {
             const double *T = c_gl + g * kTabStride;
             const double m = P0 * T[T_B3] + P1 * T[T_B3 + 1] + P2 * T[T_B3 + 2] + P3 * T[T_B3 + 3];

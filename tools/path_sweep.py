@@ -20,7 +20,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     for _ in range(10): fe.E_cost(g["x0"])
     e1.record(); torch.cuda.synchronize()
     lib.mfvgp_timing(fe._h, 0, ctypes.byref(tot), ctypes.byref(cnt))
-    print(f"{os.environ.get('MFVGP_PATH','default'):>6} {os.environ.get('MFVGP_FTILE','auto'):>7} D={D} M={M}: "
+    print(f"{Path(os.environ.get('MFVGP_LIB','base')).stem:>16} {os.environ.get('MFVGP_PATH','default'):>6} {os.environ.get('MFVGP_FTILE','auto'):>7} D={D} M={M}: "
           f"main kernel {tot.value/cnt.value*1e3:9.1f} us, eval {e0.elapsed_time(e1)/10*1e3:9.1f} us, F={F.item():.15g}", flush=True)
 else:
     M = sys.argv[1] if len(sys.argv) > 1 else "1025"
