@@ -33,19 +33,18 @@
 
 namespace mfvgp {
 
-__constant__ double c_pair[kPairs * kPairStride];
+__constant__ __align__(16) double c_pair[kPairs * kPairStride];
 __constant__ double c_vcentre;
 
 constexpr int kWalkMaxTN = 64;
 
 // tuning knobs (tools/build_variant.sh builds variants with -D overrides)
-#ifndef MFVGP_WALK_B_UNROLL
-#define MFVGP_WALK_B_UNROLL 7
+#ifndef MFVGP_WALK_GB
+#define MFVGP_WALK_GB 2
 #endif
 #ifndef MFVGP_WALK_THREADS_PER_SM
 #define MFVGP_WALK_THREADS_PER_SM 512
 #endif
-constexpr int kWalkBUnroll = MFVGP_WALK_B_UNROLL;
 
 // Sums of one Kronrod panel in panel-local coordinates x in [-1, 1].
 struct PanelSums {
@@ -193,27 +192,46 @@ __device__ __forceinline__ void rational_part(double S0, double S1, double S2, d
 struct WalkArgs {
     // inputs: x = [means [D][Nm] | log-variances [D][Ns]]
     const double *x;
-    const double *obs_times, *sigma, *theta;
+    const double *obs_times, *sigma;
     const double *mu0, *tau0, *obs_values, *obs_noise;
     const int32_t *obs_idx;      // [D] index into the observed dims or -1
     double *gm, *gs;             // gradient blocks [D][Nm], [D][Ns] (nullptr: value only)
     double *edge_m, *edge_s;     // [nruns][D]: k=3 / k=2 part of each run's last interval
     double *part;                // [(n_end-n_begin)*ntiles][kPartStride] guard partials
     double *apart;               // [gridDim.x][4]: sum log(tau0/s0), kl0 quad, obs, -
+    double theta;                // L96 forcing (lorenz_96.py:70)
     int D, M, d, Nm, Ns, L;
     int n_begin, n_end;          // intervals of this shard
     int ntiles, nruns, TN;       // dim tiles, runs, intervals per run
     int with_e0;
 };
 
-template <int TE>
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// GB = Gauss-Legendre nodes exchanged per pair of barriers (7: one batch per interval)
+template <int TE, int GB>
+struct WalkSmem {
+    double2 ms[GB][TE];           // (m, s) at the batch's nodes
+    double2 AC[GB][TE];           // (w dE_i/dm_{i+1}, w dE_i/ds_{i+1})
+    double2 BD[GB][TE];           // (w dE_i/dm_{i-1}, w dE_i/ds_{i-1})
+    double pf[6][TE];             // next interval: P1, P2, P3, log S1, log S2, y
+    double carry[2][TE];          // k=3 / k=2 part of the previous interval
+    double e0[2][TE];             // E_kl0 energy terms of the rows (run 0 only)
+    double red[9][TE / 32];
+    double dt[kWalkMaxTN], idt[kWalkMaxTN];
+};
+
+template <int TE, int GB>
 __global__ void __launch_bounds__(TE, MFVGP_WALK_THREADS_PER_SM / TE)
 esde_l96_walk_kernel(const WalkArgs a) {
     constexpr int TD = TE - 6, NW = TE / 32;
-    __shared__ double sh_m[TE], sh_s[TE];
-    __shared__ double sh_A[TE], sh_B[TE], sh_C[TE], sh_Dv[TE];
-    __shared__ double sh_red[9][NW];
-    __shared__ double sh_dt[kWalkMaxTN], sh_idt[kWalkMaxTN];
+    __shared__ WalkSmem<TE, GB> sm;
 
     const int e = threadIdx.x;
     const int tile = blockIdx.x % a.ntiles, run = blockIdx.x / a.ntiles;
@@ -224,48 +242,50 @@ esde_l96_walk_kernel(const WalkArgs a) {
     if (j < 0) j += D;
     const bool has_energy = (e >= 2) && (e <= TE - 2);
     const bool is_out = (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
-    const bool last_run = n0 + tnv == a.n_end;           // last run of this shard
-    const bool last_shard = a.n_end == a.L;
     const bool want_grad = a.gm != nullptr;
 
     for (int i = e; i < tnv; i += TE) {
         const double dt = fabs(a.obs_times[n0 + i + 1] - a.obs_times[n0 + i]);
-        sh_dt[i] = dt;
-        sh_idt[i] = 1.0 / dt;
+        sm.dt[i] = dt;
+        sm.idt[i] = 1.0 / dt;
     }
 
+    // row pointers at the run's first column; the gradient has the layout of x
     const double *mp = a.x + (int64_t)j * a.Nm + 3 * (int64_t)n0;
     const double *sp = a.x + (int64_t)D * a.Nm + (int64_t)j * a.Ns + 2 * (int64_t)n0;
+    const int64_t g_off_m = a.gm - a.x, g_off_s = a.gs - (a.x + (int64_t)D * a.Nm);
     double P0 = mp[0], P1 = mp[1], P2 = mp[2], P3 = mp[3];
     double S0 = sp[0], S1 = sp[1], S2 = sp[2];
     const double Sig = a.sigma[j];
-    const double theta = a.theta[0];
     const int jo = is_out ? a.obs_idx[j] : -1;
     double Ri = 0.0, y0 = 0.0;
     if (jo >= 0) {
         Ri = a.obs_noise[jo];
         if (n0 >= 1) y0 = a.obs_values[(int64_t)(n0 - 1) * a.d + jo];     // obs at column 3 n0
     }
-    double *gmp = want_grad ? a.gm + (int64_t)j * a.Nm + 3 * (int64_t)n0 : nullptr;
-    double *gsp = want_grad ? a.gs + (int64_t)j * a.Ns + 2 * (int64_t)n0 : nullptr;
     S0 = exp(S0); S1 = exp(S1); S2 = exp(S2);
     if (jo >= 0) Ri = 1.0 / Ri;
     const double inv_sig = 1.0 / Sig;
-    double carry_m = 0.0, carry_s = 0.0;                 // k=3 / k=2 part of the previous interval
-    double acc[3] = {0.0, 0.0, 0.0};
+    sm.carry[0][e] = 0.0;
+    sm.carry[1][e] = 0.0;
+    sm.e0[0][e] = 0.0;
+    sm.e0[1][e] = 0.0;
+    double acc_obs = 0.0;
     __syncthreads();
 
     for (int nl = 0; nl < tnv; ++nl) {
         const int n = n0 + nl;
-        // ---- loads of the next interval, consumed at the bottom of this iteration ----
-        double nP1 = 0.0, nP2 = 0.0, nP3 = 0.0, nS1 = 0.0, nS2 = 0.0, ny = 0.0;
+        // ---- next interval's support points: global -> shared, asynchronously ---------
         const bool more = nl + 1 < tnv;
         if (more) {
-            nP1 = mp[3 * nl + 4]; nP2 = mp[3 * nl + 5]; nP3 = mp[3 * nl + 6];
-            nS1 = sp[2 * nl + 3]; nS2 = sp[2 * nl + 4];
-            if (jo >= 0) ny = a.obs_values[(int64_t)n * a.d + jo];
+            cp_async8(&sm.pf[0][e], mp + 3 * nl + 4);
+            cp_async8(&sm.pf[1][e], mp + 3 * nl + 5);
+            cp_async8(&sm.pf[2][e], mp + 3 * nl + 6);
+            cp_async8(&sm.pf[3][e], sp + 2 * nl + 3);
+            cp_async8(&sm.pf[4][e], sp + 2 * nl + 4);
+            if (jo >= 0) cp_async8(&sm.pf[5][e], a.obs_values + (int64_t)n * a.d + jo);
         }
-        const double dt = sh_dt[nl], inv_dt = sh_idt[nl];
+        const double dt = sm.dt[nl], inv_dt = sm.idt[nl];
 
         // ---- (A) rational part, own dimension ---------------------------------------------
         RatOut ro;
@@ -276,43 +296,58 @@ esde_l96_walk_kernel(const WalkArgs a) {
 
         // ---- (B) coupled polynomial part, 7 Gauss-Legendre nodes ---------------------------
         double accM[4] = {0, 0, 0, 0}, accS[3] = {0, 0, 0}, accE = 0.0;
-#pragma unroll kWalkBUnroll
-        for (int g = 0; g < kGL; ++g) {
-            const double *T = c_gl + g * kTabStride;
-            const double m = P0 * T[T_B3] + P1 * T[T_B3 + 1] + P2 * T[T_B3 + 2] + P3 * T[T_B3 + 3];
-            const double dm = (P0 * T[T_DB3] + P1 * T[T_DB3 + 1] + P2 * T[T_DB3 + 2]
-                               + P3 * T[T_DB3 + 3]) * inv_dt;
-            const double s = S0 * T[T_B2] + S1 * T[T_B2 + 1] + S2 * T[T_B2 + 2];
-            sh_m[e] = m;
-            sh_s[e] = s;
-            __syncthreads();
-            double own_m = 0.0;
-            if (has_energy) {
-                const double ma = sh_m[e + 1], mb = sh_m[e - 1], mc = sh_m[e - 2];
-                const double sa = sh_s[e + 1], sb = sh_s[e - 1], sc = sh_s[e - 2];
-                const double u = ma - mc, su = sa + sc;
-                const double R = fma(u, mb, theta - m) - dm;
-                const double t1 = sb * u, t2 = mb * su;
-                const double Ec = fma(R, R, fma(t1, u, fma(t2, mb, su * sb)));
-                const double w = T[T_V] * inv_sig, w2 = w + w;
-                const double wR2 = w2 * R;
-                sh_A[e] = fma(wR2, mb, w2 * t1);
-                sh_B[e] = fma(wR2, u, w2 * t2);
-                sh_C[e] = w * fma(mb, mb, sb);
-                sh_Dv[e] = w * fma(u, u, su);
-                own_m = -wR2;
-                accE = fma(w, Ec, accE);
+#pragma unroll
+        for (int g0 = 0; g0 < kGL; g0 += GB) {
+            double own[GB];          // phase 1-2: theta - m - dm;  phase 2-3: w dE_i/dm_i
+#pragma unroll
+            for (int gg = 0; gg < GB; ++gg) {
+                if (g0 + gg >= kGL) break;
+                const double *T = c_gl + (g0 + gg) * kTabStride;
+                const double m = P0 * T[T_B3] + P1 * T[T_B3 + 1] + P2 * T[T_B3 + 2]
+                                 + P3 * T[T_B3 + 3];
+                const double dm = (P0 * T[T_DB3] + P1 * T[T_DB3 + 1] + P2 * T[T_DB3 + 2]
+                                   + P3 * T[T_DB3 + 3]) * inv_dt;
+                const double s = S0 * T[T_B2] + S1 * T[T_B2 + 1] + S2 * T[T_B2 + 2];
+                sm.ms[gg][e] = make_double2(m, s);
+                own[gg] = (a.theta - m) - dm;
             }
             __syncthreads();
-            if (is_out) {
-                const double Gm = own_m + sh_A[e - 1] + sh_B[e + 1] - sh_A[e + 2];
-                const double Gs = sh_C[e - 1] + sh_Dv[e + 1] + sh_C[e + 2];
-                const double Hm = own_m * inv_dt;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    accM[k] += Gm * T[T_B3 + k] + Hm * T[T_DB3 + k];
+            for (int gg = 0; gg < GB; ++gg) {
+                if (g0 + gg >= kGL) break;
+                if (has_energy) {
+                    const double *T = c_gl + (g0 + gg) * kTabStride;
+                    const double2 xa = sm.ms[gg][e + 1], xb = sm.ms[gg][e - 1],
+                                  xc = sm.ms[gg][e - 2];
+                    const double mb = xb.x, sb = xb.y;
+                    const double u = xa.x - xc.x, su = xa.y + xc.y;
+                    const double R = fma(u, mb, own[gg]);          // E[f_i] - dm_i
+                    const double t1 = sb * u, t2 = mb * su;
+                    const double Ec = fma(R, R, fma(t1, u, fma(t2, mb, su * sb)));
+                    const double w = T[T_V] * inv_sig, w2 = w + w;
+                    const double wR2 = w2 * R;
+                    sm.AC[gg][e] = make_double2(fma(wR2, mb, w2 * t1), w * fma(mb, mb, sb));
+                    sm.BD[gg][e] = make_double2(fma(wR2, u, w2 * t2), w * fma(u, u, su));
+                    own[gg] = -wR2;
+                    accE = fma(w, Ec, accE);
+                }
+            }
+            __syncthreads();
 #pragma unroll
-                for (int k = 0; k < 3; ++k) accS[k] = fma(Gs, T[T_B2 + k], accS[k]);
+            for (int gg = 0; gg < GB; ++gg) {
+                if (g0 + gg >= kGL) break;
+                if (is_out) {
+                    const double *T = c_gl + (g0 + gg) * kTabStride;
+                    const double2 l = sm.AC[gg][e - 1], r = sm.BD[gg][e + 1], rr = sm.AC[gg][e + 2];
+                    const double Gm = own[gg] + l.x + r.x - rr.x;
+                    const double Gs = l.y + r.y + rr.y;
+                    const double Hm = own[gg] * inv_dt;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        accM[k] += Gm * T[T_B3 + k] + Hm * T[T_DB3 + k];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) accS[k] = fma(Gs, T[T_B2 + k], accS[k]);
+                }
             }
         }
 
@@ -331,62 +366,85 @@ esde_l96_walk_kernel(const WalkArgs a) {
                 own2 = fma(o, o, own2);
             }
         }
-        // guard partials of this (interval, tile)
+        // guard partials of this (interval, tile).  The energy is summed in FP64; the eight
+        // guard quantities (sums of squares feeding a test with a 2 % margin, kernels.cuh
+        // guard_reduce_kernel) go through a transposing FP32 butterfly: 9 shuffles for all
+        // eight instead of 5 x 2 each.  Underflow -> 0 (no flag, correct: far below the
+        // threshold), overflow -> inf (flag: safe); |I_E|^2 is clamped so tol stays finite.
         {
-            double red[9] = {ksum_E * inv_sig, ksum_E * ksum_E, ro.eE[0], ro.eE[1], ro.eS[0],
-                             ro.eS[1], own2, ro.m1S[0], ro.m1S[1]};
             const int lane = e & 31, w = e >> 5;
+            const double vE = warp_sum(is_out ? ksum_E * inv_sig : 0.0);
+            float f[8] = {fminf((float)(ksum_E * ksum_E), 1.0e37f), (float)ro.eE[0],
+                          (float)ro.eE[1], (float)ro.eS[0], (float)ro.eS[1], (float)own2,
+                          (float)ro.m1S[0], (float)ro.m1S[1]};
+            if (!is_out)
 #pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                const double v = warp_sum(is_out ? red[i] : 0.0);
-                if (lane == 0) sh_red[i][w] = v;
+                for (int i = 0; i < 8; ++i) f[i] = 0.0f;
+#pragma unroll
+            for (int half = 4, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+                const bool hi = lane & bit;
+#pragma unroll
+                for (int k = 0; k < half; ++k) {
+                    const float send = hi ? f[k] : f[k + half], keep = hi ? f[k + half] : f[k];
+                    f[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                }
             }
+            f[0] += __shfl_xor_sync(0xffffffffu, f[0], 2);
+            f[0] += __shfl_xor_sync(0xffffffffu, f[0], 1);
+            if (lane == 0) sm.red[0][w] = vE;
+            if ((lane & 3) == 0) sm.red[1 + (lane >> 2)][w] = (double)f[0];
         }
         __syncthreads();
         if (e < 9) {
-            double v = sh_red[e][0];
+            double v = sm.red[e][0];
 #pragma unroll
-            for (int w = 1; w < NW; ++w) v += sh_red[e][w];
+            for (int w = 1; w < NW; ++w) v += sm.red[e][w];
             a.part[((int64_t)(n - a.n_begin) * a.ntiles + tile) * kPartStride + e] = v;
         }
 
         // ---- gradient columns 3n..3n+2 / 2n..2n+1 (free_energy.py:715-743) -------------------
         if (is_out) {
             const double sc_gl = 0.5 * dt;
-            double gm0 = fma(sc_gl, accM[0], carry_m), gs0 = dsv[0] + carry_s;
+            double gm0 = fma(sc_gl, accM[0], sm.carry[0][e]), gs0 = dsv[0] + sm.carry[1][e];
             if (n == 0 && a.with_e0) {                           // :733-734 and E_kl0 :309-310
                 const double mu = a.mu0[j], t0 = a.tau0[j];
                 const double z0 = P0 - mu, it0 = 1.0 / t0;
                 gm0 = fma(z0, it0, gm0);
                 gs0 += 0.5 * (it0 - 1.0 / S0);
-                acc[0] += log(t0 / S0);
-                acc[1] += (z0 * z0 + S0 - t0) * it0;
+                sm.e0[0][e] = log(t0 / S0);
+                sm.e0[1][e] = (z0 * z0 + S0 - t0) * it0;
             }
             if (jo >= 0 && n >= 1) {                             // :737-738 and E_obs :594-612
                 const double rr = y0 - P0;
                 gm0 = fma(-Ri, rr, gm0);
                 gs0 = fma(0.5, Ri, gs0);
-                acc[2] = fma(Ri, fma(rr, rr, S0), acc[2]);
+                acc_obs = fma(Ri, fma(rr, rr, S0), acc_obs);
             }
             if (want_grad) {
-                gmp[3 * nl] = gm0;
-                gmp[3 * nl + 1] = sc_gl * accM[1];
-                gmp[3 * nl + 2] = sc_gl * accM[2];
-                gsp[2 * nl] = gs0 * S0;                          // :743
-                gsp[2 * nl + 1] = dsv[1] * S1;
+                double *gmp = const_cast<double *>(mp) + g_off_m + 3 * nl;
+                double *gsp = const_cast<double *>(sp) + g_off_s + 2 * nl;
+                gmp[0] = gm0;
+                gmp[1] = sc_gl * accM[1];
+                gmp[2] = sc_gl * accM[2];
+                gsp[0] = gs0 * S0;                               // :743
+                gsp[1] = dsv[1] * S1;
             }
-            carry_m = sc_gl * accM[3];
-            carry_s = dsv[2];
+            sm.carry[0][e] = sc_gl * accM[3];
+            sm.carry[1][e] = dsv[2];
         }
         if (more) {
-            P0 = P3; P1 = nP1; P2 = nP2; P3 = nP3;
-            S0 = S2; S1 = exp(nS1); S2 = exp(nS2);
-            y0 = ny;
+            cp_async_wait_all();
+            P0 = P3; P1 = sm.pf[0][e]; P2 = sm.pf[1][e]; P3 = sm.pf[2][e];
+            S0 = S2; S1 = exp(sm.pf[3][e]); S2 = exp(sm.pf[4][e]);
+            if (jo >= 0) y0 = sm.pf[5][e];
         }
     }
 
     // ---- the column this run shares with the next one ------------------------------------
     if (is_out) {
+        const bool last_run = n0 + tnv == a.n_end;       // last run of this shard
+        const bool last_shard = a.n_end == a.L;
+        const double carry_m = sm.carry[0][e], carry_s = sm.carry[1][e];
         if (!last_run) {
             if (want_grad) {
                 a.edge_m[(int64_t)run * D + j] = carry_m;
@@ -396,6 +454,8 @@ esde_l96_walk_kernel(const WalkArgs a) {
             // end column of the shard, 3 n_end / 2 n_end.  On the last shard observation
             // M-1 sits on it, observation M three (two) columns further on, and the
             // remaining columns are never touched by the reference (:711-712): zeros.
+            double *gmp = const_cast<double *>(mp) + g_off_m + 3 * tnv;
+            double *gsp = const_cast<double *>(sp) + g_off_s + 2 * tnv;
             double gme = carry_m, gse = carry_s;
             if (last_shard && jo >= 0) {
                 const int64_t M = a.M;
@@ -406,24 +466,24 @@ esde_l96_walk_kernel(const WalkArgs a) {
                 const double rr = y1 - P3, r2 = y2 - mT;
                 gme = fma(-Ri, rr, gme);
                 gse = fma(0.5, Ri, gse);
-                acc[2] = fma(Ri, fma(rr, rr, S2), acc[2]);
-                acc[2] = fma(Ri, fma(r2, r2, sT), acc[2]);
+                acc_obs = fma(Ri, fma(rr, rr, S2), acc_obs);
+                acc_obs = fma(Ri, fma(r2, r2, sT), acc_obs);
                 if (want_grad) {
-                    gmp[3 * tnv + 3] = -Ri * r2;
-                    gsp[2 * tnv + 2] = 0.5 * Ri * sT;
+                    gmp[3] = -Ri * r2;
+                    gsp[2] = 0.5 * Ri * sT;
                 }
             } else if (last_shard && want_grad) {
-                gmp[3 * tnv + 3] = 0.0;
-                gsp[2 * tnv + 2] = 0.0;
+                gmp[3] = 0.0;
+                gsp[2] = 0.0;
             }
             if (want_grad) {
-                gmp[3 * tnv] = gme;
-                gsp[2 * tnv] = gse * S2;
+                gmp[0] = gme;
+                gsp[0] = gse * S2;
                 if (last_shard) {
-                    gmp[3 * tnv + 1] = 0.0; gmp[3 * tnv + 2] = 0.0;
-                    gmp[3 * tnv + 4] = 0.0; gmp[3 * tnv + 5] = 0.0; gmp[3 * tnv + 6] = 0.0;
-                    gsp[2 * tnv + 1] = 0.0;
-                    gsp[2 * tnv + 3] = 0.0; gsp[2 * tnv + 4] = 0.0;
+                    gmp[1] = 0.0; gmp[2] = 0.0;
+                    gmp[4] = 0.0; gmp[5] = 0.0; gmp[6] = 0.0;
+                    gsp[1] = 0.0;
+                    gsp[3] = 0.0; gsp[4] = 0.0;
                 }
             }
         }
@@ -432,19 +492,20 @@ esde_l96_walk_kernel(const WalkArgs a) {
     // ---- E_kl0 / E_obs energy partials of this CTA ------------------------------------------
     {
         const int lane = e & 31, w = e >> 5;
+        const double acc[3] = {sm.e0[0][e], sm.e0[1][e], acc_obs};
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const double v = warp_sum(acc[i]);
-            if (lane == 0) sh_red[i][w] = v;
+            if (lane == 0) sm.red[i][w] = v;
         }
         __syncthreads();
         if (e < 4) {
             double v = 0.0;
             if (e < 3) {
-                v = sh_red[e][0];
+                v = sm.red[e][0];
 #pragma unroll
-                for (int w2 = 1; w2 < NW; ++w2) v += sh_red[e][w2];
+                for (int w2 = 1; w2 < NW; ++w2) v += sm.red[e][w2];
             }
             a.apart[(int64_t)blockIdx.x * 4 + e] = v;
         }

@@ -39,6 +39,7 @@ struct mfvgp_handle {
     int system = 0, D = 0, M = 0, d = 0, device = 0;
     int L = 0, n_begin = 0, n_end = 0, Nm = 0, Ns = 0, ntheta = 0;
     int te = 64, ntiles = 1;
+    double theta_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int rule = 1;     // 1: split rule (default), 0: 42-node coupled rule (MFVGP_RULE=gk42)
     // fused E_cost kernel (L96, split rule): TE x TN tile, grid = fntn * fntiles
     // (fused = 2: walk kernel, l96_walk.cuh -- a CTA walks along ftn consecutive intervals)
@@ -254,6 +255,7 @@ extern "C" int mfvgp_set_sde(mfvgp_handle *h, const double *sigma_h, const doubl
     CK(cudaMemcpy(h->sigma, sigma_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->theta, theta_h, ntheta * sizeof(double), cudaMemcpyHostToDevice));
     h->ntheta = ntheta;
+    for (int i = 0; i < ntheta && i < 8; ++i) h->theta_host[i] = theta_h[i];
     h->have_sde = true;
     return MFVGP_OK;
 }
@@ -402,7 +404,7 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
     int rc = MFVGP_OK;
     if (h->fused == 2) {
         WalkArgs w;
-        w.x = x; w.obs_times = h->obs_times; w.sigma = h->sigma; w.theta = h->theta;
+        w.x = x; w.obs_times = h->obs_times; w.sigma = h->sigma; w.theta = h->theta_host[0];
         w.mu0 = h->mu0; w.tau0 = h->tau0; w.obs_values = h->obs_values;
         w.obs_noise = h->obs_noise; w.obs_idx = h->obs_idx;
         w.gm = f.gm; w.gs = f.gs; w.edge_m = h->fedge_m; w.edge_s = h->fedge_s;
@@ -411,9 +413,9 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
         w.n_begin = h->n_begin; w.n_end = h->n_end;
         w.ntiles = h->fntiles; w.nruns = h->fntn; w.TN = h->ftn;
         w.with_e0 = h->n_begin == 0;
-        if (h->fte == 32) esde_l96_walk_kernel<32><<<grid, 32, 0, st>>>(w);
-        else if (h->fte == 64) esde_l96_walk_kernel<64><<<grid, 64, 0, st>>>(w);
-        else esde_l96_walk_kernel<128><<<grid, 128, 0, st>>>(w);
+        if (h->fte == 32) esde_l96_walk_kernel<32, MFVGP_WALK_GB><<<grid, 32, 0, st>>>(w);
+        else if (h->fte == 64) esde_l96_walk_kernel<64, MFVGP_WALK_GB><<<grid, 64, 0, st>>>(w);
+        else esde_l96_walk_kernel<128, MFVGP_WALK_GB><<<grid, 128, 0, st>>>(w);
     } else {
     const int key = h->fte * 100 + h->ftn;
     switch (key) {
