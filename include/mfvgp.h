@@ -115,6 +115,21 @@ int mfvgp_ecost_host(mfvgp_handle *h, const double *x_h, int want_grad,
                      double *out_h /*[4]*/, double *grad_h, int32_t *status_h);
 
 /*
+ * E_cost on host buffers with ONE copy in each direction: buf_h holds
+ * n + 8 doubles, n = D*(3M+4) + D*(2M+3).  On return buf_h[0..n) = gradient
+ * (untouched when want_grad = 0), buf_h[n..n+4) = F, E0, Esde, Eobs and the
+ * int32 at buf_h + n + 4 = MFVGP_ST_* bits.  Meant for page-locked buffers
+ * from mfvgp_host_alloc (then both copies are plain DMA transfers).
+ */
+int mfvgp_ecost_host_packed(mfvgp_handle *h, const double *x_h, int want_grad,
+                            double *buf_h /*[n + 8]*/);
+
+/* Page-locked host memory from a small recycling pool (what numpy results of
+ * FreeEnergy.E_cost live in, so the device->host copy is a direct DMA).      */
+void *mfvgp_host_alloc(int64_t bytes);
+void mfvgp_host_free(void *p);
+
+/*
  * FreeEnergy.E_kl0(m0, s0, output_gradients) (free_energy.py:281-336) and
  * FreeEnergy.E_obs(mean_pts[d][M], vars_pts[d][M], output_gradients)
  * (:567-649) as stand-alone calls; E_cost computes both terms itself.

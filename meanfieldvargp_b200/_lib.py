@@ -32,6 +32,9 @@ SIGNATURES = {
     "mfvgp_ecost": (c_int, [c_void_p, _P, c_int, _P, _P, _P, c_void_p]),
     "mfvgp_esde_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P, _P, _P]),
     "mfvgp_ecost_host": (c_int, [c_void_p, _P, c_int, _P, _P, _P]),
+    "mfvgp_ecost_host_packed": (c_int, [c_void_p, _P, c_int, _P]),
+    "mfvgp_host_alloc": (c_void_p, [c_int64]),
+    "mfvgp_host_free": (None, [c_void_p]),
     "mfvgp_ekl0_host": (c_int, [c_void_p, _P, _P, c_int, POINTER(c_double), _P, _P, POINTER(c_int32)]),
     "mfvgp_eobs_host": (c_int, [c_void_p, _P, _P, c_int, POINTER(c_double), _P, _P, POINTER(c_int32)]),
     "mfvgp_scg": (c_int, [c_void_p, _P, c_int, c_double, c_double, _P, _P, _P, c_void_p]),
@@ -81,3 +84,37 @@ def require_device():
         raise MfvgpError("no CUDA device visible: the free-energy path runs "
                          "only on the GPU (no CPU fallback)")
     return lib
+
+
+class _PinnedBlock(object):
+    """Owner of one page-locked block of the library's pool (returned on collection)."""
+    __slots__ = ("ptr", "lib")
+
+    def __init__(self, lib, nbytes):
+        self.lib = lib
+        self.ptr = lib.mfvgp_host_alloc(nbytes)
+        if not self.ptr:
+            raise MfvgpError("mfvgp_host_alloc failed: "
+                             + lib.mfvgp_last_error().decode("utf-8", "replace"))
+
+    def __del__(self):
+        try:
+            self.lib.mfvgp_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+_ctype_cache = {}
+
+
+def pinned_empty(n):
+    """float64 numpy array of n entries in page-locked memory (recycled by the library)."""
+    import numpy as np
+    lib = load()
+    blk = _PinnedBlock(lib, 8 * n)
+    ct = _ctype_cache.get(n)
+    if ct is None:
+        ct = _ctype_cache[n] = c_double * n
+    buf = ct.from_address(blk.ptr)
+    buf._owner = blk                    # the block lives as long as any view of buf
+    return np.frombuffer(buf, dtype=np.float64)

@@ -889,17 +889,15 @@ struct GuardArgs {
     int n_begin, n_end, ntiles;
 };
 
-__global__ void __launch_bounds__(256)
-guard_reduce_kernel(const GuardArgs a) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int n = a.n_begin + warp;
-    if (n >= a.n_end) return;
+// one warp: interval n, lane = 0..31 (partials may come from other CTAs of the same launch:
+// read them through L2)
+__device__ __forceinline__ void guard_interval(const GuardArgs &a, int n, int lane) {
+    const int warp = n - a.n_begin;
     double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int t = lane; t < a.ntiles; t += 32) {
         const double *src = a.part + ((int64_t)warp * a.ntiles + t) * kPartStride;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) p[i] += src[i];
+        for (int i = 0; i < 9; ++i) p[i] += __ldcg(src + i);
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) p[i] = warp_sum(p[i]);
@@ -926,6 +924,14 @@ guard_reduce_kernel(const GuardArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(256)
+guard_reduce_kernel(const GuardArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n = a.n_begin + warp;
+    if (n >= a.n_end) return;
+    guard_interval(a, n, threadIdx.x & 31);
+}
+
 // ---------------------------------------------------------------------------
 // E_cost assembly (free_energy.py:686-750): stitches the per-interval
 // gradients (shared end points add), adds dE0 at column 0 and dEobs at the
@@ -947,10 +953,9 @@ struct AssembleArgs {
     int with_e0;              // this shard owns column 0
 };
 
-__global__ void __launch_bounds__(256)
-assemble_kernel(const AssembleArgs a) {
-    __shared__ double sh_red[3 * 8];
-    const int j = blockIdx.x;
+// row j of x / of the gradient; threads t0, t0+stride, ... share the columns
+__device__ __forceinline__ void assemble_row(const AssembleArgs &a, int j, int t0, int stride,
+                                             double (&acc)[3]) {
     const int jo = a.obs_idx[j];
     const double Ri = jo >= 0 ? 1.0 / a.obs_noise[jo] : 0.0;
     const double *xm = a.x + (int64_t)j * a.Nm;
@@ -965,9 +970,8 @@ assemble_kernel(const AssembleArgs a) {
     const int cm0 = 3 * a.n_begin, own_m1 = last ? a.Nm : 3 * a.n_end;
     const int cs0 = 2 * a.n_begin, own_s1 = last ? a.Ns : 2 * a.n_end;
     const int cm1 = last ? a.Nm : own_m1 + 1, cs1 = last ? a.Ns : own_s1 + 1;
-    double acc[3] = {0.0, 0.0, 0.0};
 
-    for (int c = cm0 + threadIdx.x; c < cm1; c += blockDim.x) {
+    for (int c = cm0 + t0; c < cm1; c += stride) {
         const int n = c / 3, k = c - 3 * n;
         double g = 0.0;
         if (a.dm != nullptr) {
@@ -989,7 +993,7 @@ assemble_kernel(const AssembleArgs a) {
         }
         if (gm) gm[c] = g;
     }
-    for (int c = cs0 + threadIdx.x; c < cs1; c += blockDim.x) {
+    for (int c = cs0 + t0; c < cs1; c += stride) {
         const int n = c >> 1, k = c & 1;
         double g = 0.0;
         if (a.ds != nullptr) {
@@ -1000,10 +1004,10 @@ assemble_kernel(const AssembleArgs a) {
         }
         const double s = exp(xs[c]);
         if (c == 0 && a.with_e0) {
-            const double t0 = a.tau0[j];
-            g += 0.5 * (1.0 / t0 - 1.0 / s);
-            acc[0] += log(t0 / s);
-            acc[1] += (s - t0) / t0;
+            const double t0_ = a.tau0[j];
+            g += 0.5 * (1.0 / t0_ - 1.0 / s);
+            acc[0] += log(t0_ / s);
+            acc[1] += (s - t0_) / t0_;
         }
         if (k == 0 && n >= 1 && n <= a.M && jo >= 0 && c < own_s1) {
             g += 0.5 * Ri;
@@ -1011,6 +1015,14 @@ assemble_kernel(const AssembleArgs a) {
         }
         if (gs) gs[c] = g * s;                       // free_energy.py:743
     }
+}
+
+__global__ void __launch_bounds__(256)
+assemble_kernel(const AssembleArgs a) {
+    __shared__ double sh_red[3 * 8];
+    const int j = blockIdx.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    assemble_row(a, j, threadIdx.x, blockDim.x, acc);
     block_sum<3, 256>(acc, sh_red);
     if (threadIdx.x == 0) {
         double *p = a.apart + (int64_t)j * 4;
@@ -1035,26 +1047,28 @@ struct FinalArgs {
     double eobs_const;        // M (d log 2pi + safe_log(prod R)), 0 on non-owning shards
 };
 
-__global__ void __launch_bounds__(256)
-final_kernel(const FinalArgs a) {
-    __shared__ double sh_red[4 * 8];
+// body for a CTA of NT threads (also the tail of assemble_tail_kernel, l96_coop.cuh);
+// inputs written by other CTAs of the same launch are read through L2
+template <int NT>
+__device__ __forceinline__ void final_body(const FinalArgs &a) {
+    __shared__ double sh_red[4 * (NT / 32)];
     __shared__ int sh_flag;
     if (threadIdx.x == 0) sh_flag = 0;
     __syncthreads();
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     int anyflag = 0;
-    for (int n = a.n_begin + threadIdx.x; n < a.n_end; n += blockDim.x) {
-        acc[0] += a.esde_n[n];
-        anyflag |= a.flags[n];
+    for (int n = a.n_begin + threadIdx.x; n < a.n_end; n += NT) {
+        acc[0] += __ldcg(a.esde_n + n);
+        anyflag |= __ldcg(a.flags + n);
     }
     if (a.apart != nullptr)
-        for (int j = threadIdx.x; j < a.D; j += blockDim.x) {
-            acc[1] += a.apart[(int64_t)j * 4 + 0];
-            acc[2] += a.apart[(int64_t)j * 4 + 1];
-            acc[3] += a.apart[(int64_t)j * 4 + 2];
+        for (int j = threadIdx.x; j < a.D; j += NT) {
+            acc[1] += __ldcg(a.apart + (int64_t)j * 4 + 0);
+            acc[2] += __ldcg(a.apart + (int64_t)j * 4 + 1);
+            acc[3] += __ldcg(a.apart + (int64_t)j * 4 + 2);
         }
     if (anyflag) atomicOr(&sh_flag, anyflag);
-    block_sum<4, 256>(acc, sh_red);
+    block_sum<4, NT>(acc, sh_red);
     __syncthreads();
     if (threadIdx.x == 0) {
         const double Esde = acc[0];
@@ -1088,6 +1102,9 @@ final_kernel(const FinalArgs a) {
         a.status[0] = st;
     }
 }
+
+__global__ void __launch_bounds__(256)
+final_kernel(const FinalArgs a) { final_body<256>(a); }
 
 // ---------------------------------------------------------------------------
 // Multi-GPU (time intervals sharded, one rank per GPU).  Neighbouring shards

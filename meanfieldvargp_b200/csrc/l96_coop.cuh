@@ -1,0 +1,341 @@
+// Lorenz 96, small problems (the north-star size D=500, M=16 has 7 500 cells --
+// 51 per SM): latency, not throughput, decides.  Here TWO lanes share one
+// (dimension, interval) cell of FreeEnergy.single_interval
+// (src/var_bayes/free_energy.py:338-459; drift lorenz_96.py:187-381):
+//   (A) the rational part: lane p integrates Kronrod panel p (10 symmetric node pairs +
+//       centre, moment form of l96_walk.cuh), one exchange of 7 values at the end;
+//   (B) the coupled polynomial part: lane 0 takes Gauss-Legendre nodes 0-3, lane 1 nodes
+//       4-6; all seven nodes travel through shared memory at once (two barriers per cell
+//       instead of 14); lane 0 ends with dEsde_dm, lane 1 with dEsde_ds and the energy.
+// Same [L][D][4] / [L][D][3] outputs and guard partials as esde_l96_split_kernel.
+// The last CTA of an interval (atomic ticket) folds the tile partials, applies the guard
+// (guard_interval, kernels.cuh) and -- when the fixed rule is not provably quad_vec's
+// answer -- runs the adaptive path (refine.cuh) on the spot: no guard / refine launches.
+// (A first version with 8 lanes per cell was shuffle-bound: 19 us; see profiles/.)
+#pragma once
+
+#include "l96_walk.cuh"
+#include "refine.cuh"
+
+namespace mfvgp {
+
+constexpr int kCoopTE = 32;                 // extended dims per CTA (26 outputs + halo)
+constexpr int kCoopW = 2;                   // lanes per cell
+constexpr int kCoopNT = kCoopTE * kCoopW;   // 64 threads
+
+struct CoopArgs {
+    EsdeArgs a;
+    GuardArgs g;
+    RefineArgs r;             // adaptive path of a flagged interval, run by its last CTA
+    unsigned *tickets;        // [n_end - n_begin], zero between launches
+    double theta;
+};
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+    return __shfl_xor_sync(0xffffffffu, v, m);
+}
+
+__global__ void __launch_bounds__(kCoopNT)
+esde_l96_coop_kernel(const CoopArgs ca) {
+    constexpr int TE = kCoopTE, TD = TE - 6;
+    const EsdeArgs &a = ca.a;
+    __shared__ double2 ms[kGL][TE], AC[kGL][TE], BD[kGL][TE];
+    __shared__ double red[9][TE + 1];
+    __shared__ int sh_last;
+
+    const int tid = threadIdx.x, l = tid & 1, e = tid >> 1;
+    const int tile = blockIdx.x % a.ntiles;
+    const int n = a.n_begin + blockIdx.x / a.ntiles;
+    const int d0 = tile * TD, D = a.D;
+    int j = (d0 - 3 + e) % D;
+    if (j < 0) j += D;
+    const bool has_energy = (e >= 2) && (e <= TE - 2);
+    const bool is_out = (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
+
+    const double ti = a.obs_times[n], tj = a.obs_times[n + 1];
+    const double *mp = a.mean + (int64_t)j * a.ldm + 3 * (int64_t)n;
+    const double *sp = a.vars + (int64_t)j * a.lds + 2 * (int64_t)n;
+    const double P0 = mp[0], P1 = mp[1], P2 = mp[2], P3 = mp[3];
+    double S0 = sp[0], S1 = sp[1], S2 = sp[2];
+    const double Sig = a.sigma[j];
+    if (a.log_vars) { S0 = exp(S0); S1 = exp(S1); S2 = exp(S2); }
+    const double dt = fabs(tj - ti);
+    const double inv_dt = fast_rcp(dt), inv_sig = fast_rcp(Sig), hid = 0.5 * inv_dt;
+
+    // ---- (A) rational part: lane l integrates Kronrod panel l ------------------------------
+    // (every cell of the warp takes part: the shuffles need all 32 lanes; halo cells work
+    // on their own valid, wrapped rows and their results are not used)
+    double aE, kS[3], eE[2], eS[2], m1S[2];
+    {
+        const double c = 0.25 + 0.5 * l;
+        const double a0 = S0, a1 = -3.0 * S0 + 4.0 * S1 - S2, a2 = 2.0 * (S0 - 2.0 * S1 + S2);
+        const double b0 = fma(a1, inv_dt, -Sig), b1 = 2.0 * a2 * inv_dt;
+        PanelSums s;
+        panel_sums(fma(fma(a2, c, a1), c, a0), 0.25 * fma(2.0 * c, a2, a1), 0.0625 * a2,
+                   fma(b1, c, b0), 0.25 * b1, s);
+        // panel -> basis sums (l96_walk.cuh sv3/sd3, written for a run-time panel centre c)
+        const double bc[3] = {fma(2.0 * c, c, fma(-3.0, c, 1.0)), 4.0 * c * (1.0 - c),
+                              c * (2.0 * c - 1.0)};
+        const double b1c[3] = {4.0 * c - 3.0, 4.0 - 8.0 * c, 4.0 * c - 1.0};
+        const double bpp[3] = {4.0, -8.0, 4.0};
+        double ks_p[3], es_p = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double sv = fma(bc[k], s.N0, fma(0.25 * b1c[k], s.N1, 0.03125 * bpp[k] * s.N2));
+            const double sd = fma(b1c[k], s.L0, 0.25 * bpp[k] * s.L1);
+            ks_p[k] = fma(hid, sd, -0.25 * sv);
+            const double dv = fma(bc[k], s.N0 - s.GN0, fma(0.25 * b1c[k], s.N1 - s.GN1,
+                                                          0.03125 * bpp[k] * (s.N2 - s.GN2)));
+            const double dd = fma(b1c[k], s.L0 - s.GL0, 0.25 * bpp[k] * (s.L1 - s.GL1));
+            const double kg = fma(hid, dd, -0.25 * dv);
+            es_p = fma(kg, kg, es_p);
+        }
+        const double dE = 0.25 * (s.kE - s.gE);
+        const double mv = fma(bc[0], s.N1, fma(0.25 * b1c[0], s.N2, 0.125 * s.N3));
+        const double md = fma(b1c[0], s.L1, s.L2);
+        const double m1 = fma(hid, md, -0.25 * mv)
+                          + fma(c_m1poly[2 * l + 1], inv_dt, c_m1poly[2 * l]);
+        const double eE_p = dE * dE, m1_p = m1 * m1;
+        // the other panel's results; panel 0 first in every sum
+        const double o_kE = shfl_xor_d(s.kE, 1), o_eE = shfl_xor_d(eE_p, 1),
+                     o_eS = shfl_xor_d(es_p, 1), o_m1 = shfl_xor_d(m1_p, 1);
+        aE = l ? o_kE + s.kE : s.kE + o_kE;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double o = shfl_xor_d(ks_p[k], 1);
+            kS[k] = l ? o + ks_p[k] : ks_p[k] + o;
+        }
+        eE[0] = l ? o_eE : eE_p; eE[1] = l ? eE_p : o_eE;
+        eS[0] = l ? o_eS : es_p; eS[1] = l ? es_p : o_eS;
+        m1S[0] = l ? o_m1 : m1_p; m1S[1] = l ? m1_p : o_m1;
+    }
+
+    // ---- (B) coupled polynomial part: lane 0 takes GL nodes 0-3, lane 1 nodes 4-6 ---------------
+    // all seven nodes travel through shared memory at once: two barriers per cell
+    const int g_lo = 4 * l, g_n = l ? 3 : 4;
+    double own[4];
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) {
+        own[gg] = 0.0;
+        if (gg < g_n) {
+            const double *T = c_gl + (g_lo + gg) * kTabStride;
+            const double m = P0 * T[T_B3] + P1 * T[T_B3 + 1] + P2 * T[T_B3 + 2] + P3 * T[T_B3 + 3];
+            const double dm = (P0 * T[T_DB3] + P1 * T[T_DB3 + 1] + P2 * T[T_DB3 + 2]
+                               + P3 * T[T_DB3 + 3]) * inv_dt;
+            const double s = S0 * T[T_B2] + S1 * T[T_B2 + 1] + S2 * T[T_B2 + 2];
+            ms[g_lo + gg][e] = make_double2(m, s);
+            own[gg] = (ca.theta - m) - dm;
+        }
+    }
+    __syncthreads();
+    double accE = 0.0;
+    if (has_energy) {
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+            if (gg < g_n) {
+                const int g = g_lo + gg;
+                const double *T = c_gl + g * kTabStride;
+                const double2 xa = ms[g][e + 1], xb = ms[g][e - 1], xc = ms[g][e - 2];
+                const double mb = xb.x, sb = xb.y;
+                const double u = xa.x - xc.x, su = xa.y + xc.y;
+                const double R = fma(u, mb, own[gg]);
+                const double t1 = sb * u, t2 = mb * su;
+                const double Ec = fma(R, R, fma(t1, u, fma(t2, mb, su * sb)));
+                const double w = T[T_V] * inv_sig, w2 = w + w;
+                const double wR2 = w2 * R;
+                AC[g][e] = make_double2(fma(wR2, mb, w2 * t1), w * fma(mb, mb, sb));
+                BD[g][e] = make_double2(fma(wR2, u, w2 * t2), w * fma(u, u, su));
+                own[gg] = -wR2;
+                accE = fma(w, Ec, accE);
+            }
+        }
+    }
+    __syncthreads();
+    double accM[4] = {0.0, 0.0, 0.0, 0.0}, accS[3] = {0.0, 0.0, 0.0};
+    if (is_out) {
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+            if (gg < g_n) {
+                const int g = g_lo + gg;
+                const double *T = c_gl + g * kTabStride;
+                const double2 lft = AC[g][e - 1], r = BD[g][e + 1], rr = AC[g][e + 2];
+                const double Gm = own[gg] + lft.x + r.x - rr.x;
+                const double Gs = lft.y + r.y + rr.y;
+                const double Hm = own[gg] * inv_dt;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) accM[k] += Gm * T[T_B3 + k] + Hm * T[T_DB3 + k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) accS[k] = fma(Gs, T[T_B2 + k], accS[k]);
+            }
+        }
+    }
+    // lane 0 ends with the dM sums, lane 1 with the dS sums and the energy (lane 0's part first)
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double mine = l ? (k < 3 ? accS[k] : accE) : accM[k];
+        const double send = l ? accM[k] : (k < 3 ? accS[k] : accE);
+        const double got = shfl_xor_d(send, 1);
+        v[k] = l ? got + mine : mine + got;
+    }
+
+    // ---- outputs (same algebra as esde_l96_split_kernel) ------------------------------------------
+    const double four_inv_dt = 4.0 * inv_dt;
+    const double polyS[3] = {dt * (1.0 / 6.0) - 1.0, dt * (4.0 / 6.0), dt * (1.0 / 6.0) + 1.0};
+    if (is_out && a.dm_out != nullptr) {
+        const double sc_gl = 0.5 * dt;
+        if (l == 0) {
+            double *om = a.dm_out + ((int64_t)n * D + j) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) om[k] = sc_gl * v[k];
+        } else {
+            double *os = a.ds_out + ((int64_t)n * D + j) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                os[k] = fma(sc_gl, v[k], fma(0.125 * dt * inv_sig, kS[k], 0.5 * inv_sig * polyS[k]));
+        }
+    }
+    if (l == 1) {                                  // this cell's guard partials
+        double r9[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (is_out) {
+            const double own_poly = dt * (S0 + 4.0 * S1 + S2) * (1.0 / 6.0) + (S2 - S0) - Sig * dt;
+            const double ksum_E = 0.25 * aE + 4.0 * v[3] * Sig + four_inv_dt * own_poly;
+            double own2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double o = fma(four_inv_dt, polyS[k], kS[k]);
+                own2 = fma(o, o, own2);
+            }
+            r9[0] = ksum_E * inv_sig; r9[1] = ksum_E * ksum_E;
+            r9[2] = eE[0]; r9[3] = eE[1]; r9[4] = eS[0]; r9[5] = eS[1];
+            r9[6] = own2; r9[7] = m1S[0]; r9[8] = m1S[1];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) red[i][e] = r9[i];
+    }
+    __syncthreads();
+    if (tid < 9) {                                 // fixed-order fold over the TE cells
+        double x = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < TE; ++c) x += red[tid][c];
+        a.part[(int64_t)blockIdx.x * kPartStride + tid] = x;
+        __threadfence();                           // the writers publish their partials
+    }
+    // ---- last CTA of this interval: fold the tiles, apply the guard ---------------------------------
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(ca.tickets + (n - a.n_begin), 1u);
+        sh_last = (t == (unsigned)a.ntiles - 1u);
+        if (sh_last) ca.tickets[n - a.n_begin] = 0u;
+    }
+    __syncthreads();
+    if (sh_last) {                                 // CTA-uniform
+        if (tid < 32) {
+            __threadfence();
+            guard_interval(ca.g, n, tid);
+        }
+        __syncthreads();
+        // quad_vec keeps bisecting where the fixed rule is not provably its answer
+        // (refine.cuh); rare, so the interval's last CTA does it on the spot
+        const int f = ca.g.flags[n];
+        if (tid == 0) ca.r.info[2 * n] = ca.r.info[2 * n + 1] = 0;
+        if (f) {
+            double *ws = ca.r.ws + (int64_t)(n - a.n_begin) * 2 * D * kMaxNE;
+            double *ws_fixed = ws + (int64_t)D * kMaxNE;
+            if (f & 1) refine_item<3, true, kCoopNT>(ca.r, n, ws, ws_fixed);
+            if ((f & 2) && ca.r.want_grad) refine_item<3, false, kCoopNT>(ca.r, n, ws, ws_fixed);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// E_cost tail for small problems (single GPU): gradient assembly
+// (free_energy.py:711-743), E_kl0 / E_obs terms (:309-310, :594-612, :733-738) and
+// -- in the last CTA to finish (atomic ticket) -- the final scalar sums of
+// final_kernel, in ONE launch.  One thread per entry of x; every load of a thread
+// is independent of the others (row tables rinv_row / y_dense instead of the
+// obs_idx -> obs_values chain), so the kernel is one memory round trip deep.
+// ---------------------------------------------------------------------------
+struct TailArgs {
+    AssembleArgs a;
+    FinalArgs f;
+    const double *y_dense;     // [M][D] observation of state dimension j at time k (0 if unobserved)
+    const double *rinv_row;    // [D] 1 / obs_noise of dimension j, 0 if unobserved
+    unsigned *ticket;          // [1], zero between launches
+};
+
+constexpr int kTailThreads = 256;
+
+__global__ void __launch_bounds__(kTailThreads)
+assemble_tail_kernel(const TailArgs t) {
+    __shared__ double sh_red[3 * (kTailThreads / 32)];
+    __shared__ int sh_last;
+    const AssembleArgs &a = t.a;
+    const int64_t idx = (int64_t)blockIdx.x * kTailThreads + threadIdx.x;
+    const int64_t nm = (int64_t)a.D * a.Nm, ntot = nm + (int64_t)a.D * a.Ns;
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (idx < ntot) {
+        const bool is_mean = idx < nm;
+        const int64_t r = is_mean ? idx : idx - nm;
+        const int W = is_mean ? a.Nm : a.Ns, step = is_mean ? 3 : 2, K = step + 1;
+        const int j = (int)(r / W), c = (int)(r - (int64_t)j * W);
+        const int n = c / step, k = c - step * n;
+        const double *ws = is_mean ? a.dm : a.ds;
+        const bool obs_col = k == 0 && n >= 1 && n <= a.M;
+        // independent loads first
+        const double xv = a.x[idx];
+        double own = 0.0, prev = 0.0, y = 0.0, Ri = 0.0, mu = 0.0, t0 = 1.0;
+        if (ws != nullptr) {
+            if (n < a.L) own = ws[((int64_t)n * a.D + j) * K + k];
+            if (k == 0 && n >= 1 && n - 1 < a.L) prev = ws[((int64_t)(n - 1) * a.D + j) * K + step];
+        }
+        if (obs_col) {
+            Ri = t.rinv_row[j];
+            y = t.y_dense[(int64_t)(n - 1) * a.D + j];
+        }
+        if (c == 0) { mu = a.mu0[j]; t0 = a.tau0[j]; }
+        double g = own;
+        g += prev;
+        if (is_mean) {
+            if (c == 0) {
+                const double z0 = xv - mu;
+                g += z0 / t0;
+                acc[1] += z0 * z0 / t0;
+            }
+            if (obs_col && Ri != 0.0) {
+                const double rr = y - xv;
+                g -= Ri * rr;
+                acc[2] += Ri * rr * rr;
+            }
+            if (a.grad) a.grad[idx] = g;
+        } else {
+            const double s = exp(xv);
+            if (c == 0) {
+                g += 0.5 * (1.0 / t0 - 1.0 / s);
+                acc[0] += log(t0 / s);
+                acc[1] += (s - t0) / t0;
+            }
+            if (obs_col && Ri != 0.0) {
+                g += 0.5 * Ri;
+                acc[2] += Ri * s;
+            }
+            if (a.grad) a.grad[idx] = g * s;             // free_energy.py:743
+        }
+    }
+    block_sum<3, kTailThreads>(acc, sh_red);
+    if (threadIdx.x == 0) {
+        double *p = a.apart + (int64_t)blockIdx.x * 4;
+        p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = 0.0;
+        __threadfence();
+        const unsigned k = atomicAdd(t.ticket, 1u);
+        sh_last = (k == gridDim.x - 1u);
+        if (sh_last) t.ticket[0] = 0u;
+    }
+    __syncthreads();
+    if (sh_last) {
+        __threadfence();
+        final_body<kTailThreads>(t.f);
+    }
+}
+
+}  // namespace mfvgp

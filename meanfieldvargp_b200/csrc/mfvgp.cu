@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -12,6 +14,7 @@
 #include "nccl_dyn.h"
 #include "refine.cuh"
 #include "l96_walk.cuh"
+#include "l96_coop.cuh"
 #include "scg.cuh"
 
 using namespace mfvgp;
@@ -39,6 +42,10 @@ struct mfvgp_handle {
     int system = 0, D = 0, M = 0, d = 0, device = 0;
     int L = 0, n_begin = 0, n_end = 0, Nm = 0, Ns = 0, ntheta = 0;
     int te = 64, ntiles = 1;
+    int coop = 0;     // small L96 problems: esde_l96_coop_kernel + assemble_tail_kernel (l96_coop.cuh)
+    unsigned *tickets = nullptr;
+    double *y_dense = nullptr, *rinv_row = nullptr;   // row tables of assemble_tail_kernel
+    int tail_grid = 1;
     double theta_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int rule = 1;     // 1: split rule (default), 0: 42-node coupled rule (MFVGP_RULE=gk42)
     // fused E_cost kernel (L96, split rule): TE x TN tile, grid = fntn * fntiles
@@ -78,6 +85,14 @@ struct mfvgp_handle {
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
 };
+
+// cudaSetDevice on every entry costs microseconds; query the current device first
+static inline cudaError_t use_device(int device) {
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess || cur != device) e = cudaSetDevice(device);
+    return e;
+}
 
 static int dev_alloc(double **p, size_t n) {
     CK(cudaMalloc((void **)p, (n ? n : 1) * sizeof(double)));
@@ -138,6 +153,15 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         std::string path = path_env ? path_env : (fuse_env && fuse_env[0] == '1' ? "fused" : "");
         if (path.empty()) path = cells > 148 * 512 ? "walk" : "split";
         h->fused = path == "walk" ? 2 : (path == "fused" ? 1 : 0);
+    }
+    if (system == MFVGP_SYS_L96 && h->rule == 1 && h->fused == 0 && cells <= 148 * 512) {
+        const char *coop_env = getenv("MFVGP_COOP");
+        h->coop = (coop_env && coop_env[0] == '0') ? 0 : 1;
+        if (h->coop) {
+            h->te = kCoopTE;
+            h->ntiles = (D + kCoopTE - 7) / (kCoopTE - 6);
+            h->tail_grid = (int)(((int64_t)D * (h->Nm + h->Ns) + kTailThreads - 1) / kTailThreads);
+        }
     }
     if (system == MFVGP_SYS_L96) {
         if (h->fused == 2) {
@@ -205,15 +229,22 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
                                 kPartStride) ||
         dev_alloc(&h->fedge_m, (size_t)h->fntn * D) || dev_alloc(&h->fedge_s, (size_t)h->fntn * D) ||
         dev_alloc(&h->fapart, (size_t)h->fntn * h->fntiles * 4) ||
-        dev_alloc(&h->esde_n, L) || dev_alloc(&h->apart, (size_t)D * 4) ||
+        dev_alloc(&h->esde_n, L) || dev_alloc(&h->apart, (size_t)(D > h->tail_grid ? D : h->tail_grid) * 4) ||
         dev_alloc(&h->out_ws, 16) || dev_alloc(&h->rec_ws, 16))
         return MFVGP_ERR_CUDA;
     h->refine_grid = 2 * nl < 296 ? 2 * nl : 296;
-    if (dev_alloc(&h->refine_ws, (size_t)h->refine_grid * 2 * D * kMaxNE)) return MFVGP_ERR_CUDA;
+    {   // scratch of the adaptive path: one slot per refine CTA, or per interval (coop path)
+        const int slots = h->coop && nl > h->refine_grid ? nl : h->refine_grid;
+        if (dev_alloc(&h->refine_ws, (size_t)slots * 2 * D * kMaxNE)) return MFVGP_ERR_CUDA;
+    }
+    if (h->coop && (dev_alloc(&h->y_dense, (size_t)M * D) || dev_alloc(&h->rinv_row, D)))
+        return MFVGP_ERR_CUDA;
     CK(cudaMalloc((void **)&h->refine_info, 2 * L * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->refine_status, sizeof(int32_t)));
     CK(cudaMemset(h->refine_info, 0, 2 * L * sizeof(int32_t)));
     CK(cudaMemset(h->refine_status, 0, sizeof(int32_t)));
+    CK(cudaMalloc((void **)&h->tickets, (L + 2) * sizeof(unsigned)));
+    CK(cudaMemset(h->tickets, 0, (L + 2) * sizeof(unsigned)));
     CK(cudaMalloc((void **)&h->obs_idx, D * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->flags, L * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->status_ws, sizeof(int32_t)));
@@ -234,7 +265,8 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->scg_vec[0], h->scg_vec[1], h->scg_vec[2], h->scg_vec[3], h->scg_vec[4],
                     h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal,
                     h->refine_ws, h->refine_info, h->refine_status, h->edge_send, h->edge_recv,
-                    h->gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart};
+                    h->gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
+                    h->y_dense, h->rinv_row};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
@@ -251,7 +283,7 @@ extern "C" int mfvgp_set_sde(mfvgp_handle *h, const double *sigma_h, const doubl
     ARG(ntheta == need, "mfvgp_set_sde: wrong number of drift parameters");
     for (int i = 0; i < h->D; ++i)   // stochastic_process.py:112-115
         ARG(sigma_h[i] > 0.0, "SDE noise vector is not positive");
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     CK(cudaMemcpy(h->sigma, sigma_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->theta, theta_h, ntheta * sizeof(double), cudaMemcpyHostToDevice));
     h->ntheta = ntheta;
@@ -262,7 +294,7 @@ extern "C" int mfvgp_set_sde(mfvgp_handle *h, const double *sigma_h, const doubl
 
 extern "C" int mfvgp_set_prior(mfvgp_handle *h, const double *mu0_h, const double *tau0_h) {
     ARG(h && mu0_h && tau0_h, "mfvgp_set_prior: NULL argument");
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     CK(cudaMemcpy(h->mu0, mu0_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->tau0, tau0_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
     h->have_prior = true;
@@ -283,17 +315,41 @@ extern "C" int mfvgp_set_obs(mfvgp_handle *h, const double *obs_times_h,
     for (int i = 0; i < h->d; ++i) prod *= obs_noise_h[i];
     const double clamped = fmax(fmin(prod, 1.0e300), 1.0e-300);
     h->eobs_const = h->M * (h->d * 1.8378770664093453 + log(clamped));
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     CK(cudaMemcpy(h->obs_times, obs_times_h, h->M * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->obs_values, obs_values_h, (size_t)h->M * h->d * sizeof(double),
                   cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->obs_noise, obs_noise_h, h->d * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->obs_idx, idx.data(), h->D * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (h->y_dense) {
+        std::vector<double> yd((size_t)h->M * h->D, 0.0), ri(h->D, 0.0);
+        for (int j = 0; j < h->D; ++j) {
+            if (idx[j] < 0) continue;
+            ri[j] = 1.0 / obs_noise_h[idx[j]];
+            for (int k = 0; k < h->M; ++k)
+                yd[(size_t)k * h->D + j] = obs_values_h[(size_t)k * h->d + idx[j]];
+        }
+        CK(cudaMemcpy(h->y_dense, yd.data(), yd.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->rinv_row, ri.data(), ri.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     h->have_obs = true;
     return MFVGP_OK;
 }
 
 // ---- launch helpers ---------------------------------------------------------
+static RefineArgs refine_args(mfvgp_handle *h, const double *mean, int64_t ldm, const double *vars,
+                              int64_t lds, int log_vars, double *ds, int delta_mode) {
+    RefineArgs r;
+    r.mean = mean; r.vars = vars; r.ldm = ldm; r.lds = lds;
+    r.obs_times = h->obs_times; r.sigma = h->sigma; r.theta = h->theta;
+    r.flags = h->flags; r.esde_n = h->esde_n; r.ds_out = ds; r.ws = h->refine_ws;
+    r.delta_mode = delta_mode;
+    r.info = h->refine_info; r.status = h->refine_status;
+    r.D = h->D; r.n_begin = h->n_begin; r.n_end = h->n_end; r.log_vars = log_vars;
+    r.want_grad = ds != nullptr;
+    return r;
+}
+
 static int launch_guard_refine(mfvgp_handle *h, const double *mean, int64_t ldm,
                                const double *vars, int64_t lds, int log_vars, double *ds,
                                int ntiles, int delta_mode, cudaStream_t st) {
@@ -305,14 +361,7 @@ static int launch_guard_refine(mfvgp_handle *h, const double *mean, int64_t ldm,
     h->launches++;
     CK(cudaGetLastError());
     // adaptive path for the flagged (interval, integrand) pairs; unflagged CTAs exit at once
-    RefineArgs r;
-    r.mean = mean; r.vars = vars; r.ldm = ldm; r.lds = lds;
-    r.obs_times = h->obs_times; r.sigma = h->sigma; r.theta = h->theta;
-    r.flags = h->flags; r.esde_n = h->esde_n; r.ds_out = ds; r.ws = h->refine_ws;
-    r.delta_mode = delta_mode;
-    r.info = h->refine_info; r.status = h->refine_status;
-    r.D = h->D; r.n_begin = h->n_begin; r.n_end = h->n_end; r.log_vars = log_vars;
-    r.want_grad = ds != nullptr;
+    const RefineArgs r = refine_args(h, mean, ldm, vars, lds, log_vars, ds, delta_mode);
     switch (h->system) {
         case MFVGP_SYS_DW: refine_kernel<0><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
         case MFVGP_SYS_OU: refine_kernel<1><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
@@ -345,7 +394,16 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         case MFVGP_SYS_L63: esde_small_kernel<2><<<nl, 64, 0, st>>>(a); break;
         default: {
             const unsigned grid = (unsigned)nl * h->ntiles;
-            if (h->rule == 0) {
+            if (h->coop) {
+                CoopArgs c;
+                c.a = a;
+                c.g.part = h->part; c.g.obs_times = h->obs_times; c.g.esde_n = h->esde_n;
+                c.g.flags = h->flags; c.g.n_begin = h->n_begin; c.g.n_end = h->n_end;
+                c.g.ntiles = h->ntiles;
+                c.r = refine_args(h, mean, ldm, vars, lds, log_vars, ds, 0);
+                c.tickets = h->tickets; c.theta = h->theta_host[0];
+                esde_l96_coop_kernel<<<grid, kCoopNT, 0, st>>>(c);
+            } else if (h->rule == 0) {
                 if (h->te == 32) esde_l96_kernel<32><<<grid, 32, 0, st>>>(a);
                 else if (h->te == 64) esde_l96_kernel<64><<<grid, 64, 0, st>>>(a);
                 else esde_l96_kernel<128><<<grid, 128, 0, st>>>(a);
@@ -362,6 +420,7 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         CK(cudaEventRecord(ev1, st));
         h->timing_events.emplace_back(ev0, ev1);
     }
+    if (h->coop) return MFVGP_OK;          // guard and adaptive path ran inside the kernel
     return launch_guard_refine(h, mean, ldm, vars, lds, log_vars, ds, h->ntiles, 0, st);
 }
 
@@ -547,7 +606,7 @@ extern "C" int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void 
     if (!nccl().load()) { g_err = "NCCL (libnccl.so.2) could not be loaded"; return MFVGP_ERR_CUDA; }
     ARG((rank == 0) == (h->n_begin == 0) && (rank == world - 1) == (h->n_end == h->L),
         "mfvgp_comm_init: the handle's interval range does not match its rank");
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     NCK(nccl().CommInitRank(&h->comm, world, id, rank));
@@ -568,7 +627,7 @@ extern "C" int mfvgp_esde(mfvgp_handle *h, const double *mean_pts_d, int64_t ldm
         g_err = "mfvgp_esde: set_sde/set_obs not called";
         return MFVGP_ERR_STATE;
     }
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = launch_esde(h, mean_pts_d, ldm, vars_pts_d, lds, 0,
                          want_grad ? dEsde_dm_d : nullptr, want_grad ? dEsde_ds_d : nullptr, st);
@@ -588,7 +647,7 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
         g_err = "mfvgp_ecost: set_sde/set_prior/set_obs not called";
         return MFVGP_ERR_STATE;
     }
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const double *mean = x_d;
     const double *lvar = x_d + (int64_t)h->D * h->Nm;
@@ -611,6 +670,22 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
     a.obs_idx = h->obs_idx; a.grad = want_grad ? grad_d : nullptr; a.apart = h->apart;
     a.D = h->D; a.M = h->M; a.d = h->d; a.Nm = h->Nm; a.Ns = h->Ns;
     a.n_begin = h->n_begin; a.n_end = h->n_end; a.L = h->L; a.with_e0 = h->n_begin == 0;
+    if (h->coop && h->world == 1) {
+        // small problems: assembly and the final scalar sums in one launch
+        TailArgs t;
+        t.a = a;
+        t.y_dense = h->y_dense; t.rinv_row = h->rinv_row;
+        const int nb = h->tail_grid;
+        t.f.esde_n = h->esde_n; t.f.flags = h->flags; t.f.apart = h->apart;
+        t.f.out = out_d; t.f.status = status_d; t.f.refine_status = h->refine_status;
+        t.f.record9 = 0; t.f.n_begin = h->n_begin; t.f.n_end = h->n_end; t.f.D = nb;
+        t.f.with_e0 = 1; t.f.eobs_const = h->eobs_const;
+        t.ticket = h->tickets + h->L + 1;
+        assemble_tail_kernel<<<nb, kTailThreads, 0, st>>>(t);
+        h->launches++;
+        CK(cudaGetLastError());
+        return MFVGP_OK;
+    }
     assemble_kernel<<<h->D, 256, 0, st>>>(a);
     h->launches++;
     CK(cudaGetLastError());
@@ -624,8 +699,91 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
 static int ensure_host_staging(mfvgp_handle *h) {
     const size_t nx = (size_t)h->D * (h->Nm + h->Ns);
     if (!h->x_dev) {
-        if (dev_alloc(&h->x_dev, nx) || dev_alloc(&h->grad_dev, nx)) return MFVGP_ERR_CUDA;
+        // grad_dev: gradient followed by [F, E0, Esde, Eobs, status] (packed host entry)
+        if (dev_alloc(&h->x_dev, nx) || dev_alloc(&h->grad_dev, nx + 8)) return MFVGP_ERR_CUDA;
     }
+    return MFVGP_OK;
+}
+
+// ---- page-locked host pool ------------------------------------------------------------
+namespace {
+struct HostPool {
+    std::mutex mu;
+    std::multimap<int64_t, void *> free_blocks;      // size -> block
+    std::map<void *, int64_t> live;                   // block -> size
+    int64_t cached_bytes = 0;
+};
+HostPool &host_pool() {
+    static HostPool *p = new HostPool();              // never destroyed: outlives the CUDA context
+    return *p;
+}
+constexpr int64_t kHostPoolCap = 1LL << 30;           // keep at most 1 GiB of idle blocks
+}  // namespace
+
+extern "C" void *mfvgp_host_alloc(int64_t bytes) {
+    if (bytes <= 0) bytes = 8;
+    bytes = (bytes + 4095) / 4096 * 4096;
+    HostPool &hp = host_pool();
+    {
+        std::lock_guard<std::mutex> lk(hp.mu);
+        auto it = hp.free_blocks.find(bytes);
+        if (it != hp.free_blocks.end()) {
+            void *p = it->second;
+            hp.free_blocks.erase(it);
+            hp.cached_bytes -= bytes;
+            hp.live[p] = bytes;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        g_err = "mfvgp_host_alloc: cudaMallocHost failed";
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(hp.mu);
+    hp.live[p] = bytes;
+    return p;
+}
+
+extern "C" void mfvgp_host_free(void *p) {
+    if (!p) return;
+    HostPool &hp = host_pool();
+    int64_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(hp.mu);
+        auto it = hp.live.find(p);
+        if (it == hp.live.end()) return;
+        bytes = it->second;
+        hp.live.erase(it);
+        if (hp.cached_bytes + bytes <= kHostPoolCap) {
+            hp.free_blocks.emplace(bytes, p);
+            hp.cached_bytes += bytes;
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
+
+extern "C" int mfvgp_ecost_host_packed(mfvgp_handle *h, const double *x_h, int want_grad,
+                                       double *buf_h) {
+    ARG(h && x_h && buf_h, "mfvgp_ecost_host_packed: NULL argument");
+    CK(use_device(h->device));
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const size_t nx = (size_t)h->D * (h->Nm + h->Ns);
+    double *out_d = h->grad_dev + nx;
+    CK(cudaMemcpyAsync(h->x_dev, x_h, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = mfvgp_ecost(h, h->x_dev, want_grad, out_d, h->grad_dev,
+                     reinterpret_cast<int32_t *>(out_d + 4), h->stream);
+    if (rc) return rc;
+    if (want_grad)
+        CK(cudaMemcpyAsync(buf_h, h->grad_dev, (nx + 5) * sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+    else
+        CK(cudaMemcpyAsync(buf_h + nx, out_d, 5 * sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return MFVGP_OK;
 }
 
@@ -633,7 +791,7 @@ extern "C" int mfvgp_ecost_host(mfvgp_handle *h, const double *x_h, int want_gra
                                 double *out_h, double *grad_h, int32_t *status_h) {
     ARG(h && x_h && out_h && status_h, "mfvgp_ecost_host: NULL argument");
     ARG(!want_grad || grad_h, "mfvgp_ecost_host: gradient buffer is NULL");
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     int rc = ensure_host_staging(h);
     if (rc) return rc;
     const size_t nx = (size_t)h->D * (h->Nm + h->Ns);
@@ -657,7 +815,7 @@ extern "C" int mfvgp_esde_host(mfvgp_handle *h, const double *mean_pts_h,
                                double *dEsde_dm_h, double *dEsde_ds_h, int32_t *status_h) {
     ARG(h && mean_pts_h && vars_pts_h && Esde_h && status_h, "mfvgp_esde_host: NULL argument");
     ARG(!want_grad || (dEsde_dm_h && dEsde_ds_h), "mfvgp_esde_host: gradient buffers are NULL");
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     int rc = ensure_host_staging(h);
     if (rc) return rc;
     const size_t nm = (size_t)h->D * h->Nm, ns = (size_t)h->D * h->Ns;
@@ -690,7 +848,7 @@ extern "C" int mfvgp_ekl0_host(mfvgp_handle *h, const double *m0_h, const double
     ARG(h && m0_h && s0_h && E0_h && status_h, "mfvgp_ekl0_host: NULL argument");
     ARG(!want_grad || (dm0_h && ds0_h), "mfvgp_ekl0_host: gradient buffers are NULL");
     if (!h->have_prior) { g_err = "mfvgp_ekl0_host: set_prior not called"; return MFVGP_ERR_STATE; }
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     int rc = ensure_host_staging(h);
     if (rc) return rc;
     const int D = h->D;
@@ -722,7 +880,7 @@ extern "C" int mfvgp_eobs_host(mfvgp_handle *h, const double *mean_obs_h,
     ARG(h && mean_obs_h && vars_obs_h && Eobs_h && status_h, "mfvgp_eobs_host: NULL argument");
     ARG(!want_grad || (dm_h && ds_h), "mfvgp_eobs_host: gradient buffers are NULL");
     if (!h->have_obs) { g_err = "mfvgp_eobs_host: set_obs not called"; return MFVGP_ERR_STATE; }
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     int rc = ensure_host_staging(h);
     if (rc) return rc;
     const size_t dm_n = (size_t)h->d * h->M;               // <= D*Nm/3, fits the staging
@@ -754,7 +912,7 @@ extern "C" int mfvgp_eobs_host(mfvgp_handle *h, const double *mean_obs_h,
 
 extern "C" int mfvgp_refine_info(mfvgp_handle *h, int32_t *info_h) {
     ARG(h && info_h, "mfvgp_refine_info: NULL argument");
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(info_h, h->refine_info, 2 * h->L * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return MFVGP_OK;
@@ -762,7 +920,7 @@ extern "C" int mfvgp_refine_info(mfvgp_handle *h, int32_t *info_h) {
 
 extern "C" int mfvgp_timing(mfvgp_handle *h, int enable, double *total_ms, int64_t *count) {
     ARG(h != nullptr, "mfvgp_timing: NULL handle");
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     double tot = 0.0;
     int64_t cnt = 0;
     for (auto &pr : h->timing_events) {
@@ -887,7 +1045,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
                          void *cuda_stream) {
     ARG(h && x_d && fx_hist_h && dfx_hist_h && result_h, "mfvgp_scg: NULL argument");
     ARG(max_it >= 1, "mfvgp_scg: max_it must be positive");
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int64_t n = (int64_t)h->D * (h->Nm + h->Ns);
     VecMap vm;
@@ -1029,7 +1187,7 @@ extern "C" int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x
                               double f_tol, double *fx_hist_h, double *dfx_hist_h,
                               double *result_h) {
     ARG(h && x_h, "mfvgp_scg_host: NULL argument");
-    CK(cudaSetDevice(h->device));
+    CK(use_device(h->device));
     int rc = ensure_host_staging(h);
     if (rc) return rc;
     const size_t nx = (size_t)h->D * (h->Nm + h->Ns);

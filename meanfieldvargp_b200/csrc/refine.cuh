@@ -230,13 +230,12 @@ __device__ __forceinline__ void gk_error(double n_kg2, double n_dabs2, double n_
     if (rnd > 2.2250738585072014e-308) err = fmax(err, rnd);
 }
 
-template <int SYS, bool ENERGY>
+template <int SYS, bool ENERGY, int NT = kRefThreads>
 __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_fixed) {
     using RE = RowEval<SYS>;
     constexpr int NE = ENERGY ? 1 : RE::NJ * 3;
     __shared__ double h_err[kHeapCap], h_a[kHeapCap], h_b[kHeapCap];
-    __shared__ double sh_red[8 * (kRefThreads / 32)];
-    __shared__ double bc[8];            // broadcast scalars
+    __shared__ double sh_red[8 * (NT / 32)];
     __shared__ int h_cnt, batch_n, stop_flag;
     __shared__ double b_err[kHeapCap], b_a[kHeapCap], b_b[kHeapCap];
 
@@ -248,7 +247,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
     // ---- initial panel [0,1] ------------------------------------------------
     {
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int i = threadIdx.x; i < D; i += kRefThreads) {
+        for (int i = threadIdx.x; i < D; i += NT) {
             RE ev;
             ev.load(a, n, i, dt);
             double integ[NE];
@@ -259,7 +258,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
                 acc[3] += integ[e] * integ[e];
             }
         }
-        block_sum<7, kRefThreads>(acc, sh_red);
+        block_sum<7, NT>(acc, sh_red);
         if (threadIdx.x == 0) {
             double e0, r0;
             gk_error(acc[0], acc[1], acc[2], e0, r0);
@@ -305,7 +304,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
         for (int t = 0; t < nb; ++t) {
             const double pa = b_a[t], pb = b_b[t], pc = 0.5 * (pa + pb);
             double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-            for (int i = threadIdx.x; i < D; i += kRefThreads) {
+            for (int i = threadIdx.x; i < D; i += NT) {
                 RE ev;
                 ev.load(a, n, i, dt);
                 double i_old[NE], i_l[NE], i_r[NE], dummy[3] = {0, 0, 0};
@@ -320,7 +319,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
                     if (!ENERGY && pa == 0.0 && pb == 1.0) ws_fixed[(int64_t)i * NE + e] = i_l[e] + i_r[e];
                 }
             }
-            block_sum<7, kRefThreads>(acc, sh_red);
+            block_sum<7, NT>(acc, sh_red);
             if (threadIdx.x == 0) {
                 double e1, r1, e2, r2;
                 gk_error(acc[0], acc[1], acc[2], e1, r1);
@@ -337,13 +336,13 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
         // |global_integral| after the batch
         {
             double acc[1] = {0.0};
-            for (int i = threadIdx.x; i < D; i += kRefThreads)
+            for (int i = threadIdx.x; i < D; i += NT)
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     const double g = ws[(int64_t)i * NE + e];
                     acc[0] += g * g;
                 }
-            block_sum<1, kRefThreads>(acc, sh_red);
+            block_sum<1, NT>(acc, sh_red);
             if (threadIdx.x == 0) {
                 normG = sqrt(acc[0]);
                 if (h_cnt >= 2) {
@@ -364,12 +363,12 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
     // ---- write the refined integral back ---------------------------------------
     if (ENERGY) {
         double acc[1] = {0.0};
-        for (int i = threadIdx.x; i < D; i += kRefThreads) acc[0] += ws[i] / a.sigma[i];
-        block_sum<1, kRefThreads>(acc, sh_red);
+        for (int i = threadIdx.x; i < D; i += NT) acc[0] += ws[i] / a.sigma[i];
+        block_sum<1, NT>(acc, sh_red);
         if (threadIdx.x == 0) a.esde_n[n] = 0.5 * acc[0];
     } else if (a.ds_out != nullptr) {
         __syncthreads();
-        for (int j = threadIdx.x; j < D; j += kRefThreads) {
+        for (int j = threadIdx.x; j < D; j += NT) {
             double o[3] = {0.0, 0.0, 0.0};
             if (SYS == 3) {
                 const int src[4] = {j, (j + D - 1) % D, (j + 1) % D, (j + 2) % D};

@@ -104,8 +104,7 @@ class FreeEnergy(object):
                                           self.dim_D, self.num_M, self.dim_d, self.device,
                                           int(n0), int(n1)), "mfvgp_create")
         self.intervals = (int(n0), self.num_L if n1 < 0 else int(n1))
-        self._sde_sent = None
-        self._prior_sent = None
+        self._params_sent = None
         self._push_obs()
         self._sync_params()
 
@@ -131,19 +130,23 @@ class FreeEnergy(object):
                    "mfvgp_set_obs")
 
     def _sync_params(self):
-        sde_key = (self.sigma.tobytes(), self.theta.tobytes())
-        if sde_key != self._sde_sent:
+        """
+        Re-reads theta, sigma, mu0, tau0 on every call (cheap byte comparison, ~2 us);
+        uploads only what changed.
+        """
+        key = (self.sigma.tobytes(), self.theta.tobytes(), self._mu0.tobytes(),
+               self._tau0.tobytes())
+        if key == self._params_sent:
+            return
+        if key[:2] != (self._params_sent or (None, None))[:2]:
             s, t = _f64(self.sigma), _f64(self.theta)
             _lib.check(self._lib.mfvgp_set_sde(self._h, _ptr(s), _ptr(t), t.size),
                        "mfvgp_set_sde")
-            self._sde_sent = sde_key
         mu0 = _f64(np.broadcast_to(self._mu0, (self.dim_D,)))
         tau0 = _f64(np.broadcast_to(self._tau0, (self.dim_D,)))
-        prior_key = (mu0.tobytes(), tau0.tobytes())
-        if prior_key != self._prior_sent:
-            _lib.check(self._lib.mfvgp_set_prior(self._h, _ptr(mu0), _ptr(tau0)),
-                       "mfvgp_set_prior")
-            self._prior_sent = prior_key
+        _lib.check(self._lib.mfvgp_set_prior(self._h, _ptr(mu0), _ptr(tau0)),
+                   "mfvgp_set_prior")
+        self._params_sent = key
 
     # ---- accessors, free_energy.py:181-279 ---------------------------------
     @property
@@ -308,34 +311,38 @@ class FreeEnergy(object):
         want = 1 if output_gradients else 0
         if _is_tensor(x):
             import torch
-            xd = x.contiguous()
+            xd = x if x.is_contiguous() else x.contiguous()
             if xd.numel() != n:
                 raise ValueError(f"E_cost: x has {xd.numel()} entries, expected {n}")
-            out = torch.empty(4, dtype=torch.float64, device=xd.device)
-            st = torch.empty(1, dtype=torch.int32, device=xd.device)
-            grad = torch.empty(n, dtype=torch.float64, device=xd.device) if want else None
-            stream = torch.cuda.current_stream(xd.device).cuda_stream
-            _lib.check(self._lib.mfvgp_ecost(self._h, xd.data_ptr(), want, out.data_ptr(),
+            dev = xd.device
+            # out = [F, E0, Esde, Eobs, status bits (int32 in the 5th slot)]
+            out = torch.empty(5, dtype=torch.float64, device=dev)
+            grad = torch.empty(n, dtype=torch.float64, device=dev) if want else None
+            stream = torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None
+                                                        else torch.cuda.current_device())
+            p_out = out.data_ptr()
+            _lib.check(self._lib.mfvgp_ecost(self._h, xd.data_ptr(), want, p_out,
                                              grad.data_ptr() if want else None,
-                                             st.data_ptr(), stream), "mfvgp_ecost")
+                                             p_out + 32, stream), "mfvgp_ecost")
             self.last_out = out
-            self.last_status_tensor = st
             return (out[0], grad) if output_gradients else out[0]
-        xh = _f64(x).ravel()
+        xh = x if (type(x) is np.ndarray and x.dtype == np.float64 and x.ndim == 1
+                   and x.flags.c_contiguous) else _f64(x).ravel()
         if xh.size != n:
             raise ValueError(f"E_cost: x has {xh.size} entries, expected {n}")
-        out = np.empty(4)
-        status = ctypes.c_int32()
-        grad = np.empty(n) if want else None
-        _lib.check(self._lib.mfvgp_ecost_host(self._h, _ptr(xh), want, _ptr(out),
-                                              _ptr(grad) if want else None,
-                                              ctypes.byref(status)), "mfvgp_ecost_host")
-        self.last_status = status.value
+        # one page-locked buffer receives [gradient | F, E0, Esde, Eobs | status] in one DMA
+        buf = _lib.pinned_empty(n + 8)
+        _lib.check(self._lib.mfvgp_ecost_host_packed(self._h, xh.ctypes.data, want,
+                                                     buf.ctypes.data), "mfvgp_ecost_host_packed")
+        out = buf[n:n + 4]
+        status = int(buf[n + 4:n + 5].view(np.int32)[0])
+        self.last_status = status
         self.last_terms = {"F": out[0], "E0": out[1], "Esde": out[2], "Eobs": out[3]}
-        self._raise_on_status(status.value, E0=out[1], Esde=out[2], Eobs=out[3])
+        if status & 7:
+            self._raise_on_status(status, E0=out[1], Esde=out[2], Eobs=out[3])
         if not output_gradients:
             return float(out[0])
-        return float(out[0]), grad
+        return float(out[0]), buf[:n]
 
     # ---- find_minimum, free_energy.py:753-862 --------------------------------
     def find_minimum(self, x0, max_iter=100, x_tol=1.0e-5, f_tol=1.0e-5,

@@ -160,14 +160,19 @@ def _check_path_equals_split(path, D, M, rough, monkeypatch, ftile=None):
     g = synthetic_l96(D, M, seed=D + M)
     x = _roughen(g, D, M, rough)
     monkeypatch.setenv("MFVGP_PATH", "split")
+    monkeypatch.setenv("MFVGP_COOP", "0")
     fe0 = make_free_energy(g)
     F0, g0 = fe0.E_cost(x)
     info0 = fe0.refine_info()
-    monkeypatch.setenv("MFVGP_PATH", path)
+    if path == "coop":              # split path with the cooperative small-problem kernels
+        monkeypatch.setenv("MFVGP_COOP", "1")
+    else:
+        monkeypatch.setenv("MFVGP_PATH", path)
     if ftile:
         monkeypatch.setenv("MFVGP_FTILE", ftile)
     fe1 = make_free_energy(g)
     monkeypatch.delenv("MFVGP_PATH")
+    monkeypatch.delenv("MFVGP_COOP")
     monkeypatch.delenv("MFVGP_FTILE", raising=False)
     F1, g1 = fe1.E_cost(x)
     assert np.array_equal(fe1.refine_info(), info0)
@@ -205,6 +210,30 @@ def test_walk_ecost_equals_split(D, M, rough, ftile, monkeypatch):
     single-interval runs and the maximum run length.
     """
     _check_path_equals_split("walk", D, M, rough, monkeypatch, ftile)
+
+
+@pytest.mark.parametrize("D,M,rough", [(4, 2, False), (5, 3, False), (26, 9, True), (27, 5, True),
+                                       (40, 7, False), (67, 12, True), (123, 40, True),
+                                       (500, 16, False), (500, 16, True), (300, 200, True)])
+def test_coop_ecost_equals_split(D, M, rough, monkeypatch):
+    """
+    Small problems run esde_l96_coop_kernel (8 lanes per cell, guard folded in by the
+    last CTA of each interval) + assemble_tail_kernel (assembly + final sums); they must
+    reproduce the one-thread-per-cell split kernel + assemble_kernel + final_kernel.
+    """
+    _check_path_equals_split("coop", D, M, rough, monkeypatch)
+    # E_sde alone goes through the same kernel
+    g = synthetic_l96(D, M, seed=D + M)
+    fe = make_free_energy(g)
+    mp = g["x0"][:fe.num_mp].reshape(D, 3 * M + 4)
+    sp = np.exp(g["x0"][fe.num_mp:].reshape(D, 2 * M + 3))
+    Es, dm, ds = fe.E_sde(mp, sp)
+    monkeypatch.setenv("MFVGP_COOP", "0")
+    fe0 = make_free_energy(g)
+    monkeypatch.delenv("MFVGP_COOP")
+    Es0, dm0, ds0 = fe0.E_sde(mp, sp)
+    assert abs(Es - Es0) <= 1e-13 * abs(Es0)
+    assert rel_err(dm, dm0) <= 1e-12 and rel_err(ds, ds0) <= 1e-12
 
 
 @pytest.mark.parametrize("name", EVAL_CASES)
