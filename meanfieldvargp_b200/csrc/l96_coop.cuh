@@ -31,6 +31,16 @@ struct CoopArgs {
     double theta;
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the
+// programmatic-stream-serialization attribute may be scheduled while its predecessor in
+// the stream is still running; pdl_wait() blocks until that predecessor has completed and
+// its writes are visible (no-op for a normal launch), pdl_launch_dependents() lets the
+// successor's CTAs be scheduled early.  Hides ~2 us of launch latency per kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
     return __shfl_xor_sync(0xffffffffu, v, m);
 }
@@ -52,6 +62,8 @@ esde_l96_coop_kernel(const CoopArgs ca) {
     const bool has_energy = (e >= 2) && (e <= TE - 2);
     const bool is_out = (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
 
+    pdl_launch_dependents();
+    pdl_wait();                     // x and the workspaces belong to the predecessor until here
     const double ti = a.obs_times[n], tj = a.obs_times[n + 1];
     const double *mp = a.mean + (int64_t)j * a.ldm + 3 * (int64_t)n;
     const double *sp = a.vars + (int64_t)j * a.lds + 2 * (int64_t)n;
@@ -274,6 +286,8 @@ assemble_tail_kernel(const TailArgs t) {
     const int64_t idx = (int64_t)blockIdx.x * kTailThreads + threadIdx.x;
     const int64_t nm = (int64_t)a.D * a.Nm, ntot = nm + (int64_t)a.D * a.Ns;
     double acc[3] = {0.0, 0.0, 0.0};
+    pdl_launch_dependents();
+    pdl_wait();
     if (idx < ntot) {
         const bool is_mean = idx < nm;
         const int64_t r = is_mean ? idx : idx - nm;
