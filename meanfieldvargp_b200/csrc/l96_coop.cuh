@@ -54,11 +54,17 @@ esde_l96_coop_kernel(const CoopArgs ca) {
     __shared__ int sh_last;
 
     const int tid = threadIdx.x, l = tid & 1, e = tid >> 1;
-    const int tile = blockIdx.x % a.ntiles;
-    const int n = a.n_begin + blockIdx.x / a.ntiles;
+    const int tile = blockIdx.x, cta = blockIdx.y * gridDim.x + blockIdx.x;   // grid = (tiles, intervals)
+    const int n = a.n_begin + blockIdx.y;
     const int d0 = tile * TD, D = a.D;
-    int j = (d0 - 3 + e) % D;
-    if (j < 0) j += D;
+    int j = d0 - 3 + e;                  // circular index (lorenz_96.py:232-235), no division
+    if (D >= TE) {
+        if (j < 0) j += D;
+        if (j >= D) j -= D;
+    } else {
+        j %= D;
+        if (j < 0) j += D;
+    }
     const bool has_energy = (e >= 2) && (e <= TE - 2);
     const bool is_out = (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
 
@@ -227,10 +233,13 @@ esde_l96_coop_kernel(const CoopArgs ca) {
     }
     __syncthreads();
     if (tid < 9) {                                 // fixed-order fold over the TE cells
-        double x = 0.0;
-#pragma unroll 8
-        for (int c = 0; c < TE; ++c) x += red[tid][c];
-        a.part[(int64_t)blockIdx.x * kPartStride + tid] = x;
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;     // four chains, fixed order
+#pragma unroll
+        for (int c = 0; c < TE; c += 4) {
+            x0 += red[tid][c]; x1 += red[tid][c + 1]; x2 += red[tid][c + 2]; x3 += red[tid][c + 3];
+        }
+        const double x = (x0 + x1) + (x2 + x3);
+        a.part[(int64_t)cta * kPartStride + tid] = x;
         __threadfence();                           // the writers publish their partials
     }
     // ---- last CTA of this interval: fold the tiles, apply the guard ---------------------------------
@@ -283,17 +292,19 @@ assemble_tail_kernel(const TailArgs t) {
     __shared__ double sh_red[3 * (kTailThreads / 32)];
     __shared__ int sh_last;
     const AssembleArgs &a = t.a;
-    const int64_t idx = (int64_t)blockIdx.x * kTailThreads + threadIdx.x;
-    const int64_t nm = (int64_t)a.D * a.Nm, ntot = nm + (int64_t)a.D * a.Ns;
+    // small problems only: the element count fits 32 bits (mfvgp_create checks)
+    const unsigned idx = blockIdx.x * kTailThreads + threadIdx.x;
+    const unsigned nm = (unsigned)a.D * a.Nm, ntot = nm + (unsigned)a.D * a.Ns;
     double acc[3] = {0.0, 0.0, 0.0};
     pdl_launch_dependents();
     pdl_wait();
     if (idx < ntot) {
         const bool is_mean = idx < nm;
-        const int64_t r = is_mean ? idx : idx - nm;
-        const int W = is_mean ? a.Nm : a.Ns, step = is_mean ? 3 : 2, K = step + 1;
-        const int j = (int)(r / W), c = (int)(r - (int64_t)j * W);
-        const int n = c / step, k = c - step * n;
+        const unsigned r = is_mean ? idx : idx - nm;
+        const unsigned W = is_mean ? a.Nm : a.Ns;
+        const int step = is_mean ? 3 : 2, K = step + 1;
+        const int j = (int)(r / W), c = (int)(r - (unsigned)j * W);
+        const int n = is_mean ? c / 3 : c >> 1, k = c - step * n;
         const double *ws = is_mean ? a.dm : a.ds;
         const bool obs_col = k == 0 && n >= 1 && n <= a.M;
         // independent loads first

@@ -340,14 +340,14 @@ extern "C" int mfvgp_set_obs(mfvgp_handle *h, const double *obs_times_h,
 // launch that may overlap the tail of its predecessor in the stream (the kernel calls
 // pdl_wait() before touching global data); MFVGP_PDL=0 falls back to a plain launch
 template <typename A>
-static cudaError_t launch_pdl(void (*kern)(A), unsigned grid, unsigned block, cudaStream_t st,
+static cudaError_t launch_pdl(void (*kern)(A), dim3 grid, unsigned block, cudaStream_t st,
                               const A &arg) {
     static const bool enabled = [] {
         const char *e = getenv("MFVGP_PDL");
         return !(e && e[0] == '0');
     }();
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -420,7 +420,7 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
                 c.g.ntiles = h->ntiles;
                 c.r = refine_args(h, mean, ldm, vars, lds, log_vars, ds, 0);
                 c.tickets = h->tickets; c.theta = h->theta_host[0];
-                CK(launch_pdl(esde_l96_coop_kernel, grid, kCoopNT, st, c));
+                CK(launch_pdl(esde_l96_coop_kernel, dim3(h->ntiles, nl), kCoopNT, st, c));
             } else if (h->rule == 0) {
                 if (h->te == 32) esde_l96_kernel<32><<<grid, 32, 0, st>>>(a);
                 else if (h->te == 64) esde_l96_kernel<64><<<grid, 64, 0, st>>>(a);
@@ -699,7 +699,7 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
         t.f.record9 = 0; t.f.n_begin = h->n_begin; t.f.n_end = h->n_end; t.f.D = nb;
         t.f.with_e0 = 1; t.f.eobs_const = h->eobs_const;
         t.ticket = h->tickets + h->L + 1;
-        CK(launch_pdl(assemble_tail_kernel, (unsigned)nb, kTailThreads, st, t));
+        CK(launch_pdl(assemble_tail_kernel, dim3(nb), kTailThreads, st, t));
         h->launches++;
         CK(cudaGetLastError());
         return MFVGP_OK;
