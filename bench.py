@@ -46,10 +46,10 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 FLOP_PER_CELL = 4620.0      # 110 FLOP/(dim,node) x 42 nodes
 BYTE_PER_CELL = 96.0        # 40 B read + 56 B written per cell
-# What the split-rule kernel actually executes per cell (static SASS count of the fully
-# unrolled esde_l96_split_kernel, `cuobjdump -sass`: 1054 DFMA + 291 DMUL + 222 DADD):
-EXEC_FP64_INST_PER_CELL = 1567.0
-EXEC_FLOP_PER_CELL = 2.0 * 1054.0 + 291.0 + 222.0
+# What the kernels actually execute and move per cell, from the committed ncu captures
+# (profiles/r1_kernel_counts.json: FP64 thread instructions, DFMA share, DRAM bytes):
+COUNTS = json.loads((Path(__file__).resolve().parent / "profiles" / "r1_kernel_counts.json")
+                    .read_text())
 METRIC = "free-energy+gradient evals/sec (L96 D=500)"
 WORKLOAD = "L96 D=500 d=125 M=16 (example_500D.ipynb), synthetic state seed 8192"
 
@@ -139,28 +139,39 @@ def kernel_time(fe, lib, fn, reps):
     return tot.value / max(cnt.value, 1), cnt.value
 
 
-def roofline(D, L, kernel_ms, fp64_peak_tf, hbm_peak_gbs, traffic=None):
+def roofline(D, L, kernel_ms, fp64_peak_tf, hbm_peak_gbs, kernel):
+    """
+    achieved = ALGORITHMIC FLOPs of SURVEY 8(d) (4 620 per (dimension, interval) cell,
+    the 42-node formulation) / measured kernel time; peak = DFMA rate measured in this
+    run.  The kernels use the split rule, which needs fewer FLOPs for the same result
+    (DESIGN.md 4), so `executed` states what the pipe really did (ncu counts).
+    """
     cells = float(D) * L
-    tf = FLOP_PER_CELL * cells / (kernel_ms * 1e-3) * 1e-12
-    gbs = BYTE_PER_CELL * cells / (kernel_ms * 1e-3) * 1e-9
-    return {"bound": "fp64", "achieved": tf, "peak": fp64_peak_tf, "unit": "TFLOP/s",
-            "frac": tf / fp64_peak_tf, "traffic": traffic,
-            "peak_source": "DFMA micro-benchmark measured in this run (mfvgp_fp64_peak); "
-                           "MEASURED_PEAKS.json has no FP64 entry",
-            "kernel": "esde_l96_split_kernel", "kernel_ms": kernel_ms,
-            "algorithmic_flop_per_launch": FLOP_PER_CELL * cells,
-            "algorithmic_bytes_per_launch": BYTE_PER_CELL * cells,
-            "executed": {
-                "note": "frac is on the ALGORITHMIC FLOPs of SURVEY 8(d) (42-node rule); the "
-                        "split-rule kernel executes fewer (DESIGN.md 4), so frac may exceed 1. "
-                        "fp64_pipe_frac = executed FP64 instructions / (time x measured DFMA "
-                        "issue rate) is the utilisation of the pipe that bounds the kernel.",
-                "flop_per_launch": EXEC_FLOP_PER_CELL * cells,
-                "tflops": EXEC_FLOP_PER_CELL * cells / (kernel_ms * 1e-3) * 1e-12,
-                "fp64_pipe_frac": EXEC_FP64_INST_PER_CELL * cells / (kernel_ms * 1e-3)
-                                  / (fp64_peak_tf * 0.5e12)},
-            "hbm": {"achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s",
-                    "frac": gbs / hbm_peak_gbs, "peak_source": "MEASURED_PEAKS.json hbm_gbs"}}
+    sec = kernel_ms * 1e-3
+    tf = FLOP_PER_CELL * cells / sec * 1e-12
+    gbs = BYTE_PER_CELL * cells / sec * 1e-9
+    c = COUNTS.get(kernel, {})
+    out = {"bound": "fp64", "achieved": tf, "peak": fp64_peak_tf, "unit": "TFLOP/s",
+           "frac": tf / fp64_peak_tf,
+           "traffic": c["dram_bytes_per_cell"] * cells if "dram_bytes_per_cell" in c else None,
+           "peak_source": "DFMA micro-benchmark measured in this run (mfvgp_fp64_peak); "
+                          "MEASURED_PEAKS.json has no FP64 entry",
+           "kernel": kernel, "kernel_ms": kernel_ms,
+           "algorithmic_flop_per_launch": FLOP_PER_CELL * cells,
+           "algorithmic_bytes_per_launch": BYTE_PER_CELL * cells,
+           "hbm": {"achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s",
+                   "frac": gbs / hbm_peak_gbs, "peak_source": "MEASURED_PEAKS.json hbm_gbs"}}
+    if "fp64_inst_per_cell" in c:
+        inst = c["fp64_inst_per_cell"] * cells
+        flop = (c["fp64_inst_per_cell"] + c["dfma_per_cell"]) * cells       # FMA = 2
+        out["executed"] = {
+            "source": c.get("source"),
+            "fp64_inst_per_cell": c["fp64_inst_per_cell"],
+            "tflops": flop / sec * 1e-12,
+            # executed FP64 instructions / (time x measured DFMA issue rate): utilisation of
+            # the pipe that bounds the kernel (an FMA, a multiply and an add each take one slot)
+            "fp64_pipe_frac": inst / sec / (fp64_peak_tf * 0.5e12)}
+    return out
 
 
 def hbm_peak():
@@ -254,11 +265,13 @@ def run_large(torch, dist, rank, world, steps, warmup, fp64_peak_tf, hbm_gbs, D=
     lib = _lib.load()
     k_ms, _ = kernel_time(fe.local, lib, step, 3)
     Lloc = fe.local.intervals[1] - fe.local.intervals[0]
+    desc = fe.local.describe()
     out = {"workload": f"L96 D={D} d={D // 4} M={M} (L={L} intervals), synthetic seed 8192",
            "value": 1e3 / ms_step, "unit": "evals/s", "ms_per_eval": ms_step,
            "scaling": "strong", "parallelism": f"time-intervals sharded x{world}",
            "l2": "inputs larger than L2",
-           "roofline": roofline(D, Lloc, k_ms, fp64_peak_tf, hbm_gbs),
+           "path": desc,
+           "roofline": roofline(D, Lloc, k_ms, fp64_peak_tf, hbm_gbs, desc["kernel"]),
            "job_tflops_algorithmic": FLOP_PER_CELL * D * L / (ms_step * 1e-3) * 1e-12}
     del fe, g, x
     torch.cuda.empty_cache()
@@ -330,6 +343,24 @@ def main():
     ms_step = tms.item() / args.steps
     value = world * 1e3 / ms_step          # N independent replicas
 
+    # ---- extra: the bare C-ABI call, back to back, no flush (what SCG sees) -------------
+    out_d = torch.empty(8, dtype=torch.float64, device="cuda")
+    grad_d = torch.empty(n, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    cargs = (fe._h, x_dev.data_ptr(), 1, out_d.data_ptr(), grad_d.data_ptr(),
+             out_d.data_ptr() + 32, stream)
+    for _ in range(args.warmup):
+        lib.mfvgp_ecost(*cargs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lib.mfvgp_ecost(*cargs)
+    e1.record()
+    torch.cuda.synchronize()
+    c_abi = {"value": world * args.steps / (e0.elapsed_time(e1) * 1e-3), "unit": "evals/s",
+             "note": "mfvgp_ecost on device pointers, back to back, x in L2 (no flush)"}
+
     # ---- e2e: host buffers through the public API ----------------------------
     for _ in range(args.warmup):
         fe.E_cost(x_host)
@@ -345,14 +376,17 @@ def main():
         dist.all_reduce(twall, op=dist.ReduceOp.MAX)
     clock_info = clocks.stop()          # sampled over the device-timed and the e2e regions
     e2e = {"value": world * args.steps / twall.item(), "unit": "evals/s",
-           "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 8 + 36),
-           "api": "FreeEnergy.E_cost(numpy x) -> (float, numpy grad); wall clock, "
-                  "stream synchronised inside each call"}
+           "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(n * 8 + 40),
+           "api": "FreeEnergy.E_cost(numpy x in pinned memory) -> (float, numpy grad); wall "
+                  "clock; one H2D and one D2H DMA per call, stream synchronised inside"}
 
     # ---- roofline of the dominant kernel ------------------------------------
     k_ms, k_cnt = kernel_time(fe, lib, step_dev, 50)
-    roof = roofline(D, L, k_ms, fp64_peak_tf, hbm_gbs)
+    desc = fe.describe()
+    roof = roofline(D, L, k_ms, fp64_peak_tf, hbm_gbs, desc["kernel"])
     roof["hbm"]["peak_source"] = f"MEASURED_PEAKS.json hbm_gbs ({hbm_src})"
+    roof["note"] = ("7 500 cells = 51 per SM: this launch is latency-bound (DESIGN.md 5); the "
+                    "roofline fraction that characterises the kernels is large.roofline")
 
     # ---- SCG iterations per second -------------------------------------------
     import contextlib
@@ -386,10 +420,12 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB write) between steps",
+                           "path": desc,
                            "parallelism": "single GPU" if world == 1 else
                            f"replicas only x{world} (evaluation is < 1 wave of one GPU)"},
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "scg": scg, "large": large,
+                "roofline": roof, "cpu_baseline": cpu, "c_abi_back_to_back": c_abi,
+                "scg": scg, "large": large,
                 "fp64_peak_tflops_measured": fp64_peak_tf}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -175,6 +175,11 @@ int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x_tol,
 int mfvgp_comm_unique_id(void *id128_out /*128 bytes*/);
 int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void *id128);
 
+/* Which kernels this handle runs, as text ("system=L96 path=walk te=128 tn=32
+ * ntiles=68 nruns=128 ..."): for benchmark reports and logs.  Returns the
+ * length written (excluding the terminating 0).                            */
+int mfvgp_describe(const mfvgp_handle *h, char *buf, int buflen);
+
 /* counters for benchmarks: number of kernels this handle has launched      */
 int64_t mfvgp_launch_count(const mfvgp_handle *h);
 

@@ -113,6 +113,27 @@ extern "C" int mfvgp_device_count(void) {
 
 extern "C" int64_t mfvgp_launch_count(const mfvgp_handle *h) { return h ? h->launches : 0; }
 
+extern "C" int mfvgp_describe(const mfvgp_handle *h, char *buf, int buflen) {
+    if (!h || !buf || buflen <= 0) return 0;
+    static const char *sys[] = {"DW", "OU", "L63", "L96"};
+    const char *path = "small";        // DW / OU / L63: esde_small_kernel + assemble + final
+    const char *kern = "esde_small_kernel";
+    int te = 0, tn = 1, nt = 1, nr = h->n_end - h->n_begin;
+    if (h->system == MFVGP_SYS_L96) {
+        if (h->rule == 0) { path = "gk42"; kern = "esde_l96_kernel"; te = h->te; nt = h->ntiles; }
+        else if (h->fused == 2) { path = "walk"; kern = "esde_l96_walk_kernel"; te = h->fte; tn = h->ftn; nt = h->fntiles; nr = h->fntn; }
+        else if (h->fused == 1) { path = "fused"; kern = "esde_l96_fused_kernel"; te = h->fte; tn = h->ftn; nt = h->fntiles; nr = h->fntn; }
+        else if (h->coop) { path = "coop"; kern = "esde_l96_coop_kernel"; te = h->te; nt = h->ntiles; }
+        else { path = "split"; kern = "esde_l96_split_kernel"; te = h->te; nt = h->ntiles; }
+    }
+    const int n = snprintf(buf, (size_t)buflen,
+                           "system=%s path=%s kernel=%s te=%d tn=%d ntiles=%d nruns=%d D=%d M=%d "
+                           "intervals=%d..%d world=%d",
+                           sys[h->system], path, kern, te, tn, nt, nr, h->D, h->M, h->n_begin,
+                           h->n_end, h->world);
+    return n < buflen ? n : buflen - 1;
+}
+
 extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
                             int device, int n_begin, int n_end) {
     ARG(out != nullptr, "mfvgp_create: out is NULL");

@@ -185,6 +185,12 @@ class FreeEnergy(object):
     def kernel_launches(self):
         return int(self._lib.mfvgp_launch_count(self._h))
 
+    def describe(self):
+        """Which kernels this object runs, e.g. {'path': 'walk', 'kernel': ..., 'te': '128'}."""
+        buf = ctypes.create_string_buffer(512)
+        self._lib.mfvgp_describe(self._h, buf, 512)
+        return dict(kv.split("=", 1) for kv in buf.value.decode().split())
+
     def attach_communicator(self, rank, world):
         """
         Join this object (created with ``intervals=`` = the rank's block) to the

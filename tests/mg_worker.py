@@ -38,12 +38,19 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    for D, M in ((67, 9), (130, 13)):
+    # sharded path: default kernels (small problems: coop kernel + assemble + edge exchange)
+    # and the walk kernel (what the D=8192 long-horizon problem runs)
+    for D, M, path in ((67, 9, ""), (130, 13, ""), (67, 9, "walk"), (130, 41, "walk")):
         g = synthetic_l96(D, M, seed=77 + D)
+        os.environ.pop("MFVGP_PATH", None)
         single = make_free_energy(g, device=local)
         x = torch.tensor(g["x0"], dtype=torch.float64, device="cuda")
         F1, g1 = single.E_cost(x)
+        if path:
+            os.environ["MFVGP_PATH"] = path
         sh = ShardedFreeEnergy(g, rank, world, device=local)
+        os.environ.pop("MFVGP_PATH", None)
+        assert sh.local.describe()["path"] == (path or "coop")
         Fs, gs = sh.E_cost(x)
         idx = active_columns(sh.local, D, M)
         assert abs(Fs.item() - F1.item()) <= 1e-13 * abs(F1.item()), (Fs.item(), F1.item())
