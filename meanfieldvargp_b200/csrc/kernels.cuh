@@ -758,9 +758,11 @@ edge_fixup_kernel(const FixupArgs a) {
 // node; each thread evaluates all dimensions at its node, the 42 node values
 // are then summed in scipy's order (panel 1 then panel 2, r = 0..20).
 // ---------------------------------------------------------------------------
+// write_mask: bit 0 dm_out, bit 1 ds_out (esde_small_inkernel runs two CTAs per interval
+// that each own one of the two outputs); slot = row of `part` to write
 template <int SYS>
-__global__ void __launch_bounds__(64)
-esde_small_kernel(const EsdeArgs a) {
+__device__ __forceinline__ void esde_small_body(const EsdeArgs &a, int write_mask = 3,
+                                                int slot = -1) {
     using Dr = Drift<SYS>;
     constexpr int D = Dr::D;
     constexpr int NV = 1 + 4 * D + 3 * D + D + 3 * D;   // see value layout below
@@ -841,9 +843,9 @@ esde_small_kernel(const EsdeArgs a) {
         sums[q][4] = M1; sums[q][5] = M2;
         const double scale = 0.5 * (0.25 * dt);
         if (a.dm_out != nullptr) {
-            if (q >= V_DM && q < V_DS)
+            if (q >= V_DM && q < V_DS && (write_mask & 1))
                 a.dm_out[(int64_t)n * D * 4 + (q - V_DM)] = scale * (K1 + K2);
-            else if (q >= V_DS && q < V_RE)
+            else if (q >= V_DS && q < V_RE && (write_mask & 2))
                 a.ds_out[(int64_t)n * D * 3 + (q - V_DS)] = scale * (K1 + K2);
         }
     }
@@ -868,10 +870,14 @@ esde_small_kernel(const EsdeArgs a) {
             p[7] += sums[V_RS + 3 * i][4] * sums[V_RS + 3 * i][4];
             p[8] += sums[V_RS + 3 * i][5] * sums[V_RS + 3 * i][5];
         }
-        double *out = a.part + (int64_t)blockIdx.x * kPartStride;
+        double *out = a.part + (int64_t)(slot < 0 ? blockIdx.x : slot) * kPartStride;
         for (int i = 0; i < kPartStride; ++i) out[i] = p[i];
     }
 }
+
+template <int SYS>
+__global__ void __launch_bounds__(64)
+esde_small_kernel(const EsdeArgs a) { esde_small_body<SYS>(a); }
 
 // ---------------------------------------------------------------------------
 // Per-interval reduction of the dim-tile partials: the interval's Esde share

@@ -270,6 +270,42 @@ esde_l96_coop_kernel(const CoopArgs ca) {
 }
 
 // ---------------------------------------------------------------------------
+// DW / OU / L63: esde_small_kernel with the guard and the adaptive path folded in.
+// Two CTAs per interval (blockIdx.y) integrate it redundantly -- it is tiny -- so that,
+// when quad_vec would refine, the energy integrand (CTA 0, which owns dEsde_dm and the
+// interval's Esde) and the dS integrand (CTA 1, which owns dEsde_ds) are refined side by
+// side, as refine_kernel does; both reach the same guard decision from identical sums.
+// g2: CTA 1's private guard outputs.
+// ---------------------------------------------------------------------------
+struct SmallArgs {
+    CoopArgs c;
+    double *part2, *esde_n2;
+    int32_t *flags2;
+};
+
+template <int SYS>
+__global__ void __launch_bounds__(64)
+esde_small_inkernel(const SmallArgs sa) {
+    const EsdeArgs &a = sa.c.a;
+    const int n = a.n_begin + blockIdx.x, tid = threadIdx.x, y = blockIdx.y;
+    pdl_launch_dependents();
+    pdl_wait();
+    EsdeArgs mine = a;
+    GuardArgs g = sa.c.g;
+    if (y == 1) { mine.part = sa.part2; g.part = sa.part2; g.esde_n = sa.esde_n2; g.flags = sa.flags2; }
+    esde_small_body<SYS>(mine, y == 0 ? 1 : 2);
+    __syncthreads();
+    if (tid < 32) guard_interval(g, n, tid);
+    __syncthreads();
+    const int f = g.flags[n];
+    if (tid == 0) sa.c.r.info[2 * n + y] = 0;
+    double *ws = sa.c.r.ws + ((int64_t)(n - a.n_begin) * 2 + y) * 2 * a.D * kMaxNE;
+    double *ws_fixed = ws + (int64_t)a.D * kMaxNE;
+    if (y == 0 && (f & 1)) refine_item<SYS, true, 64>(sa.c.r, n, ws, ws_fixed);
+    if (y == 1 && (f & 2) && sa.c.r.want_grad) refine_item<SYS, false, 64>(sa.c.r, n, ws, ws_fixed);
+}
+
+// ---------------------------------------------------------------------------
 // E_cost tail for small problems (single GPU): gradient assembly
 // (free_energy.py:711-743), E_kl0 / E_obs terms (:309-310, :594-612, :733-738) and
 // -- in the last CTA to finish (atomic ticket) -- the final scalar sums of

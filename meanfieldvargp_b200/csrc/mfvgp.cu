@@ -45,6 +45,8 @@ struct mfvgp_handle {
     int coop = 0;     // small L96 problems: esde_l96_coop_kernel + assemble_tail_kernel (l96_coop.cuh)
     unsigned *tickets = nullptr;
     double *y_dense = nullptr, *rinv_row = nullptr;   // row tables of assemble_tail_kernel
+    double *esde_n2 = nullptr;                        // esde_small_inkernel: CTA 1's guard outputs
+    int32_t *flags2 = nullptr;
     int tail_grid = 1;
     double theta_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int rule = 1;     // 1: split rule (default), 0: 42-node coupled rule (MFVGP_RULE=gk42)
@@ -184,6 +186,13 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
             h->tail_grid = (int)(((int64_t)D * (h->Nm + h->Ns) + kTailThreads - 1) / kTailThreads);
         }
     }
+    if (system != MFVGP_SYS_L96) {
+        // DW / OU / L63: guard + adaptive path inside esde_small_inkernel, one-launch tail
+        const char *coop_env = getenv("MFVGP_COOP");
+        h->coop = (coop_env && coop_env[0] == '0') ? 0 : 1;
+        if (h->coop)
+            h->tail_grid = (int)(((int64_t)D * (h->Nm + h->Ns) + kTailThreads - 1) / kTailThreads);
+    }
     if (system == MFVGP_SYS_L96) {
         if (h->fused == 2) {
             // dim tile: the TE in {32, 64, 128} that wastes the fewest threads on halo / padding
@@ -246,8 +255,10 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         dev_alloc(&h->tau0, D) || dev_alloc(&h->obs_times, M) ||
         dev_alloc(&h->obs_values, (size_t)M * d) || dev_alloc(&h->obs_noise, d) ||
         dev_alloc(&h->dm_ws, (size_t)L * D * 4) || dev_alloc(&h->ds_ws, (size_t)L * D * 3) ||
-        dev_alloc(&h->part, (size_t)nl * (h->ntiles > h->fntiles ? h->ntiles : h->fntiles) *
+        dev_alloc(&h->part, (size_t)nl * (h->ntiles > h->fntiles ? (h->ntiles > 2 ? h->ntiles : 2)
+                                                                   : (h->fntiles > 2 ? h->fntiles : 2)) *
                                 kPartStride) ||
+        dev_alloc(&h->esde_n2, L) ||
         dev_alloc(&h->fedge_m, (size_t)h->fntn * D) || dev_alloc(&h->fedge_s, (size_t)h->fntn * D) ||
         dev_alloc(&h->fapart, (size_t)h->fntn * h->fntiles * 4) ||
         dev_alloc(&h->esde_n, L) || dev_alloc(&h->apart, (size_t)(D > h->tail_grid ? D : h->tail_grid) * 4) ||
@@ -255,7 +266,8 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         return MFVGP_ERR_CUDA;
     h->refine_grid = 2 * nl < 296 ? 2 * nl : 296;
     {   // scratch of the adaptive path: one slot per refine CTA, or per interval (coop path)
-        const int slots = h->coop && nl > h->refine_grid ? nl : h->refine_grid;
+        const int need = system == MFVGP_SYS_L96 ? nl : 2 * nl;      // in-kernel adaptive path
+        const int slots = h->coop && need > h->refine_grid ? need : h->refine_grid;
         if (dev_alloc(&h->refine_ws, (size_t)slots * 2 * D * kMaxNE)) return MFVGP_ERR_CUDA;
     }
     if (h->coop && (dev_alloc(&h->y_dense, (size_t)M * D) || dev_alloc(&h->rinv_row, D)))
@@ -268,6 +280,7 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     CK(cudaMemset(h->tickets, 0, (L + 2) * sizeof(unsigned)));
     CK(cudaMalloc((void **)&h->obs_idx, D * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->flags, L * sizeof(int32_t)));
+    CK(cudaMalloc((void **)&h->flags2, L * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->status_ws, sizeof(int32_t)));
     CK(cudaMemset(h->flags, 0, L * sizeof(int32_t)));
     CK(cudaMemset(h->esde_n, 0, L * sizeof(double)));
@@ -287,7 +300,7 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal,
                     h->refine_ws, h->refine_info, h->refine_status, h->edge_send, h->edge_recv,
                     h->gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
-                    h->y_dense, h->rinv_row};
+                    h->y_dense, h->rinv_row, h->esde_n2, h->flags2};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
@@ -427,20 +440,35 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         CK(cudaEventCreate(&ev1));
         CK(cudaEventRecord(ev0, st));
     }
+    CoopArgs c;                               // small-problem kernels: guard + refine inside
+    if (h->coop) {
+        c.a = a;
+        c.g.part = h->part; c.g.obs_times = h->obs_times; c.g.esde_n = h->esde_n;
+        c.g.flags = h->flags; c.g.n_begin = h->n_begin; c.g.n_end = h->n_end;
+        c.g.ntiles = h->ntiles;
+        c.r = refine_args(h, mean, ldm, vars, lds, log_vars, ds, 0);
+        c.tickets = h->tickets; c.theta = h->theta_host[0];
+    }
+    SmallArgs sa;
+    sa.c = c;
+    sa.part2 = h->part + (size_t)nl * kPartStride;           // second half of `part`
+    sa.esde_n2 = h->esde_n2; sa.flags2 = h->flags2;
     switch (h->system) {
-        case MFVGP_SYS_DW: esde_small_kernel<0><<<nl, 64, 0, st>>>(a); break;
-        case MFVGP_SYS_OU: esde_small_kernel<1><<<nl, 64, 0, st>>>(a); break;
-        case MFVGP_SYS_L63: esde_small_kernel<2><<<nl, 64, 0, st>>>(a); break;
+        case MFVGP_SYS_DW:
+            if (h->coop) CK(launch_pdl(esde_small_inkernel<0>, dim3(nl, 2), 64, st, sa));
+            else esde_small_kernel<0><<<nl, 64, 0, st>>>(a);
+            break;
+        case MFVGP_SYS_OU:
+            if (h->coop) CK(launch_pdl(esde_small_inkernel<1>, dim3(nl, 2), 64, st, sa));
+            else esde_small_kernel<1><<<nl, 64, 0, st>>>(a);
+            break;
+        case MFVGP_SYS_L63:
+            if (h->coop) CK(launch_pdl(esde_small_inkernel<2>, dim3(nl, 2), 64, st, sa));
+            else esde_small_kernel<2><<<nl, 64, 0, st>>>(a);
+            break;
         default: {
             const unsigned grid = (unsigned)nl * h->ntiles;
             if (h->coop) {
-                CoopArgs c;
-                c.a = a;
-                c.g.part = h->part; c.g.obs_times = h->obs_times; c.g.esde_n = h->esde_n;
-                c.g.flags = h->flags; c.g.n_begin = h->n_begin; c.g.n_end = h->n_end;
-                c.g.ntiles = h->ntiles;
-                c.r = refine_args(h, mean, ldm, vars, lds, log_vars, ds, 0);
-                c.tickets = h->tickets; c.theta = h->theta_host[0];
                 CK(launch_pdl(esde_l96_coop_kernel, dim3(h->ntiles, nl), kCoopNT, st, c));
             } else if (h->rule == 0) {
                 if (h->te == 32) esde_l96_kernel<32><<<grid, 32, 0, st>>>(a);
