@@ -74,6 +74,8 @@ struct mfvgp_handle {
     // SCG workspace (device): two iterates, direction, 3 rotating gradients, g_plus
     double *scg_vec[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *scg_part = nullptr, *scg_scal = nullptr;
+    double *scg_hostrec = nullptr, *scg_hostrec_dev = nullptr;   // host-mapped record + flag
+    long long scg_epoch = 0;
     int scg_nblk = 0;
     // multi-GPU: one rank per GPU, intervals [n_begin, n_end) of this handle
     ncclComm_t comm = nullptr;
@@ -305,6 +307,7 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
         if (p) cudaFree(p);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->scg_hostrec) cudaFreeHost(h->scg_hostrec);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MFVGP_OK;
@@ -373,9 +376,9 @@ extern "C" int mfvgp_set_obs(mfvgp_handle *h, const double *obs_times_h,
 // ---- launch helpers ---------------------------------------------------------
 // launch that may overlap the tail of its predecessor in the stream (the kernel calls
 // pdl_wait() before touching global data); MFVGP_PDL=0 falls back to a plain launch
-template <typename A>
-static cudaError_t launch_pdl(void (*kern)(A), dim3 grid, unsigned block, cudaStream_t st,
-                              const A &arg) {
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, unsigned block, cudaStream_t st,
+                              Args &&...args) {
     static const bool enabled = [] {
         const char *e = getenv("MFVGP_PDL");
         return !(e && e[0] == '0');
@@ -386,7 +389,7 @@ static cudaError_t launch_pdl(void (*kern)(A), dim3 grid, unsigned block, cudaSt
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, arg);
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 static RefineArgs refine_args(mfvgp_handle *h, const double *mean, int64_t ldm, const double *vars,
@@ -1048,8 +1051,22 @@ struct ScgRun {
     cudaStream_t st;
     VecMap n;          // index map of this rank's part of x (named n: it replaces the length)
     int status_or = 0;
+    bool fused = false;          // single GPU: folds in the producers, host-mapped record
 
+    FoldArgs fold_args() {
+        FoldArgs fa;
+        fa.ticket = nullptr; fa.scal = h->scg_scal; fa.status = h->status_ws;
+        fa.host_rec = h->scg_hostrec_dev;
+        fa.host_flag = reinterpret_cast<volatile long long *>(h->scg_hostrec_dev + 16);
+        fa.epoch = 0;
+        if (fused) {
+            fa.ticket = h->tickets + h->L;
+            fa.epoch = ++h->scg_epoch;
+        }
+        return fa;
+    }
     int fold() {
+        if (fused) return MFVGP_OK;
         scg_fold_kernel<<<1, kRedBlock, 0, st>>>(h->scg_part, h->scg_nblk, h->scg_scal);
         h->launches++;
         CK(cudaGetLastError());
@@ -1059,6 +1076,24 @@ struct ScgRun {
     }
     // reads scal[0..3] (fold output), scal[4..7] (E_cost output) and the status
     int read(double *s8) {
+        if (fused) {
+            // the last reduction kernel publishes the record and then the epoch
+            volatile long long *flag = reinterpret_cast<volatile long long *>(h->scg_hostrec + 16);
+            long spins = 0;
+            while (*flag != h->scg_epoch) {
+                if ((++spins & 0xfffff) == 0) {             // a faulted kernel never publishes
+                    cudaError_t q = cudaStreamQuery(st);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) {
+                        g_err = std::string("mfvgp_scg: ") + cudaGetErrorString(q);
+                        return MFVGP_ERR_CUDA;
+                    }
+                }
+            }
+            __sync_synchronize();
+            memcpy(s8, h->scg_hostrec, 8 * sizeof(double));
+            status_or |= (int32_t)h->scg_hostrec[8];
+            return MFVGP_OK;
+        }
         CK(cudaMemcpyAsync(h->pin, h->scg_scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h->pin + 8, h->status_ws, sizeof(int32_t), cudaMemcpyDeviceToHost,
                            st));
@@ -1073,28 +1108,26 @@ struct ScgRun {
         return mfvgp_ecost(h, x, 1, h->scg_scal + 4, g, h->status_ws, st);
     }
     int direction(double *d, const double *g, double gamma, int restart) {
-        scg_direction_kernel<<<h->scg_nblk, kRedBlock, 0, st>>>(d, g, gamma, restart, n,
-                                                                h->scg_part);
+        CK(launch_pdl(scg_direction_kernel, dim3(h->scg_nblk), kRedBlock, st, d, g, gamma, restart,
+                      n, h->scg_part, fold_args()));
         h->launches++;
-        CK(cudaGetLastError());
         return fold();
     }
     int axpy(double *y, const double *x, const double *d, double a) {
-        scg_axpy_kernel<<<h->scg_nblk, kRedBlock, 0, st>>>(y, x, d, a, n);
+        CK(launch_pdl(scg_axpy_kernel, dim3(h->scg_nblk), kRedBlock, st, y, x, d, a, n));
         h->launches++;
-        CK(cudaGetLastError());
         return MFVGP_OK;
     }
     int theta(const double *d, const double *gp, const double *g) {
-        scg_theta_kernel<<<h->scg_nblk, kRedBlock, 0, st>>>(d, gp, g, n, h->scg_part);
+        CK(launch_pdl(scg_theta_kernel, dim3(h->scg_nblk), kRedBlock, st, d, gp, g, n,
+                      h->scg_part, fold_args()));
         h->launches++;
-        CK(cudaGetLastError());
         return fold();
     }
     int stats(const double *g_now, const double *g_new, const double *d) {
-        scg_stats_kernel<<<h->scg_nblk, kRedBlock, 0, st>>>(g_now, g_new, d, n, h->scg_part);
+        CK(launch_pdl(scg_stats_kernel, dim3(h->scg_nblk), kRedBlock, st, g_now, g_new, d, n,
+                      h->scg_part, fold_args()));
         h->launches++;
-        CK(cudaGetLastError());
         return fold();
     }
 };
@@ -1138,7 +1171,16 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
             dev_alloc(&h->scg_scal, 8))
             return MFVGP_ERR_CUDA;
     }
+    if (!h->scg_hostrec) {
+        CK(cudaHostAlloc((void **)&h->scg_hostrec, 32 * sizeof(double), cudaHostAllocMapped));
+        memset(h->scg_hostrec, 0, 32 * sizeof(double));
+        CK(cudaHostGetDevicePointer((void **)&h->scg_hostrec_dev, h->scg_hostrec, 0));
+    }
     ScgRun R{h, st, vm};
+    {
+        const char *e = getenv("MFVGP_SCG_FUSED");
+        R.fused = h->world == 1 && !(e && e[0] == '0');
+    }
     double *x = h->scg_vec[0], *xt = h->scg_vec[1], *d = h->scg_vec[2];
     double *gnew = h->scg_vec[3], *gold = h->scg_vec[4], *gnow = h->scg_vec[5];
     double *gp = h->scg_vec[6];

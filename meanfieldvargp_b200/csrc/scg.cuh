@@ -13,6 +13,27 @@ namespace mfvgp {
 constexpr int kRedBlock = 256;
 constexpr int kRedSlots = 4;
 
+// programmatic dependent launch (see l96_coop.cuh)
+__device__ __forceinline__ void scg_pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Single-GPU runs fold the per-block partials in the LAST block of the producing kernel
+// (atomic ticket, fixed order => deterministic) and publish the scalars the host control
+// loop branches on straight into host-mapped memory: [0..3] this kernel's sums,
+// [4..7] F, E0, Esde, Eobs of the last E_cost, [8] its status bits, then the epoch flag.
+// The host spins on the flag: no memcpy, no stream synchronisation (scaled_cg.py's
+// branches at :194, :233, :254 stay on the host, the vectors never leave the device).
+struct FoldArgs {
+    unsigned *ticket;          // nullptr: partials only, scg_fold_kernel follows (multi-GPU)
+    double *scal;              // [8] device scalars: [0..3] sums, [4..7] E_cost outputs
+    const int32_t *status;     // status word of the last E_cost
+    double *host_rec;          // [16] host-mapped record
+    volatile long long *host_flag;
+    long long epoch;
+};
+
 // Index map of the optimisation vector a rank works on.  Single GPU: the whole
 // x.  Sharded: the rank's active columns of the mean block [D][Nm] and of the
 // log-variance block [D][Ns]; the last active column may be a ghost column
@@ -53,8 +74,38 @@ __device__ __forceinline__ double warp_max_d(double v) {
 
 // Block-level combine of kRedSlots values (slots 0..2 summed, slot 3 max'ed)
 // and store to part[blockIdx.x][*].
-__device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part) {
+__device__ __forceinline__ void fold_partials(const double *part, int nblk, double (&r)[kRedSlots],
+                                              double (*sh)[kRedBlock / 32]) {
+    double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < nblk; b += kRedBlock) {
+        v[0] += __ldcg(part + (int64_t)b * kRedSlots + 0);
+        v[1] += __ldcg(part + (int64_t)b * kRedSlots + 1);
+        v[2] += __ldcg(part + (int64_t)b * kRedSlots + 2);
+        v[3] = fmax(v[3], __ldcg(part + (int64_t)b * kRedSlots + 3));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = warp_sum_d(v[i]);
+    v[3] = warp_max_d(v[3]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) sh[i][w] = v[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) r[i] = sh[i][0];
+        for (int k = 1; k < kRedBlock / 32; ++k) {
+            r[0] += sh[0][k]; r[1] += sh[1][k]; r[2] += sh[2][k];
+            r[3] = fmax(r[3], sh[3][k]);
+        }
+    }
+}
+
+__device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part,
+                                          const FoldArgs &fa) {
     __shared__ double sh[kRedSlots][kRedBlock / 32];
+    __shared__ int sh_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < 3; ++i) v[i] = warp_sum_d(v[i]);
@@ -73,6 +124,28 @@ __device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part) 
         }
 #pragma unroll
         for (int i = 0; i < kRedSlots; ++i) part[(int64_t)blockIdx.x * kRedSlots + i] = r[i];
+        sh_last = 0;
+        if (fa.ticket != nullptr) {
+            __threadfence();
+            const unsigned k = atomicAdd(fa.ticket, 1u);
+            sh_last = (k == gridDim.x - 1u);
+            if (sh_last) fa.ticket[0] = 0u;
+        }
+    }
+    if (fa.ticket == nullptr) return;
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    double r[kRedSlots];
+    fold_partials(part, (int)gridDim.x, r, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) { fa.scal[i] = r[i]; fa.host_rec[i] = r[i]; }
+#pragma unroll
+        for (int i = 4; i < 8; ++i) fa.host_rec[i] = __ldcg(fa.scal + i);
+        fa.host_rec[8] = (double)__ldcg(fa.status);
+        __threadfence_system();
+        *fa.host_flag = fa.epoch;
     }
 }
 
@@ -80,8 +153,9 @@ __device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part) 
 // partials: [0] mu = d.g, [1] kappa = d.d     (scaled_cg.py:192-200, 361-369)
 __global__ void __launch_bounds__(kRedBlock)
 scg_direction_kernel(double *d, const double *g, double gamma, int restart, const VecMap vm,
-                     double *part) {
+                     double *part, const FoldArgs fa) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    scg_pdl_enter();
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
          t += (int64_t)gridDim.x * blockDim.x) {
         bool own;
@@ -94,12 +168,13 @@ scg_direction_kernel(double *d, const double *g, double gamma, int restart, cons
             v[1] = fma(di, di, v[1]);
         }
     }
-    red_store(v, part);
+    red_store(v, part, fa);
 }
 
 // y = x + a*d                                   (scaled_cg.py:222, :242)
 __global__ void __launch_bounds__(kRedBlock)
 scg_axpy_kernel(double *y, const double *x, const double *d, double a, const VecMap vm) {
+    scg_pdl_enter();
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
          t += (int64_t)gridDim.x * blockDim.x) {
         bool own;
@@ -111,15 +186,16 @@ scg_axpy_kernel(double *y, const double *x, const double *d, double a, const Vec
 // partial [0] = d.(gp - g)                      (scaled_cg.py:228)
 __global__ void __launch_bounds__(kRedBlock)
 scg_theta_kernel(const double *d, const double *gp, const double *g, const VecMap vm,
-                 double *part) {
+                 double *part, const FoldArgs fa) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    scg_pdl_enter();
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
          t += (int64_t)gridDim.x * blockDim.x) {
         bool own;
         const int64_t i = vm.at(t, own);
         if (own) v[0] = fma(d[i], gp[i] - g[i], v[0]);
     }
-    red_store(v, part);
+    red_store(v, part, fa);
 }
 
 // After the trial evaluation at x + alpha d:
@@ -128,8 +204,9 @@ scg_theta_kernel(const double *d, const double *gp, const double *g, const VecMa
 // :367), [3] max |d| (:306).
 __global__ void __launch_bounds__(kRedBlock)
 scg_stats_kernel(const double *g_now, const double *g_new, const double *d, const VecMap vm,
-                 double *part) {
+                 double *part, const FoldArgs fa) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    scg_pdl_enter();
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
          t += (int64_t)gridDim.x * blockDim.x) {
         bool own;
@@ -141,7 +218,7 @@ scg_stats_kernel(const double *g_now, const double *g_new, const double *d, cons
         v[2] = fma(a, g_new[i] - a, v[2]);
         v[3] = fmax(v[3], fabs(d[i]));
     }
-    red_store(v, part);
+    red_store(v, part, fa);
 }
 
 // Second stage: one block folds the per-block partials in a fixed order.
