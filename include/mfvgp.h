@@ -175,6 +175,23 @@ int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x_tol,
 int mfvgp_comm_unique_id(void *id128_out /*128 bytes*/);
 int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void *id128);
 
+/*
+ * Posterior reconstruction on a fine time grid: what the
+ * notebooks do after find_minimum with symbolics.get_local_polynomials
+ * (src/numerical/symbolics.py:102-149; examples/example_500D.ipynb:537-575).
+ * Tx = [t0, obs_times..., tf] (M+2 values, M+1 intervals).  Each interval is sampled at
+ * `num` points of linspace(ti, tj, num, endpoint=False), plus tf at the end:
+ * P = (M+1)*num + 1 samples.  mean_pts [D][ldm >= 3M+4], vars_pts [D][lds >= 2M+3]
+ * (log-variances if log_vars != 0).  Outputs tt [P], mt [D][P], st [D][P].
+ * _d: device pointers on the current device; _h: host buffers (copied inside).
+ */
+int mfvgp_reconstruct(int D, int M, int num, const double *Tx_d, const double *mean_pts_d,
+                      int64_t ldm, const double *vars_pts_d, int64_t lds, int log_vars,
+                      double *tt_d, double *mt_d, double *st_d, void *cuda_stream);
+int mfvgp_reconstruct_host(int device, int D, int M, int num, const double *Tx_h,
+                           const double *mean_pts_h, const double *vars_pts_h, int log_vars,
+                           double *tt_h, double *mt_h, double *st_h);
+
 /* Which kernels this handle runs, as text ("system=L96 path=walk te=128 tn=32
  * ntiles=68 nruns=128 ..."): for benchmark reports and logs.  Returns the
  * length written (excluding the terminating 0).                            */

@@ -6,8 +6,11 @@ include/mfvgp.h.
 """
 from ._lib import MfvgpError, load as load_library          # noqa: F401
 from .free_energy import FreeEnergy                          # noqa: F401
+from .posterior import (pack, reconstruct, support_indices,  # noqa: F401
+                        time_knots, unpack)
 from .systems import (DoubleWell, Lorenz63, Lorenz96,        # noqa: F401
                       OrnsteinUhlenbeck, StochasticProcess)
 
 __all__ = ["FreeEnergy", "DoubleWell", "OrnsteinUhlenbeck", "Lorenz63", "Lorenz96",
-           "StochasticProcess", "MfvgpError", "load_library"]
+           "StochasticProcess", "MfvgpError", "load_library", "reconstruct",
+           "support_indices", "pack", "unpack", "time_knots"]

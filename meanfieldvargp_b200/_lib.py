@@ -42,6 +42,9 @@ SIGNATURES = {
     "mfvgp_comm_unique_id": (c_int, [_P]),
     "mfvgp_comm_init": (c_int, [c_void_p, c_int, c_int, _P]),
     "mfvgp_launch_count": (c_int64, [c_void_p]),
+    "mfvgp_reconstruct": (c_int, [c_int, c_int, c_int, _P, _P, c_int64, _P, c_int64, c_int, _P, _P, _P,
+                                  c_void_p]),
+    "mfvgp_reconstruct_host": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P]),
     "mfvgp_describe": (c_int, [c_void_p, c_char_p, c_int]),
     "mfvgp_refine_info": (c_int, [c_void_p, _P]),
     "mfvgp_timing": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),

@@ -15,6 +15,7 @@
 #include "refine.cuh"
 #include "l96_walk.cuh"
 #include "l96_coop.cuh"
+#include "posterior.cuh"
 #include "scg.cuh"
 
 using namespace mfvgp;
@@ -1307,4 +1308,57 @@ extern "C" int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x
     CK(cudaMemcpyAsync(x_h, h->x_dev, nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return MFVGP_OK;
+}
+
+// ---- posterior reconstruction -------------------------------------
+extern "C" int mfvgp_reconstruct(int D, int M, int num, const double *Tx_d,
+                                 const double *mean_pts_d, int64_t ldm, const double *vars_pts_d,
+                                 int64_t lds, int log_vars, double *tt_d, double *mt_d,
+                                 double *st_d, void *cuda_stream) {
+    ARG(Tx_d && mean_pts_d && vars_pts_d && tt_d && mt_d && st_d, "mfvgp_reconstruct: NULL argument");
+    ARG(D >= 1 && D <= 65535 && M >= 1 && num >= 1, "mfvgp_reconstruct: need 1 <= D <= 65535, M >= 1, num >= 1");
+    ARG(ldm >= 3 * (int64_t)M + 4 && lds >= 2 * (int64_t)M + 3, "mfvgp_reconstruct: row pitch too small");
+    ReconArgs a;
+    a.Tx = Tx_d; a.mean = mean_pts_d; a.vars = vars_pts_d; a.ldm = ldm; a.lds = lds;
+    a.tt = tt_d; a.mt = mt_d; a.st = st_d;
+    a.P = ((int64_t)M + 1) * num + 1;
+    a.D = D; a.M = M; a.num = num; a.log_vars = log_vars;
+    const int64_t nbx = (a.P + 255) / 256;
+    ARG(nbx <= 2147483647LL, "mfvgp_reconstruct: too many samples");
+    reconstruct_kernel<<<dim3((unsigned)nbx, (unsigned)D), 256, 0, (cudaStream_t)cuda_stream>>>(a);
+    CK(cudaGetLastError());
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_reconstruct_host(int device, int D, int M, int num, const double *Tx_h,
+                                      const double *mean_pts_h, const double *vars_pts_h,
+                                      int log_vars, double *tt_h, double *mt_h, double *st_h) {
+    ARG(Tx_h && mean_pts_h && vars_pts_h && tt_h && mt_h && st_h, "mfvgp_reconstruct_host: NULL argument");
+    ARG(D >= 1 && M >= 1 && num >= 1, "mfvgp_reconstruct_host: bad size");
+    if (mfvgp_device_count() <= device) {
+        g_err = "mfvgp_reconstruct_host: no CUDA device (this library has no CPU fallback)";
+        return MFVGP_ERR_CUDA;
+    }
+    CK(use_device(device));
+    const int64_t Nm = 3 * (int64_t)M + 4, Ns = 2 * (int64_t)M + 3, P = ((int64_t)M + 1) * num + 1;
+    double *buf = nullptr;
+    const size_t n_in = (size_t)(M + 2) + (size_t)D * (Nm + Ns), n_out = (size_t)P * (2 * (size_t)D + 1);
+    CK(cudaMalloc((void **)&buf, (n_in + n_out) * sizeof(double)));
+    double *Tx = buf, *mp = Tx + (M + 2), *sp = mp + (size_t)D * Nm, *tt = sp + (size_t)D * Ns,
+           *mt = tt + P, *st = mt + (size_t)D * P;
+    int rc = MFVGP_OK;
+    cudaError_t e = cudaMemcpy(Tx, Tx_h, (M + 2) * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(mp, mean_pts_h, (size_t)D * Nm * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(sp, vars_pts_h, (size_t)D * Ns * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = mfvgp_reconstruct(D, M, num, Tx, mp, Nm, sp, Ns, log_vars, tt, mt, st, nullptr);
+        if (rc == MFVGP_OK) {
+            e = cudaMemcpy(tt_h, tt, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(mt_h, mt, (size_t)D * P * sizeof(double), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(st_h, st, (size_t)D * P * sizeof(double), cudaMemcpyDeviceToHost);
+        }
+    }
+    cudaFree(buf);
+    if (e != cudaSuccess) { g_err = std::string("mfvgp_reconstruct_host: ") + cudaGetErrorString(e); return MFVGP_ERR_CUDA; }
+    return rc;
 }

@@ -1,0 +1,104 @@
+"""
+Posterior reconstruction and the wire format of the optimisation vector -- the steps either
+side of the free-energy path in the reference's notebooks.
+
+``reconstruct`` replaces the triple Python loop of examples/example_500D.ipynb cell 29
+(:537-575), which calls the two lambdified Lagrange polynomials of
+``symbolics.get_local_polynomials`` (src/numerical/symbolics.py:102-149) once per
+(time sample, dimension), by one CUDA kernel (csrc/posterior.cuh).  ``support_indices``,
+``pack`` and ``unpack`` are the host-side bookkeeping of cells 17/19 and of
+free_energy.py:678-684.  No CPU fallback: ``reconstruct`` needs the library and a GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _is_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def time_knots(t0, obs_times, tf):
+    """Tx = [t0, *obs_times, tf] (example_500D.ipynb:543)."""
+    return np.concatenate(([float(t0)], np.asarray(obs_times, dtype=float).ravel(), [float(tf)]))
+
+
+def reconstruct(mean_pts, vars_pts, t0, obs_times, tf, num=100, log_vars=False, device=0):
+    """
+    m(t), s(t) on the fine grid of the notebooks: every interval of
+    ``Tx = [t0, *obs_times, tf]`` sampled at ``np.linspace(ti, tj, num, endpoint=False)``,
+    plus ``tf``.  ``mean_pts`` [D, 3M+4], ``vars_pts`` [D, 2M+3] (the optimised support
+    points; pass ``log_vars=True`` to hand over the log-variance block of ``x`` directly).
+
+    Returns ``(tt [P], mt [D, P], st [D, P])`` with ``P = (M+1) num + 1`` -- numpy for numpy
+    inputs, CUDA tensors (same stream, no copies) for CUDA ``torch.float64`` inputs.
+    """
+    Tx = time_knots(t0, obs_times, tf)
+    M = Tx.size - 2
+    num = int(num)
+    if num < 1:
+        raise ValueError("reconstruct: num must be >= 1")
+    P = (M + 1) * num + 1
+    lib = _lib.require_device()
+    if _is_tensor(mean_pts):
+        import torch
+        mp = mean_pts if mean_pts.is_contiguous() else mean_pts.contiguous()
+        sp = vars_pts if vars_pts.is_contiguous() else vars_pts.contiguous()
+        D = mp.shape[0]
+        if mp.shape[1] != 3 * M + 4 or sp.shape != (D, 2 * M + 3):
+            raise ValueError(f"reconstruct: expected [{D}, {3 * M + 4}] mean and "
+                             f"[{D}, {2 * M + 3}] variance points for M = {M}")
+        Tx_d = torch.tensor(Tx, dtype=torch.float64, device=mp.device)
+        tt = torch.empty(P, dtype=torch.float64, device=mp.device)
+        mt = torch.empty((D, P), dtype=torch.float64, device=mp.device)
+        st = torch.empty((D, P), dtype=torch.float64, device=mp.device)
+        stream = torch.cuda.current_stream(mp.device).cuda_stream
+        _lib.check(lib.mfvgp_reconstruct(D, M, num, Tx_d.data_ptr(), mp.data_ptr(), mp.shape[1],
+                                         sp.data_ptr(), sp.shape[1], 1 if log_vars else 0,
+                                         tt.data_ptr(), mt.data_ptr(), st.data_ptr(), stream),
+                   "mfvgp_reconstruct")
+        return tt, mt, st
+    mp = np.ascontiguousarray(np.atleast_2d(np.asarray(mean_pts, dtype=np.float64)))
+    sp = np.ascontiguousarray(np.atleast_2d(np.asarray(vars_pts, dtype=np.float64)))
+    D = mp.shape[0]
+    if mp.shape[1] != 3 * M + 4 or sp.shape != (D, 2 * M + 3):
+        raise ValueError(f"reconstruct: expected [{D}, {3 * M + 4}] mean and "
+                         f"[{D}, {2 * M + 3}] variance points for M = {M}")
+    tt, mt, st = np.empty(P), np.empty((D, P)), np.empty((D, P))
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)                    # noqa: E731
+    _lib.check(lib.mfvgp_reconstruct_host(int(device), D, M, num, ptr(Tx), ptr(mp), ptr(sp),
+                                          1 if log_vars else 0, ptr(tt), ptr(mt), ptr(st)),
+               "mfvgp_reconstruct_host")
+    return tt, mt, st
+
+
+def support_indices(obs_idk, n_t):
+    """
+    Time-grid indices of the mean / variance support points (example_500D.ipynb cell 17,
+    :356-384): every interval of ``[0, *obs_idk, n_t - 1]`` contributes 4 (mean) and 3
+    (variance) equally spaced integer positions, duplicates at the observation times removed.
+    """
+    time_space = [0, *[int(i) for i in obs_idk], int(n_t) - 1]
+    mp_idk, sp_idk = [], []
+    for n in range(len(time_space) - 1):
+        mp_idk.extend(np.linspace(time_space[n], time_space[n + 1], num=4, endpoint=True, dtype=int))
+        sp_idk.extend(np.linspace(time_space[n], time_space[n + 1], num=3, endpoint=True, dtype=int))
+    return np.unique(mp_idk), np.unique(sp_idk)
+
+
+def pack(mean_pts, vars_pts):
+    """x = [means | log-variances], both row-major [D][cols] (free_energy.py:678-684;
+    the notebooks' ``np.concatenate((mp_t0.flatten(), sp_t0.flatten()))`` with sp in log-space)."""
+    return np.concatenate((np.asarray(mean_pts, dtype=float).ravel(),
+                           np.log(np.asarray(vars_pts, dtype=float)).ravel()))
+
+
+def unpack(x, dim_D, num_M):
+    """Inverse of :func:`pack`: ``(mean_pts [D, 3M+4], vars_pts [D, 2M+3])`` (variances)."""
+    x = np.asarray(x, dtype=float).ravel()
+    nm, ns = dim_D * (3 * num_M + 4), dim_D * (2 * num_M + 3)
+    if x.size != nm + ns:
+        raise ValueError(f"unpack: x has {x.size} entries, expected {nm + ns}")
+    return x[:nm].reshape(dim_D, 3 * num_M + 4), np.exp(x[nm:]).reshape(dim_D, 2 * num_M + 3)

@@ -1,0 +1,121 @@
+"""
+Posterior reconstruction and the x wire format (rank 2).
+
+CPU: the numpy oracle against golden vectors produced by the reference's own lambdified
+polynomials (symbolics.get_local_polynomials driven as in example_500D.ipynb cell 29), and
+the host-side index/pack helpers against the notebook's recipe.
+GPU: csrc/posterior.cuh through the C ABI against the same goldens and the oracle.
+Tolerance: 1e-10 relative (max norm), as for the free-energy path.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import rel_err
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+CASES = ["D5_irregular", "D1_single", "D12_uniform"]
+RTOL = 1.0e-10
+
+
+def _load(name):
+    z = np.load(GOLDEN / f"posterior_{name}.npz")
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_polynomials(name):
+    from oracle import posterior_oracle as O
+    g = _load(name)
+    tt, mt, st = O.reconstruct(g["mean_pts"], g["vars_pts"], float(g["t0"]), g["obs_times"],
+                               float(g["tf"]), int(g["num"]))
+    assert tt.shape == g["tt"].shape and mt.shape == g["mt"].shape
+    assert np.array_equal(tt, g["tt"])
+    assert rel_err(mt, g["mt"]) <= 1e-13 and rel_err(st, g["st"]) <= 1e-13
+    # the polynomials interpolate: at the left knot of every interval m(t) is the support point
+    num = int(g["num"])
+    assert rel_err(mt[:, ::num][:, :-1], g["mean_pts"][:, 0:-3:3]) <= 1e-13
+
+
+def test_support_indices_and_pack_follow_the_notebook():
+    import meanfieldvargp_b200 as mf
+    # example_500D.ipynb cell 17 (:356-384) on a small grid
+    obs_idk, n_t = [25, 50, 75], 101
+    mp_idk, sp_idk = mf.support_indices(obs_idk, n_t)
+    M = len(obs_idk)
+    assert mp_idk.size == 3 * M + 4 and sp_idk.size == 2 * M + 3
+    time_space = [0, *obs_idk, n_t - 1]
+    ref_m, ref_s = [], []
+    for n in range(len(time_space) - 1):
+        ref_m.extend(np.linspace(time_space[n], time_space[n + 1], num=4, endpoint=True, dtype=int))
+        ref_s.extend(np.linspace(time_space[n], time_space[n + 1], num=3, endpoint=True, dtype=int))
+    assert np.array_equal(mp_idk, np.unique(ref_m)) and np.array_equal(sp_idk, np.unique(ref_s))
+    assert set(obs_idk) <= set(mp_idk) and set(obs_idk) <= set(sp_idk)
+    rng = np.random.default_rng(0)
+    D = 4
+    mp, sp = rng.normal(size=(D, 3 * M + 4)), 4.0 + rng.random((D, 2 * M + 3))
+    x = mf.pack(mp, sp)
+    assert x.size == D * (5 * M + 7)
+    assert np.array_equal(x[:mp.size], mp.ravel()) and np.allclose(np.exp(x[mp.size:]), sp.ravel())
+    mp2, sp2 = mf.unpack(x, D, M)
+    assert np.array_equal(mp2, mp) and rel_err(sp2, sp) <= 1e-15
+    with pytest.raises(ValueError):
+        mf.unpack(x[:-1], D, M)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_matches_reference_polynomials(name):
+    import meanfieldvargp_b200 as mf
+    g = _load(name)
+    tt, mt, st = mf.reconstruct(g["mean_pts"], g["vars_pts"], float(g["t0"]), g["obs_times"],
+                                float(g["tf"]), int(g["num"]))
+    assert rel_err(tt, g["tt"]) <= 1e-15
+    assert rel_err(mt, g["mt"]) <= RTOL and rel_err(st, g["st"]) <= RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,M,num", [(1, 1, 1), (3, 2, 5), (40, 19, 100), (500, 16, 100), (7, 300, 33)])
+def test_gpu_matches_oracle_and_tensor_api(D, M, num):
+    import torch
+    import meanfieldvargp_b200 as mf
+    from oracle import posterior_oracle as O
+    rng = np.random.default_rng(D * 1000 + M)
+    obs_times = np.cumsum(0.1 + rng.random(M))
+    t0, tf = 0.0, float(obs_times[-1] + 0.37)
+    mp = rng.normal(2.3, 3.6, size=(D, 3 * M + 4))
+    sp = 4.0 + 2.0 * rng.random((D, 2 * M + 3))
+    tt_o, mt_o, st_o = O.reconstruct(mp, sp, t0, obs_times, tf, num)
+    tt, mt, st = mf.reconstruct(mp, sp, t0, obs_times, tf, num)
+    assert mt.shape == (D, (M + 1) * num + 1)
+    assert rel_err(tt, tt_o) <= 1e-15 and rel_err(mt, mt_o) <= RTOL and rel_err(st, st_o) <= RTOL
+    # CUDA tensors in -> tensors out; log-variance block of x handed over directly
+    x = mf.pack(mp, sp)
+    xd = torch.tensor(x, dtype=torch.float64, device="cuda")
+    mpd = xd[:mp.size].view(D, -1)
+    lsd = xd[mp.size:].view(D, -1)
+    tt2, mt2, st2 = mf.reconstruct(mpd, lsd, t0, obs_times, tf, num, log_vars=True)
+    assert mt2.is_cuda and rel_err(mt2.cpu().numpy(), mt_o) <= RTOL
+    assert rel_err(st2.cpu().numpy(), st_o) <= RTOL and rel_err(tt2.cpu().numpy(), tt_o) <= 1e-15
+
+
+@pytest.mark.gpu
+def test_reconstruct_after_find_minimum_interpolates_support_points():
+    """End of the notebook flow: optimise, reconstruct, and the fine-grid curves pass through
+    the optimised support points at the interval boundaries."""
+    import contextlib
+    import io
+    import meanfieldvargp_b200 as mf
+    from helpers import make_free_energy, synthetic_l96
+    D, M = 40, 8
+    g = synthetic_l96(D, M, seed=3)
+    fe = make_free_energy(g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        x, fx, _ = fe.find_minimum(g["x0"], max_iter=10)
+    mp, sp = mf.unpack(x, D, M)
+    t0, tf = 0.0, float(g["obs_times"][-1] + 0.25)
+    tt, mt, st = mf.reconstruct(mp, sp, t0, g["obs_times"], tf, num=50)
+    assert rel_err(mt[:, ::50][:, :-1], mp[:, 0:-3:3]) <= 1e-12
+    assert rel_err(st[:, ::50][:, :-1], sp[:, 0:-2:2]) <= 1e-12
+    assert np.all(np.diff(tt) > 0)
