@@ -1316,17 +1316,40 @@ extern "C" int mfvgp_reconstruct(int D, int M, int num, const double *Tx_d,
                                  int64_t lds, int log_vars, double *tt_d, double *mt_d,
                                  double *st_d, void *cuda_stream) {
     ARG(Tx_d && mean_pts_d && vars_pts_d && tt_d && mt_d && st_d, "mfvgp_reconstruct: NULL argument");
-    ARG(D >= 1 && D <= 65535 && M >= 1 && num >= 1, "mfvgp_reconstruct: need 1 <= D <= 65535, M >= 1, num >= 1");
+    ARG(D >= 1 && D <= 65535 * kReconRows && M >= 1 && num >= 1, "mfvgp_reconstruct: need 1 <= D <= 524280, M >= 1, num >= 1");
     ARG(ldm >= 3 * (int64_t)M + 4 && lds >= 2 * (int64_t)M + 3, "mfvgp_reconstruct: row pitch too small");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    double *vexp = nullptr;                    // variances of a log-variance input
+    const int Ns = 2 * M + 3;
+    if (log_vars) {
+        // stream-ordered scratch; keep freed blocks in the pool instead of returning them to
+        // the driver at every synchronisation (default threshold 0 makes each call re-map)
+        static thread_local int pool_ready_dev = -1;
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        if (pool_ready_dev != dev) {
+            cudaMemPool_t pool;
+            CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+            uint64_t keep = ~0ull;
+            CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            pool_ready_dev = dev;
+        }
+        CK(cudaMallocAsync((void **)&vexp, (size_t)D * Ns * sizeof(double), st));
+        const int64_t ne = (int64_t)D * Ns;
+        exp_rows_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(vars_pts_d, lds, Ns, D, vexp);
+        CK(cudaGetLastError());
+    }
     ReconArgs a;
-    a.Tx = Tx_d; a.mean = mean_pts_d; a.vars = vars_pts_d; a.ldm = ldm; a.lds = lds;
+    a.Tx = Tx_d; a.mean = mean_pts_d; a.ldm = ldm;
+    a.vars = log_vars ? vexp : vars_pts_d; a.lds = log_vars ? Ns : lds;
     a.tt = tt_d; a.mt = mt_d; a.st = st_d;
     a.P = ((int64_t)M + 1) * num + 1;
-    a.D = D; a.M = M; a.num = num; a.log_vars = log_vars;
+    a.D = D; a.M = M; a.num = num;
     const int64_t nbx = (a.P + 255) / 256;
-    ARG(nbx <= 2147483647LL, "mfvgp_reconstruct: too many samples");
-    reconstruct_kernel<<<dim3((unsigned)nbx, (unsigned)D), 256, 0, (cudaStream_t)cuda_stream>>>(a);
+    ARG(a.P < 4294967296LL, "mfvgp_reconstruct: too many samples (P must fit 32 bits)");
+    reconstruct_kernel<<<dim3((unsigned)nbx, (unsigned)((D + kReconRows - 1) / kReconRows)), 256, 0, st>>>(a);
     CK(cudaGetLastError());
+    if (vexp) CK(cudaFreeAsync(vexp, st));
     return MFVGP_OK;
 }
 
