@@ -231,7 +231,8 @@ template <int TE, int GB>
 __global__ void __launch_bounds__(TE, MFVGP_WALK_THREADS_PER_SM / TE)
 esde_l96_walk_kernel(const WalkArgs a) {
     constexpr int TD = TE - 6, NW = TE / 32;
-    __shared__ WalkSmem<TE, GB> sm;
+    extern __shared__ __align__(16) unsigned char walk_smem_raw[];
+    WalkSmem<TE, GB> &sm = *reinterpret_cast<WalkSmem<TE, GB> *>(walk_smem_raw);
 
     const int e = threadIdx.x;
     const int tile = blockIdx.x % a.ntiles, run = blockIdx.x / a.ntiles;

@@ -509,6 +509,19 @@ static int launch_fused_kernel(const EsdeArgs &a, const FusedArgs &f, unsigned g
     return MFVGP_OK;
 }
 
+template <int TE>
+static int launch_walk_kernel(const WalkArgs &w, unsigned grid, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = sizeof(WalkSmem<TE, MFVGP_WALK_GB>);
+    if (!configured) {
+        CK(cudaFuncSetAttribute(esde_l96_walk_kernel<TE, MFVGP_WALK_GB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    esde_l96_walk_kernel<TE, MFVGP_WALK_GB><<<grid, TE, smem, st>>>(w);
+    return MFVGP_OK;
+}
+
 // L96, split rule: E_cost in one main kernel (esde_l96_fused_kernel) + small follow-ups
 static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStream_t st) {
     const double *lvar = x + (int64_t)h->D * h->Nm;
@@ -543,9 +556,9 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
         w.n_begin = h->n_begin; w.n_end = h->n_end;
         w.ntiles = h->fntiles; w.nruns = h->fntn; w.TN = h->ftn;
         w.with_e0 = h->n_begin == 0;
-        if (h->fte == 32) esde_l96_walk_kernel<32, MFVGP_WALK_GB><<<grid, 32, 0, st>>>(w);
-        else if (h->fte == 64) esde_l96_walk_kernel<64, MFVGP_WALK_GB><<<grid, 64, 0, st>>>(w);
-        else esde_l96_walk_kernel<128, MFVGP_WALK_GB><<<grid, 128, 0, st>>>(w);
+        if (h->fte == 32) rc = launch_walk_kernel<32>(w, grid, st);
+        else if (h->fte == 64) rc = launch_walk_kernel<64>(w, grid, st);
+        else rc = launch_walk_kernel<128>(w, grid, st);
     } else {
     const int key = h->fte * 100 + h->ftn;
     switch (key) {
@@ -843,17 +856,36 @@ extern "C" int mfvgp_ecost_host_packed(mfvgp_handle *h, const double *x_h, int w
     int rc = ensure_host_staging(h);
     if (rc) return rc;
     const size_t nx = (size_t)h->D * (h->Nm + h->Ns);
-    double *out_d = h->grad_dev + nx;
     CK(cudaMemcpyAsync(h->x_dev, x_h, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    rc = mfvgp_ecost(h, h->x_dev, want_grad, out_d, h->grad_dev,
-                     reinterpret_cast<int32_t *>(out_d + 4), h->stream);
-    if (rc) return rc;
-    if (want_grad)
-        CK(cudaMemcpyAsync(buf_h, h->grad_dev, (nx + 5) * sizeof(double), cudaMemcpyDeviceToHost,
-                           h->stream));
-    else
-        CK(cudaMemcpyAsync(buf_h + nx, out_d, 5 * sizeof(double), cudaMemcpyDeviceToHost,
-                           h->stream));
+    // Small-problem path: assemble_tail_kernel writes every gradient entry exactly once, in
+    // index order, and never reads it back -- so it can store straight into the caller's
+    // page-locked buffer over PCIe (zero-copy), together with the scalars: no D2H copy.
+    bool direct = false;
+    if (h->coop && h->world == 1) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, buf_h) == cudaSuccess)
+            direct = attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+        else
+            cudaGetLastError();
+        if (direct) {
+            double *buf_d = static_cast<double *>(attr.devicePointer);
+            rc = mfvgp_ecost(h, h->x_dev, want_grad, buf_d + nx, buf_d,
+                             reinterpret_cast<int32_t *>(buf_d + nx + 4), h->stream);
+            if (rc) return rc;
+        }
+    }
+    if (!direct) {
+        double *out_d = h->grad_dev + nx;
+        rc = mfvgp_ecost(h, h->x_dev, want_grad, out_d, h->grad_dev,
+                         reinterpret_cast<int32_t *>(out_d + 4), h->stream);
+        if (rc) return rc;
+        if (want_grad)
+            CK(cudaMemcpyAsync(buf_h, h->grad_dev, (nx + 5) * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->stream));
+        else
+            CK(cudaMemcpyAsync(buf_h + nx, out_d, 5 * sizeof(double), cudaMemcpyDeviceToHost,
+                               h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return MFVGP_OK;
 }
