@@ -157,7 +157,12 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         return MFVGP_ERR_CUDA;
     }
     CK(cudaSetDevice(device));
+    // every error return below goes through `guard`, which releases the half-built handle
     mfvgp_handle *h = new mfvgp_handle();
+    struct Guard {
+        mfvgp_handle *h;
+        ~Guard() { if (h) mfvgp_destroy(h); }
+    } guard{h};
     h->system = system; h->D = D; h->M = M; h->d = d; h->device = device;
     h->L = L; h->n_begin = n_begin; h->n_end = n_end;
     h->Nm = 3 * M + 4; h->Ns = 2 * M + 3;
@@ -289,6 +294,7 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     CK(cudaMemset(h->esde_n, 0, L * sizeof(double)));
     CK(cudaMallocHost((void **)&h->pin, 16 * sizeof(double)));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    guard.h = nullptr;
     *out = h;
     return MFVGP_OK;
 }
@@ -498,12 +504,14 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
 template <int TE, int TN>
 static int launch_fused_kernel(const EsdeArgs &a, const FusedArgs &f, unsigned grid,
                                cudaStream_t st) {
-    static bool configured = false;
+    static uint64_t configured = 0;                 // one bit per device (attribute is per device)
     const size_t smem = sizeof(FusedSmem<TE, TN>);
-    if (!configured) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (!(configured >> (dev & 63) & 1)) {
         CK(cudaFuncSetAttribute(esde_l96_fused_kernel<TE, TN>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured |= 1ull << (dev & 63);
     }
     esde_l96_fused_kernel<TE, TN><<<grid, dim3(TE, TN), smem, st>>>(a, f);
     return MFVGP_OK;
@@ -511,12 +519,14 @@ static int launch_fused_kernel(const EsdeArgs &a, const FusedArgs &f, unsigned g
 
 template <int TE>
 static int launch_walk_kernel(const WalkArgs &w, unsigned grid, cudaStream_t st) {
-    static bool configured = false;
+    static uint64_t configured = 0;                 // one bit per device (attribute is per device)
     const size_t smem = sizeof(WalkSmem<TE, MFVGP_WALK_GB>);
-    if (!configured) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (!(configured >> (dev & 63) & 1)) {
         CK(cudaFuncSetAttribute(esde_l96_walk_kernel<TE, MFVGP_WALK_GB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured |= 1ull << (dev & 63);
     }
     esde_l96_walk_kernel<TE, MFVGP_WALK_GB><<<grid, TE, smem, st>>>(w);
     return MFVGP_OK;
