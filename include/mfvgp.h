@@ -46,7 +46,9 @@ enum {
     MFVGP_ST_E0_NONFINITE = 2,
     MFVGP_ST_EOBS_NONFINITE = 4,
     MFVGP_ST_REFINED = 8,        /* >=1 interval took the adaptive path      */
-    MFVGP_ST_REFINE_LIMIT = 16   /* adaptive path hit scipy's limit=100      */
+    MFVGP_ST_REFINE_LIMIT = 16,  /* adaptive path hit scipy's limit=100      */
+    MFVGP_ST_SYNC_TIMEOUT = 32   /* internal: a CTA gave up waiting for its neighbour's mailbox
+                                    (never expected; the gradient is then incomplete)        */
 };
 
 typedef struct mfvgp_handle mfvgp_handle;

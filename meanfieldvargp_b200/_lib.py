@@ -13,7 +13,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmfvgp.so"
 
 SYS_ID = {"DW": 0, "OU": 1, "L63": 2, "L96": 3}
-ST_ESDE, ST_E0, ST_EOBS, ST_REFINED, ST_LIMIT = 1, 2, 4, 8, 16
+ST_ESDE, ST_E0, ST_EOBS, ST_REFINED, ST_LIMIT, ST_SYNC = 1, 2, 4, 8, 16, 32
 
 _P = c_void_p     # every data pointer crosses the ABI as a plain address
 

@@ -15,9 +15,11 @@
 //     gets dE0 (:733-734), dEobs (:737-738) and the log-variance chain rule
 //     (:743) and is written straight into the gradient of x -- no per-interval
 //     workspace, no assembly pass.
-// Only the one column a run shares with the NEXT run needs another CTA: it goes
-// to a small edge buffer and edge_fixup_kernel adds it (one writer per element,
-// fixed order: deterministic).
+// Only the one column a run shares with the NEXT run needs another CTA: the next
+// run publishes its part of that column (k=0 part + dEobs) through a mailbox after
+// its first interval, and this run adds its own k=3 / k=2 part at its end and writes
+// the column (one writer per element, fixed order: deterministic; CTAs are numbered
+// by an atomic ticket so that a CTA only waits for CTAs that started before it).
 //
 // Quadrature = the split rule of esde_l96_split_kernel (kernels.cuh):
 //   (A) rational part q^2/(4s) and its d/dS on scipy's 2 x 21 Kronrod nodes, plus
@@ -196,7 +198,11 @@ struct WalkArgs {
     const double *mu0, *tau0, *obs_values, *obs_noise;
     const int32_t *obs_idx;      // [D] index into the observed dims or -1
     double *gm, *gs;             // gradient blocks [D][Nm], [D][Ns] (nullptr: value only)
-    double *edge_m, *edge_s;     // [nruns][D]: k=3 / k=2 part of each run's last interval
+    double *head_m, *head_s;     // [nruns][D]: first column of each run (k=0 part + dEobs), mailbox
+    int *head_flag;              // [nruns][ntiles]: == epoch once the run's heads are published
+    unsigned *run_ticket;        // [1]: dynamic CTA numbering (0 between launches)
+    int32_t *status;             // OR-ed MFVGP_ST_SYNC_TIMEOUT if a mailbox wait gives up
+    int epoch;                   // launch counter of this handle
     double *part;                // [(n_end-n_begin)*ntiles][kPartStride] guard partials
     double *apart;               // [gridDim.x][4]: sum log(tau0/s0), kl0 quad, obs, -
     double theta;                // L96 forcing (lorenz_96.py:70)
@@ -205,6 +211,15 @@ struct WalkArgs {
     int ntiles, nruns, TN;       // dim tiles, runs, intervals per run
     int with_e0;
 };
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -225,6 +240,8 @@ struct WalkSmem {
     double e0[2][TE];             // E_kl0 energy terms of the rows (run 0 only)
     double red[9][TE / 32];
     double dt[kWalkMaxTN], idt[kWalkMaxTN];
+    unsigned cta_id;
+    int wait_ok;
 };
 
 template <int TE, int GB>
@@ -235,7 +252,18 @@ esde_l96_walk_kernel(const WalkArgs a) {
     WalkSmem<TE, GB> &sm = *reinterpret_cast<WalkSmem<TE, GB> *>(walk_smem_raw);
 
     const int e = threadIdx.x;
-    const int tile = blockIdx.x % a.ntiles, run = blockIdx.x / a.ntiles;
+    // CTAs number themselves in the order they start (atomic ticket) and take the runs from the
+    // LAST one backwards: a run hands the k=0 part of its first column to the run before it
+    // (mailbox below), so a CTA only ever waits for CTAs that started earlier -- no deadlock,
+    // whatever order the hardware dispatches blocks in.
+    if (e == 0) {
+        const unsigned id = atomicAdd(a.run_ticket, 1u);
+        if (id == gridDim.x - 1u) *a.run_ticket = 0u;    // everybody has drawn: reset for the next launch
+        sm.cta_id = id;
+    }
+    __syncthreads();
+    const int lid = (int)sm.cta_id;
+    const int tile = lid % a.ntiles, run = a.nruns - 1 - lid / a.ntiles;
     const int n0 = a.n_begin + run * a.TN;
     const int tnv = min(a.TN, a.n_end - n0);            // intervals in this run
     const int d0 = tile * TD, D = a.D;
@@ -424,14 +452,26 @@ esde_l96_walk_kernel(const WalkArgs a) {
             if (want_grad) {
                 double *gmp = const_cast<double *>(mp) + g_off_m + 3 * nl;
                 double *gsp = const_cast<double *>(sp) + g_off_s + 2 * nl;
-                gmp[0] = gm0;
+                if (nl == 0 && run > 0) {
+                    // this column also receives the k=3 / k=2 part of the previous run's last
+                    // interval: that run adds it and writes the column (mailbox, see below)
+                    a.head_m[(int64_t)run * D + j] = gm0;
+                    a.head_s[(int64_t)run * D + j] = gs0;
+                } else {
+                    gmp[0] = gm0;
+                    gsp[0] = gs0 * S0;                           // :743
+                }
                 gmp[1] = sc_gl * accM[1];
                 gmp[2] = sc_gl * accM[2];
-                gsp[0] = gs0 * S0;                               // :743
                 gsp[1] = dsv[1] * S1;
             }
             sm.carry[0][e] = sc_gl * accM[3];
             sm.carry[1][e] = dsv[2];
+        }
+        if (nl == 0 && run > 0 && want_grad) {               // publish the heads of this run
+            __threadfence();
+            __syncthreads();
+            if (e == 0) st_release_gpu(a.head_flag + run * a.ntiles + tile, a.epoch);
         }
         if (more) {
             cp_async_wait_all();
@@ -442,14 +482,32 @@ esde_l96_walk_kernel(const WalkArgs a) {
     }
 
     // ---- the column this run shares with the next one ------------------------------------
+    const bool last_run = n0 + tnv == a.n_end;           // last run of this shard (CTA-uniform)
+    if (!last_run && want_grad) {
+        // the next run published the rest of that column after ITS first interval, long ago
+        if (e == 0) {
+            const int *flag = a.head_flag + (run + 1) * a.ntiles + tile;
+            int ok = 0;
+            for (long spin = 0; spin < (1L << 26); ++spin) {
+                if (ld_acquire_gpu(flag) == a.epoch) { ok = 1; break; }
+                __nanosleep(64);
+            }
+            if (!ok) atomicOr(a.status, 32);              // MFVGP_ST_SYNC_TIMEOUT: never expected
+            sm.wait_ok = ok;
+        }
+        __syncthreads();
+    }
     if (is_out) {
-        const bool last_run = n0 + tnv == a.n_end;       // last run of this shard
         const bool last_shard = a.n_end == a.L;
         const double carry_m = sm.carry[0][e], carry_s = sm.carry[1][e];
         if (!last_run) {
             if (want_grad) {
-                a.edge_m[(int64_t)run * D + j] = carry_m;
-                a.edge_s[(int64_t)run * D + j] = carry_s;
+                const double hm = __ldcg(a.head_m + (int64_t)(run + 1) * D + j);
+                const double hs = __ldcg(a.head_s + (int64_t)(run + 1) * D + j);
+                double *gmp = const_cast<double *>(mp) + g_off_m + 3 * tnv;
+                double *gsp = const_cast<double *>(sp) + g_off_s + 2 * tnv;
+                gmp[0] = hm + carry_m;
+                gsp[0] = (hs + carry_s) * S2;                    // :743, same support point
             }
         } else {
             // end column of the shard, 3 n_end / 2 n_end.  On the last shard observation

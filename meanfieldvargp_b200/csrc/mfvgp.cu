@@ -45,6 +45,8 @@ struct mfvgp_handle {
     int te = 64, ntiles = 1;
     int coop = 0;     // small L96 problems: esde_l96_coop_kernel + assemble_tail_kernel (l96_coop.cuh)
     unsigned *tickets = nullptr;
+    int *head_flag = nullptr;     // walk kernel mailbox flags [fntn][fntiles]
+    int walk_epoch = 0;
     double *y_dense = nullptr, *rinv_row = nullptr;   // row tables of assemble_tail_kernel
     double *esde_n2 = nullptr;                        // esde_small_inkernel: CTA 1's guard outputs
     int32_t *flags2 = nullptr;
@@ -284,8 +286,11 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     CK(cudaMalloc((void **)&h->refine_status, sizeof(int32_t)));
     CK(cudaMemset(h->refine_info, 0, 2 * L * sizeof(int32_t)));
     CK(cudaMemset(h->refine_status, 0, sizeof(int32_t)));
-    CK(cudaMalloc((void **)&h->tickets, (L + 2) * sizeof(unsigned)));
-    CK(cudaMemset(h->tickets, 0, (L + 2) * sizeof(unsigned)));
+    CK(cudaMalloc((void **)&h->head_flag, (size_t)h->fntn * h->fntiles * sizeof(int)));
+    CK(cudaMemset(h->head_flag, 0, (size_t)h->fntn * h->fntiles * sizeof(int)));
+    // [0, L): coop kernel, one per interval; L: SCG folds; L+1: tail kernel; L+2: walk kernel
+    CK(cudaMalloc((void **)&h->tickets, (L + 4) * sizeof(unsigned)));
+    CK(cudaMemset(h->tickets, 0, (L + 4) * sizeof(unsigned)));
     CK(cudaMalloc((void **)&h->obs_idx, D * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->flags, L * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->flags2, L * sizeof(int32_t)));
@@ -309,7 +314,7 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal,
                     h->refine_ws, h->refine_info, h->refine_status, h->edge_send, h->edge_recv,
                     h->gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
-                    h->y_dense, h->rinv_row, h->esde_n2, h->flags2};
+                    h->y_dense, h->rinv_row, h->esde_n2, h->flags2, h->head_flag};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
@@ -560,7 +565,9 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
         w.x = x; w.obs_times = h->obs_times; w.sigma = h->sigma; w.theta = h->theta_host[0];
         w.mu0 = h->mu0; w.tau0 = h->tau0; w.obs_values = h->obs_values;
         w.obs_noise = h->obs_noise; w.obs_idx = h->obs_idx;
-        w.gm = f.gm; w.gs = f.gs; w.edge_m = h->fedge_m; w.edge_s = h->fedge_s;
+        w.gm = f.gm; w.gs = f.gs; w.head_m = h->fedge_m; w.head_s = h->fedge_s;
+        w.head_flag = h->head_flag; w.run_ticket = h->tickets + h->L + 2;
+        w.status = h->refine_status; w.epoch = ++h->walk_epoch;
         w.part = h->part; w.apart = h->fapart;
         w.D = h->D; w.M = h->M; w.d = h->d; w.Nm = h->Nm; w.Ns = h->Ns; w.L = h->L;
         w.n_begin = h->n_begin; w.n_end = h->n_end;
@@ -595,7 +602,7 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
                              h->fntiles, 1, st);
     if (rc) return rc;
     if (grad != nullptr) {
-        if (h->fntn > 1) {
+        if (h->fntn > 1 && h->fused != 2) {       // the walk kernel stitches its runs itself
             FixupArgs fx;
             fx.x = x; fx.gm = f.gm; fx.gs = f.gs; fx.edge_m = h->fedge_m; fx.edge_s = h->fedge_s;
             fx.D = h->D; fx.Nm = h->Nm; fx.Ns = h->Ns; fx.n_begin = h->n_begin; fx.ntn = h->fntn;

@@ -225,6 +225,9 @@ class FreeEnergy(object):
     # ---- error convention ----------------------------------------------------
     def _raise_on_status(self, status, E0=None, Esde=None, Eobs=None):
         name = self.__class__.__name__
+        if status & _lib.ST_SYNC:
+            raise _lib.MfvgpError("internal synchronisation timeout in the Lorenz-96 kernel "
+                                  "(MFVGP_ST_SYNC_TIMEOUT): the gradient is incomplete")
         if status & _lib.ST_E0:                                   # :313-316
             raise RuntimeError(f" {name}: E0 is not a finite number: {E0}")
         if status & _lib.ST_ESDE:                                 # :547-550
@@ -344,7 +347,7 @@ class FreeEnergy(object):
         status = int(buf[n + 4:n + 5].view(np.int32)[0])
         self.last_status = status
         self.last_terms = {"F": out[0], "E0": out[1], "Esde": out[2], "Eobs": out[3]}
-        if status & 7:
+        if status & 39:
             self._raise_on_status(status, E0=out[1], Esde=out[2], Eobs=out[3])
         if not output_gradients:
             return float(out[0])
