@@ -332,6 +332,37 @@ def run_posterior(torch, hbm_gbs):
     return out
 
 
+def run_trajectory(torch):
+    """Lorenz 96 sample path on the device (csrc/trajectory.cuh)."""
+    import meanfieldvargp_b200 as mf
+    out = {}
+    for tag, D, tf, dt in (("L96-500 (example_500D.ipynb: T=[0,4], dt=1e-3)", 500, 4.0, 1.0e-3),
+                           ("L96-8192", 8192, 1.0, 1.0e-3)):
+        rng = np.random.default_rng(575)
+        dim_t = mf.trajectory.time_window(0.0, tf, dt).size
+        noise = torch.as_tensor(rng.standard_normal((D, dim_t)), device="cuda")
+        mf.simulate_l96(40.0, 8.0, D, 0.0, tf, dt, noise=noise)            # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tk, x = mf.simulate_l96(40.0, 8.0, D, 0.0, tf, dt, noise=noise)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        steps = 125 * D + dim_t - 1
+        out[tag] = {"D": D, "burn_in_steps": 125 * D, "path_steps": dim_t - 1, "wall_s": wall,
+                    "steps_per_s": steps / wall, "us_per_step": 1e6 * wall / steps,
+                    "bound": "latency (time is sequential: one CTA, one barrier per step)"}
+        if D == 500:
+            from oracle import trajectory_oracle as O
+            t0 = time.perf_counter()
+            _, xo = O.make_trajectory(40.0, 8.0, D, 0.0, tf, dt, noise=noise.cpu().numpy())
+            cw = time.perf_counter() - t0
+            out[tag]["cpu_baseline"] = {"value": steps / cw, "unit": "steps/s", "cores": 1,
+                                        "kind": "port", "sample": f"the same path, {cw:.2f} s "
+                                        "(oracle/trajectory_oracle.py = the reference's numpy loop)"}
+            out[tag]["bit_identical_to_cpu"] = bool(np.array_equal(x.cpu().numpy(), xo))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -473,6 +504,12 @@ def main():
             posterior = run_posterior(torch, hbm_gbs)
         except Exception as ex:
             posterior = {"error": f"{type(ex).__name__}: {ex}"}
+    trajectory = None
+    if rank == 0 and not args.no_large:
+        try:
+            trajectory = run_trajectory(torch)
+        except Exception as ex:
+            trajectory = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world,
@@ -486,6 +523,7 @@ def main():
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "c_abi_back_to_back": c_abi,
                 "scg": scg, "large": large, "next_posterior": posterior,
+                "next_trajectory": trajectory,
                 "fp64_peak_tflops_measured": fp64_peak_tf}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -194,6 +194,19 @@ int mfvgp_reconstruct_host(int device, int D, int M, int num, const double *Tx_h
                            const double *mean_pts_h, const double *vars_pts_h, int log_vars,
                            double *tt_h, double *mt_h, double *st_h);
 
+/*
+ * Lorenz 96 sample path: Lorenz96.make_trajectory
+ * (src/dynamical_systems/lorenz_96.py:103-185) -- burn-in of nburn Euler steps of size
+ * delta_t from x = theta (+0.01 at D/2), then dim_t - 1 Euler-Maruyama steps of size dt
+ * with the noise increments ek_td [dim_t][D] (time major; row 0 unused; the reference's
+ * sqrt(sigma dt) * standard_normal((D, dim_t)), transposed).  x_out_d [dim_t][D].
+ * Bit-identical to the reference's arithmetic (separately rounded multiplies and adds).
+ * status_h: bit 0 = NaN after the burn-in, bit 1 = NaN on the path (the reference raises).
+ */
+int mfvgp_l96_trajectory(int D, double theta, double dt, int dim_t, int nburn, double delta_t,
+                         const double *ek_td_d, double *x_out_d, int32_t *status_h,
+                         void *cuda_stream);
+
 /* Which kernels this handle runs, as text ("system=L96 path=walk te=128 tn=32
  * ntiles=68 nruns=128 ..."): for benchmark reports and logs.  Returns the
  * length written (excluding the terminating 0).                            */

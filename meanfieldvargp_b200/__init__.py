@@ -8,9 +8,10 @@ from ._lib import MfvgpError, load as load_library          # noqa: F401
 from .free_energy import FreeEnergy                          # noqa: F401
 from .posterior import (pack, reconstruct, support_indices,  # noqa: F401
                         time_knots, unpack)
+from .trajectory import collect_obs, simulate_l96          # noqa: F401
 from .systems import (DoubleWell, Lorenz63, Lorenz96,        # noqa: F401
                       OrnsteinUhlenbeck, StochasticProcess)
 
 __all__ = ["FreeEnergy", "DoubleWell", "OrnsteinUhlenbeck", "Lorenz63", "Lorenz96",
            "StochasticProcess", "MfvgpError", "load_library", "reconstruct",
-           "support_indices", "pack", "unpack", "time_knots"]
+           "support_indices", "pack", "unpack", "time_knots", "simulate_l96", "collect_obs"]

@@ -16,6 +16,7 @@
 #include "l96_walk.cuh"
 #include "l96_coop.cuh"
 #include "posterior.cuh"
+#include "trajectory.cuh"
 #include "scg.cuh"
 
 using namespace mfvgp;
@@ -1433,4 +1434,38 @@ extern "C" int mfvgp_reconstruct_host(int device, int D, int M, int num, const d
     cudaFree(buf);
     if (e != cudaSuccess) { g_err = std::string("mfvgp_reconstruct_host: ") + cudaGetErrorString(e); return MFVGP_ERR_CUDA; }
     return rc;
+}
+
+// ---- Lorenz 96 sample path ------------------------------------------
+extern "C" int mfvgp_l96_trajectory(int D, double theta, double dt, int dim_t, int nburn,
+                                    double delta_t, const double *ek_td_d, double *x_out_d,
+                                    int32_t *status_h, void *cuda_stream) {
+    ARG(ek_td_d && x_out_d && status_h, "mfvgp_l96_trajectory: NULL argument");
+    ARG(D >= 4, "Lorenz96: Insufficient state vector dimensions");          // lorenz_96.py:60-63
+    ARG(dim_t >= 1 && nburn >= 0, "mfvgp_l96_trajectory: bad step counts");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    TrajArgs a;
+    a.ek = ek_td_d; a.x_out = x_out_d; a.scratch = nullptr;
+    a.theta = theta; a.dt = dt; a.delta_t = delta_t;
+    a.D = D; a.dim_t = dim_t; a.nburn = nburn;
+    const size_t smem = 2 * (size_t)D * sizeof(double);
+    a.use_smem = smem <= 200 * 1024;
+    int threads = (D + 31) / 32 * 32;
+    if (threads > 1024) threads = 1024;
+    int32_t *status_d = nullptr;
+    CK(cudaMallocAsync((void **)&status_d, sizeof(int32_t), st));
+    if (a.use_smem) {
+        CK(cudaFuncSetAttribute(l96_trajectory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+    } else {
+        CK(cudaMallocAsync((void **)&a.scratch, smem, st));
+    }
+    a.status = status_d;
+    l96_trajectory_kernel<<<1, threads, a.use_smem ? smem : 0, st>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(status_h, status_d, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFreeAsync(status_d, st));
+    if (a.scratch) CK(cudaFreeAsync(a.scratch, st));
+    return MFVGP_OK;
 }
