@@ -1158,6 +1158,70 @@ add_edges_kernel(const EdgeArgs a) {
     }
 }
 
+// One-collective exchange (E_cost with gradient): every rank all-gathers
+// [record 16 | left edge 2D | right edge 2D]; stride = 16 + 4 D doubles.
+struct XchgArgs {
+    double *grad;
+    const double *rec;        // [16] local record (final_kernel)
+    double *send;             // [16 + 4 D]
+    const double *gathered;   // [world][16 + 4 D]
+    double *out;              // [4] F, E0, Esde, Eobs
+    int32_t *status;
+    int D, Nm, Ns, n_begin, n_end, rank, world;
+};
+
+__global__ void __launch_bounds__(256)
+pack_all_kernel(const XchgArgs a) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x < 16) a.send[threadIdx.x] = a.rec[threadIdx.x];
+    if (j >= a.D) return;
+    const double *gm = a.grad + (int64_t)j * a.Nm;
+    const double *gs = a.grad + (int64_t)a.D * a.Nm + (int64_t)j * a.Ns;
+    double *e = a.send + 16;
+    e[j] = gm[3 * a.n_begin];
+    e[a.D + j] = gs[2 * a.n_begin];
+    e[2 * a.D + j] = gm[3 * a.n_end];
+    e[3 * a.D + j] = gs[2 * a.n_end];
+}
+
+// folds the records in rank order and adds the neighbours' parts of the shared columns:
+// the left neighbour's RIGHT edge onto column 3 n_begin, the right neighbour's LEFT edge onto
+// column 3 n_end (two addends each, so both owners end up with identical bits)
+__global__ void __launch_bounds__(256)
+combine_all_kernel(const XchgArgs a) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = 16 + 4 * (int64_t)a.D;
+    if (blockIdx.x == 0 && threadIdx.x < 9) {
+        const int i = threadIdx.x;
+        double v = a.gathered[i];
+        for (int r = 1; r < a.world; ++r) v += a.gathered[r * stride + i];
+        if (i < 4) a.out[i] = v;
+        // status bits travel as 0/1 in slots 4..8 (final_kernel record9)
+        __shared__ double sh_bits[9];
+        sh_bits[i] = v;
+        __syncwarp();
+        if (i == 0) {
+            int32_t st = 0;
+            for (int b = 0; b < 5; ++b)
+                if (sh_bits[4 + b] > 0.0) st |= 1 << b;
+            a.status[0] = st;
+        }
+    }
+    if (j >= a.D) return;
+    double *gm = a.grad + (int64_t)j * a.Nm;
+    double *gs = a.grad + (int64_t)a.D * a.Nm + (int64_t)j * a.Ns;
+    if (a.rank > 0) {
+        const double *e = a.gathered + (a.rank - 1) * stride + 16;
+        gm[3 * a.n_begin] += e[2 * a.D + j];
+        gs[2 * a.n_begin] += e[3 * a.D + j];
+    }
+    if (a.rank < a.world - 1) {
+        const double *e = a.gathered + (a.rank + 1) * stride + 16;
+        gm[3 * a.n_end] += e[j];
+        gs[2 * a.n_end] += e[a.D + j];
+    }
+}
+
 // gathered [world][n]: slots < nsum are summed in rank order, the rest max'ed
 __global__ void combine_record_kernel(const double *gathered, int world, int n, int nsum,
                                       double *out, int32_t *status /*or nullptr*/) {

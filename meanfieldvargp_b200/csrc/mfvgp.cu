@@ -84,8 +84,10 @@ struct mfvgp_handle {
     // multi-GPU: one rank per GPU, intervals [n_begin, n_end) of this handle
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    int one_collective = 1;       // MFVGP_XCHG=split: send/recv of the edges + all-gather of the record
     double *edge_send = nullptr, *edge_recv = nullptr;   // [4][D] each
     double *gather = nullptr;                            // [world][16]
+    double *xchg_send = nullptr, *xchg_gather = nullptr; // one-collective exchange: [16 + 4D], [world][..]
     double *rec_ws = nullptr;                            // [16] local record before combine
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
@@ -314,7 +316,7 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->scg_vec[0], h->scg_vec[1], h->scg_vec[2], h->scg_vec[3], h->scg_vec[4],
                     h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal,
                     h->refine_ws, h->refine_info, h->refine_status, h->edge_send, h->edge_recv,
-                    h->gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
+                    h->gather, h->xchg_send, h->xchg_gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
                     h->y_dense, h->rinv_row, h->esde_n2, h->flags2, h->head_flag};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -641,8 +643,11 @@ static int combine_over_ranks(mfvgp_handle *h, const double *local, int n, int n
     return MFVGP_OK;
 }
 
+// grad != nullptr on a sharded handle: ONE all-gather carries the scalar record and both shared
+// columns of every rank (replaces send/recv + all-gather: the collectives' latency is what
+// limits the 8-GPU point)
 static int launch_final(mfvgp_handle *h, const double *apart, int napart, double *out,
-                        int32_t *status, cudaStream_t st) {
+                        int32_t *status, cudaStream_t st, double *grad = nullptr) {
     FinalArgs f;
     const bool multi = h->world > 1;
     f.esde_n = h->esde_n; f.flags = h->flags; f.apart = apart;
@@ -655,6 +660,23 @@ static int launch_final(mfvgp_handle *h, const double *apart, int napart, double
     final_kernel<<<1, 256, 0, st>>>(f);
     h->launches++;
     CK(cudaGetLastError());
+    if (multi && grad != nullptr && h->one_collective) {
+        XchgArgs x;
+        x.grad = grad; x.rec = h->rec_ws; x.send = h->xchg_send; x.gathered = h->xchg_gather;
+        x.out = out; x.status = status;
+        x.D = h->D; x.Nm = h->Nm; x.Ns = h->Ns; x.n_begin = h->n_begin; x.n_end = h->n_end;
+        x.rank = h->rank; x.world = h->world;
+        const int nb = (h->D + 255) / 256;
+        pack_all_kernel<<<nb, 256, 0, st>>>(x);
+        h->launches++;
+        CK(cudaGetLastError());
+        NCK(nccl().AllGather(h->xchg_send, h->xchg_gather, 16 + 4 * (size_t)h->D, kNcclFloat64,
+                             h->comm, st));
+        combine_all_kernel<<<nb, 256, 0, st>>>(x);
+        h->launches++;
+        CK(cudaGetLastError());
+        return MFVGP_OK;
+    }
     if (multi) {
         // scalar free energy: every rank ends up with the same F, E0, Esde, Eobs
         int rc = combine_over_ranks(h, h->rec_ws, 9, 9, h->rec_ws, status, st);
@@ -713,8 +735,14 @@ extern "C" int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void 
     memcpy(&id, id128, sizeof(id));
     NCK(nccl().CommInitRank(&h->comm, world, id, rank));
     h->rank = rank; h->world = world;
+    {
+        const char *e = getenv("MFVGP_XCHG");
+        h->one_collective = !(e && std::string(e) == "split");
+    }
     if (dev_alloc(&h->edge_send, 4 * (size_t)h->D) || dev_alloc(&h->edge_recv, 4 * (size_t)h->D) ||
-        dev_alloc(&h->gather, 16 * (size_t)world))
+        dev_alloc(&h->gather, 16 * (size_t)world) ||
+        dev_alloc(&h->xchg_send, 16 + 4 * (size_t)h->D) ||
+        dev_alloc(&h->xchg_gather, (size_t)world * (16 + 4 * (size_t)h->D)))
         return MFVGP_ERR_CUDA;
     return MFVGP_OK;
 }
@@ -757,11 +785,12 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
     if (h->fused) {
         rc = launch_fused(h, x_d, want_grad ? grad_d : nullptr, st);
         if (rc) return rc;
-        if (h->world > 1 && want_grad) {
+        if (h->world > 1 && want_grad && !h->one_collective) {
             rc = exchange_edges(h, grad_d, st);
             if (rc) return rc;
         }
-        return launch_final(h, h->fapart, h->fntn * h->fntiles, out_d, status_d, st);
+        return launch_final(h, h->fapart, h->fntn * h->fntiles, out_d, status_d, st,
+                            want_grad ? grad_d : nullptr);
     }
     rc = launch_esde(h, mean, h->Nm, lvar, h->Ns, 1, want_grad ? h->dm_ws : nullptr,
                      want_grad ? h->ds_ws : nullptr, st);
@@ -791,11 +820,11 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
     assemble_kernel<<<h->D, 256, 0, st>>>(a);
     h->launches++;
     CK(cudaGetLastError());
-    if (h->world > 1 && want_grad) {
+    if (h->world > 1 && want_grad && !h->one_collective) {
         rc = exchange_edges(h, grad_d, st);
         if (rc) return rc;
     }
-    return launch_final(h, h->apart, h->D, out_d, status_d, st);
+    return launch_final(h, h->apart, h->D, out_d, status_d, st, want_grad ? grad_d : nullptr);
 }
 
 static int ensure_host_staging(mfvgp_handle *h) {
