@@ -1133,15 +1133,16 @@ struct ScgRun {
     int status_or = 0;
     bool fused = false;          // single GPU: folds in the producers, host-mapped record
 
-    FoldArgs fold_args() {
+    FoldArgs fold_args(int mode = 0, double beta_in = 0.0) {
         FoldArgs fa;
+        fa.mode = mode; fa.ctrl = h->scg_scal + 16; fa.beta_in = beta_in;
         fa.ticket = nullptr; fa.scal = h->scg_scal; fa.status = h->status_ws;
         fa.host_rec = h->scg_hostrec_dev;
         fa.host_flag = reinterpret_cast<volatile long long *>(h->scg_hostrec_dev + 16);
         fa.epoch = 0;
         if (fused) {
             fa.ticket = h->tickets + h->L;
-            fa.epoch = ++h->scg_epoch;
+            if (mode == 0 || mode == 3) fa.epoch = ++h->scg_epoch;    // only these publish
         }
         return fa;
     }
@@ -1193,9 +1194,51 @@ struct ScgRun {
         h->launches++;
         return fold();
     }
-    int axpy(double *y, const double *x, const double *d, double a) {
-        CK(launch_pdl(scg_axpy_kernel, dim3(h->scg_nblk), kRedBlock, st, y, x, d, a, n));
+    int axpy(double *y, const double *x, const double *d, double a, const double *a_dev = nullptr) {
+        CK(launch_pdl(scg_axpy_kernel, dim3(h->scg_nblk), kRedBlock, st, y, x, d, a, a_dev, n));
         h->launches++;
+        return MFVGP_OK;
+    }
+    // One successful iteration enqueued in one go (scaled_cg.py:192-247 + :361-369): direction
+    // update, sigma step, theta, alpha step, trial statistics -- sigma and alpha stay on the
+    // device (FoldArgs modes 1-3); the host reads ONE record at the end instead of three.
+    int chain(double *d, const double *g, double gamma, int restart, double beta, double *x,
+              double *xt, double *gp, double *gnow) {
+        const double *ctrl = h->scg_scal + 16;
+        CK(launch_pdl(scg_direction_kernel, dim3(h->scg_nblk), kRedBlock, st, d, g, gamma, restart,
+                      n, h->scg_part, fold_args(1)));
+        h->launches++;
+        int rc = axpy(xt, x, d, 0.0, ctrl + 0);
+        if (rc) return rc;
+        rc = eval(xt, gp);
+        if (rc) return rc;
+        CK(launch_pdl(scg_theta_kernel, dim3(h->scg_nblk), kRedBlock, st, (const double *)d,
+                      (const double *)gp, g, n, h->scg_part, fold_args(2, beta)));
+        h->launches++;
+        rc = axpy(xt, x, d, 0.0, ctrl + 1);
+        if (rc) return rc;
+        rc = eval(xt, gnow);
+        if (rc) return rc;
+        CK(launch_pdl(scg_stats_kernel, dim3(h->scg_nblk), kRedBlock, st, (const double *)gnow, g,
+                      (const double *)d, n, h->scg_part, fold_args(3)));
+        h->launches++;
+        return MFVGP_OK;
+    }
+    // waits for the record of the last publishing kernel; rec16 = host_rec[0..15]
+    int read16(double *rec16) {
+        volatile long long *flag = reinterpret_cast<volatile long long *>(h->scg_hostrec + 16);
+        long spins = 0;
+        while (*flag != h->scg_epoch) {
+            if ((++spins & 0xfffff) == 0) {
+                cudaError_t q = cudaStreamQuery(st);
+                if (q != cudaSuccess && q != cudaErrorNotReady) {
+                    g_err = std::string("mfvgp_scg: ") + cudaGetErrorString(q);
+                    return MFVGP_ERR_CUDA;
+                }
+            }
+        }
+        __sync_synchronize();
+        memcpy(rec16, h->scg_hostrec, 16 * sizeof(double));
         return MFVGP_OK;
     }
     int theta(const double *d, const double *gp, const double *g) {
@@ -1248,7 +1291,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         int64_t nb = (n + kRedBlock * 4 - 1) / (kRedBlock * 4);
         h->scg_nblk = (int)(nb < 1 ? 1 : (nb > 1184 ? 1184 : nb));
         if (dev_alloc(&h->scg_part, (size_t)h->scg_nblk * kRedSlots) ||
-            dev_alloc(&h->scg_scal, 8))
+            dev_alloc(&h->scg_scal, 32))
             return MFVGP_ERR_CUDA;
     }
     if (!h->scg_hostrec) {
@@ -1289,7 +1332,34 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     int64_t count_success = 0;
     if (failed) { nit = 0; fx = f_now; }
 
+    bool chained = false;          // a speculative chain for this iteration is in flight
+    double alpha = 0.0;
     for (int j = 0; j < max_it && !done; ++j) {                   // :186
+        bool have_stats = false;
+        if (chained) {
+            chained = false;
+            double r16[16];
+            RC(R.read16(r16));
+            const int flags = (int)r16[15];
+            mu = r16[9]; kappa = r16[10];
+            if (flags & 1) {
+                // mu >= 0 (:194-197): rare; the chain's results are void, redo the iteration
+                // on the step-by-step path below (it restarts the direction first)
+            } else if (flags & 2) {                               // :203
+                fx = f_now; nit = j + 1; done = true; break;
+            } else {
+                func_eval++;
+                R.status_or |= (int32_t)r16[11];
+                if (R.status_or & 7) { fx = f_now; nit = j + 1; done = true; break; }
+                theta = r16[12]; alpha = r16[13]; beta = r16[14];
+                func_eval++;
+                R.status_or |= (int32_t)r16[8];
+                if (R.status_or & 7) { fx = f_now; nit = j + 1; done = true; break; }
+                memcpy(s8, r16, 8 * sizeof(double));
+                have_stats = true;
+            }
+        }
+        if (!have_stats) {
         if (success) {
             if (mu >= 0.0) {                                      // :194-197
                 RC(R.direction(d, gnew, 0.0, 1));
@@ -1311,13 +1381,14 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
             delta = beta * kappa;
             beta = beta - theta / kappa;
         }
-        const double alpha = -(mu / delta);
+        alpha = -(mu / delta);
         RC(R.axpy(xt, x, d, alpha));
         RC(R.eval(xt, gnow));                                     // :247
         RC(R.stats(gnow, gnew, d));
         RC(R.read(s8));
         func_eval++;
         if (R.status_or & 7) { fx = f_now; nit = j + 1; done = true; break; }
+        }
         const double f_new = s8[4], sa_now = s8[0], gg = s8[1], prnum = s8[2], maxd = s8[3];
         const double Delta = 2.0 * (f_new - f_old) / (alpha * mu);   // :253
         double total_grad;
@@ -1350,16 +1421,29 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         }
         if (Delta < 0.25) beta = fmin(4.0 * beta, beta_max);      // :350-356
         if (Delta > 0.75) beta = fmax(0.5 * beta, beta_min);
-        if (count_success == n_total) {                           // :361-369
-            RC(R.direction(d, gnew, 0.0, 1));
-            RC(R.read(s8));
-            mu = s8[0]; kappa = s8[1];
+        // :361-369 -- the new direction; on one GPU it opens the speculative chain of the
+        // next iteration (direction, sigma step, theta, alpha step, statistics: one host read)
+        const bool spec = R.fused && success && j + 1 < max_it;
+        if (count_success == n_total) {
             count_success = 0;
+            if (spec) {
+                RC(R.chain(d, gnew, 0.0, 1, beta, x, xt, gp, gnow));
+                chained = true;
+            } else {
+                RC(R.direction(d, gnew, 0.0, 1));
+                RC(R.read(s8));
+                mu = s8[0]; kappa = s8[1];
+            }
         } else if (success) {
             const double gamma = fmax(prnum / mu, 0.0);
-            RC(R.direction(d, gnew, gamma, 0));
-            RC(R.read(s8));
-            mu = s8[0]; kappa = s8[1];
+            if (spec) {
+                RC(R.chain(d, gnew, gamma, 0, beta, x, xt, gp, gnow));
+                chained = true;
+            } else {
+                RC(R.direction(d, gnew, gamma, 0));
+                RC(R.read(s8));
+                mu = s8[0]; kappa = s8[1];
+            }
         }
     }
     if (!done) fx = f_old;                                        // :379

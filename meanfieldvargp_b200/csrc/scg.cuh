@@ -32,6 +32,15 @@ struct FoldArgs {
     double *host_rec;          // [16] host-mapped record
     volatile long long *host_flag;
     long long epoch;
+    // Speculative chain of one successful iteration (mfvgp_scg): the scalars between the
+    // kernels stay on the device.  mode 0: publish (above).  mode 1 (direction): mu, kappa,
+    // sigma = 1e-3/sqrt(kappa) (scaled_cg.py:203-212) -> ctrl.  mode 2 (theta): theta, delta,
+    // beta, alpha (:228-239) -> ctrl.  mode 3 (stats): publish sums + ctrl.  ctrl [16]:
+    // 0 sigma, 1 alpha, 2 theta, 3 delta, 4 beta, 5 mu, 6 kappa, 7 flags (1: mu >= 0,
+    // 2: kappa < eps), 8 status of the sigma-step evaluation.
+    int mode;
+    double *ctrl;
+    double beta_in;
 };
 
 // Index map of the optimisation vector a rank works on.  Single GPU: the whole
@@ -140,10 +149,38 @@ __device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part,
     fold_partials(part, (int)gridDim.x, r, sh);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < kRedSlots; ++i) { fa.scal[i] = r[i]; fa.host_rec[i] = r[i]; }
+        for (int i = 0; i < kRedSlots; ++i) fa.scal[i] = r[i];
+        double *c = fa.ctrl;
+        if (fa.mode == 1) {                    // the host's arithmetic, operation for operation
+            const double mu = r[0], kappa = r[1];
+            c[5] = mu; c[6] = kappa;
+            c[7] = (mu >= 0.0 ? 1.0 : 0.0) + (kappa < 2.220446049250313e-16 ? 2.0 : 0.0);
+            c[0] = 1.0e-3 / sqrt(kappa);
+            return;
+        }
+        if (fa.mode == 2) {
+            const double sigma = c[0], mu = c[5], kappa = c[6];
+            const double theta = r[0] / sigma;
+            double beta = fa.beta_in;
+            double delta = __dadd_rn(theta, __dmul_rn(beta, kappa));
+            if (delta <= 0.0) {
+                delta = __dmul_rn(beta, kappa);
+                beta = __dsub_rn(beta, theta / kappa);
+            }
+            c[1] = -(mu / delta); c[2] = theta; c[3] = delta; c[4] = beta;
+            c[8] = (double)__ldcg(fa.status);
+            return;
+        }
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) fa.host_rec[i] = r[i];
 #pragma unroll
         for (int i = 4; i < 8; ++i) fa.host_rec[i] = __ldcg(fa.scal + i);
         fa.host_rec[8] = (double)__ldcg(fa.status);
+        if (fa.mode == 3) {
+            fa.host_rec[9] = c[5]; fa.host_rec[10] = c[6]; fa.host_rec[11] = c[8];
+            fa.host_rec[12] = c[2]; fa.host_rec[13] = c[1]; fa.host_rec[14] = c[4];
+            fa.host_rec[15] = c[7];
+        }
         __threadfence_system();
         *fa.host_flag = fa.epoch;
     }
@@ -173,8 +210,10 @@ scg_direction_kernel(double *d, const double *g, double gamma, int restart, cons
 
 // y = x + a*d                                   (scaled_cg.py:222, :242)
 __global__ void __launch_bounds__(kRedBlock)
-scg_axpy_kernel(double *y, const double *x, const double *d, double a, const VecMap vm) {
+scg_axpy_kernel(double *y, const double *x, const double *d, double a, const double *a_dev,
+                const VecMap vm) {
     scg_pdl_enter();
+    if (a_dev != nullptr) a = __ldcg(a_dev);      // step length computed on the device
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
          t += (int64_t)gridDim.x * blockDim.x) {
         bool own;
