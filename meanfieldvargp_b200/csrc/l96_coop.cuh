@@ -68,8 +68,8 @@ esde_l96_coop_kernel(const CoopArgs ca) {
     const bool has_energy = (e >= 2) && (e <= TE - 2);
     const bool is_out = (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
 
-    pdl_launch_dependents();
     pdl_wait();                     // x and the workspaces belong to the predecessor until here
+    pdl_launch_dependents();        // only now: the tail kernel reads x before ITS wait
     const double ti = a.obs_times[n], tj = a.obs_times[n + 1];
     const double *mp = a.mean + (int64_t)j * a.ldm + 3 * (int64_t)n;
     const double *sp = a.vars + (int64_t)j * a.lds + 2 * (int64_t)n;
@@ -288,8 +288,8 @@ __global__ void __launch_bounds__(64)
 esde_small_inkernel(const SmallArgs sa) {
     const EsdeArgs &a = sa.c.a;
     const int n = a.n_begin + blockIdx.x, tid = threadIdx.x, y = blockIdx.y;
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();        // only now: the tail kernel reads x before ITS wait
     EsdeArgs mine = a;
     GuardArgs g = sa.c.g;
     if (y == 1) { mine.part = sa.part2; g.part = sa.part2; g.esde_n = sa.esde_n2; g.flags = sa.flags2; }
@@ -333,7 +333,7 @@ assemble_tail_kernel(const TailArgs t) {
     const unsigned nm = (unsigned)a.D * a.Nm, ntot = nm + (unsigned)a.D * a.Ns;
     double acc[3] = {0.0, 0.0, 0.0};
     pdl_launch_dependents();
-    pdl_wait();
+    if (idx >= ntot) pdl_wait();
     if (idx < ntot) {
         const bool is_mean = idx < nm;
         const unsigned r = is_mean ? idx : idx - nm;
@@ -343,18 +343,22 @@ assemble_tail_kernel(const TailArgs t) {
         const int n = is_mean ? c / 3 : c >> 1, k = c - step * n;
         const double *ws = is_mean ? a.dm : a.ds;
         const bool obs_col = k == 0 && n >= 1 && n <= a.M;
-        // independent loads first
+        // inputs that do not depend on the preceding kernel first: their latency hides under
+        // that kernel's tail (programmatic dependent launch); x itself was final before the
+        // preceding kernel started
         const double xv = a.x[idx];
         double own = 0.0, prev = 0.0, y = 0.0, Ri = 0.0, mu = 0.0, t0 = 1.0;
-        if (ws != nullptr) {
-            if (n < a.L) own = ws[((int64_t)n * a.D + j) * K + k];
-            if (k == 0 && n >= 1 && n - 1 < a.L) prev = ws[((int64_t)(n - 1) * a.D + j) * K + step];
-        }
         if (obs_col) {
             Ri = t.rinv_row[j];
             y = t.y_dense[(int64_t)(n - 1) * a.D + j];
         }
         if (c == 0) { mu = a.mu0[j]; t0 = a.tau0[j]; }
+        const double s = is_mean ? 0.0 : exp(xv);
+        pdl_wait();                                   // the per-interval gradients are ready
+        if (ws != nullptr) {
+            if (n < a.L) own = ws[((int64_t)n * a.D + j) * K + k];
+            if (k == 0 && n >= 1 && n - 1 < a.L) prev = ws[((int64_t)(n - 1) * a.D + j) * K + step];
+        }
         double g = own;
         g += prev;
         if (is_mean) {
@@ -370,7 +374,6 @@ assemble_tail_kernel(const TailArgs t) {
             }
             if (a.grad) a.grad[idx] = g;
         } else {
-            const double s = exp(xv);
             if (c == 0) {
                 g += 0.5 * (1.0 / t0 - 1.0 / s);
                 acc[0] += log(t0 / s);
