@@ -68,17 +68,21 @@ esde_l96_coop_kernel(const CoopArgs ca) {
     const bool has_energy = (e >= 2) && (e <= TE - 2);
     const bool is_out = (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
 
+    // problem data never written by a kernel: load it (and warm the constant tables) while the
+    // predecessor is still running
+    const double ti = a.obs_times[n], tj = a.obs_times[n + 1];
+    const double Sig = a.sigma[j];
+    const double dt = fabs(tj - ti);
+    const double inv_dt = fast_rcp(dt), inv_sig = fast_rcp(Sig), hid = 0.5 * inv_dt;
+    double warm = c_pair[(tid * 8) % (kPairs * kPairStride)] + c_gl[(tid * 8) % (kGL * kTabStride)];
     pdl_wait();                     // x and the workspaces belong to the predecessor until here
     pdl_launch_dependents();        // only now: the tail kernel reads x before ITS wait
-    const double ti = a.obs_times[n], tj = a.obs_times[n + 1];
     const double *mp = a.mean + (int64_t)j * a.ldm + 3 * (int64_t)n;
     const double *sp = a.vars + (int64_t)j * a.lds + 2 * (int64_t)n;
     const double P0 = mp[0], P1 = mp[1], P2 = mp[2], P3 = mp[3];
     double S0 = sp[0], S1 = sp[1], S2 = sp[2];
-    const double Sig = a.sigma[j];
     if (a.log_vars) { S0 = exp(S0); S1 = exp(S1); S2 = exp(S2); }
-    const double dt = fabs(tj - ti);
-    const double inv_dt = fast_rcp(dt), inv_sig = fast_rcp(Sig), hid = 0.5 * inv_dt;
+    if (warm == 1.2345e300) S0 = warm;          // never true: keeps the warm-up loads alive
 
     // ---- (A) rational part: lane l integrates Kronrod panel l ------------------------------
     // (every cell of the warp takes part: the shuffles need all 32 lanes; halo cells work

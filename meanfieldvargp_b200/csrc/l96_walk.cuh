@@ -65,8 +65,10 @@ __device__ __forceinline__ void panel_sums(double al0, double al1, double al2, d
     for (int ii = 0; ii < kPairs / 2; ++ii) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const double *T = c_pair + (2 * ii + h) * kPairStride;
-            const double x = T[PR_X];
+            // 8 constants of the pair as four 16-byte constant loads
+            const double2 *T2 = reinterpret_cast<const double2 *>(c_pair) + (2 * ii + h) * 4;
+            const double2 c01 = T2[0], c23 = T2[1], c45 = T2[2], c67 = T2[3];
+            const double x = c01.x, v = c01.y, vx = c23.x, vx2 = c23.y, vx3 = c45.x;
             const double sp = fma(fma(al2, x, al1), x, al0);
             const double sm = fma(fma(al2, -x, al1), -x, al0);
             const double qp = fma(be1, x, be0), qm = fma(-be1, x, be0);
@@ -74,21 +76,22 @@ __device__ __forceinline__ void panel_sums(double al0, double al1, double al2, d
             const double tE = fma(qp, ip, qm * im);                          // sum of q^2 / s
             const double p2 = ip * ip, m2 = im * im;                         // (q/s)^2
             const double ue = p2 + m2, uo = p2 - m2, le = ip + im, lo = ip - im;
-            kE = fma(T[PR_V], tE, kE);
-            N0 = fma(T[PR_V], ue, N0);
-            N2 = fma(T[PR_VX2], ue, N2);
-            N1 = fma(T[PR_VX], uo, N1);
-            N3 = fma(T[PR_VX3], uo, N3);
-            L0 = fma(T[PR_V], le, L0);
-            L2 = fma(T[PR_VX2], le, L2);
-            L1 = fma(T[PR_VX], lo, L1);
+            kE = fma(v, tE, kE);
+            N0 = fma(v, ue, N0);
+            N2 = fma(vx2, ue, N2);
+            N1 = fma(vx, uo, N1);
+            N3 = fma(vx3, uo, N3);
+            L0 = fma(v, le, L0);
+            L2 = fma(vx2, le, L2);
+            L1 = fma(vx, lo, L1);
             if (h == 1) {
-                gE = fma(T[PR_W], tE, gE);
-                GN0 = fma(T[PR_W], ue, GN0);
-                GN2 = fma(T[PR_WX2], ue, GN2);
-                GN1 = fma(T[PR_WX], uo, GN1);
-                GL0 = fma(T[PR_W], le, GL0);
-                GL1 = fma(T[PR_WX], lo, GL1);
+                const double w = c45.y, wx = c67.x, wx2 = c67.y;
+                gE = fma(w, tE, gE);
+                GN0 = fma(w, ue, GN0);
+                GN2 = fma(wx2, ue, GN2);
+                GN1 = fma(wx, uo, GN1);
+                GL0 = fma(w, le, GL0);
+                GL1 = fma(wx, lo, GL1);
             }
         }
     }
