@@ -892,6 +892,8 @@ struct GuardArgs {
     const double *obs_times;
     double *esde_n;            // [L] per-interval Esde (already * 1/2)
     int32_t *flags;            // [L] bit0 energy integrand, bit1 dS integrand
+    int32_t *nflagged;         // [1] number of flagged intervals of this evaluation, or nullptr
+                               //     (lets refine / apply_refine exit without scanning the flags)
     int n_begin, n_end, ntiles;
 };
 
@@ -927,6 +929,7 @@ __device__ __forceinline__ void guard_interval(const GuardArgs &a, int n, int la
         if (!(ubE < 0.125 * tolE)) f |= 1;
         if (!(ubS < 0.125 * tolS)) f |= 2;
         a.flags[n] = f;
+        if (f && a.nflagged != nullptr) atomicAdd(a.nflagged, 1);
     }
 }
 
@@ -1047,6 +1050,7 @@ struct FinalArgs {
     double *out;              // [4]
     int32_t *status;          // [1]
     int32_t *refine_status;   // [1] bits set by refine_kernel, consumed here
+    int32_t *nflagged;        // [1] GuardArgs::nflagged, reset here (or nullptr)
     int record9;              // out has 9 slots (multi-GPU record)
     int n_begin, n_end, D;    // D = number of apart rows (state dims, or CTAs of the fused kernel)
     int with_e0;
@@ -1095,6 +1099,7 @@ __device__ __forceinline__ void final_body(const FinalArgs &a) {
         if (sh_flag) st |= 8;
         st |= a.refine_status[0];
         a.refine_status[0] = 0;
+        if (a.nflagged != nullptr) a.nflagged[0] = 0;
         // record[0..3] = F, E0, Esde, Eobs; record[4..8] = status bits as 0/1 so
         // that shards can be combined by summation (combine_record_kernel)
         a.out[0] = E0 + Esde + Eobs;
@@ -1111,6 +1116,10 @@ __device__ __forceinline__ void final_body(const FinalArgs &a) {
 
 __global__ void __launch_bounds__(256)
 final_kernel(const FinalArgs a) { final_body<256>(a); }
+
+// many partial rows (walk path: one per CTA of the main kernel): 1024 threads
+__global__ void __launch_bounds__(1024)
+final_kernel_wide(const FinalArgs a) { final_body<1024>(a); }
 
 // ---------------------------------------------------------------------------
 // Multi-GPU (time intervals sharded, one rank per GPU).  Neighbouring shards

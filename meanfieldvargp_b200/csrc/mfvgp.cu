@@ -70,7 +70,7 @@ struct mfvgp_handle {
     int32_t *flags = nullptr, *status_ws = nullptr;
     // adaptive refinement (refine.cuh)
     double *refine_ws = nullptr;
-    int32_t *refine_info = nullptr, *refine_status = nullptr;
+    int32_t *refine_info = nullptr, *refine_status = nullptr;   // refine_status[1] = flagged count
     int refine_grid = 1;
     // host-API staging
     double *x_dev = nullptr, *grad_dev = nullptr;
@@ -286,9 +286,9 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     if (h->coop && (dev_alloc(&h->y_dense, (size_t)M * D) || dev_alloc(&h->rinv_row, D)))
         return MFVGP_ERR_CUDA;
     CK(cudaMalloc((void **)&h->refine_info, 2 * L * sizeof(int32_t)));
-    CK(cudaMalloc((void **)&h->refine_status, sizeof(int32_t)));
+    CK(cudaMalloc((void **)&h->refine_status, 2 * sizeof(int32_t)));
     CK(cudaMemset(h->refine_info, 0, 2 * L * sizeof(int32_t)));
-    CK(cudaMemset(h->refine_status, 0, sizeof(int32_t)));
+    CK(cudaMemset(h->refine_status, 0, 2 * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->head_flag, (size_t)h->fntn * h->fntiles * sizeof(int)));
     CK(cudaMemset(h->head_flag, 0, (size_t)h->fntn * h->fntiles * sizeof(int)));
     // [0, L): coop kernel, one per interval; L: SCG folds; L+1: tail kernel; L+2: walk kernel
@@ -413,6 +413,7 @@ static RefineArgs refine_args(mfvgp_handle *h, const double *mean, int64_t ldm, 
     r.mean = mean; r.vars = vars; r.ldm = ldm; r.lds = lds;
     r.obs_times = h->obs_times; r.sigma = h->sigma; r.theta = h->theta;
     r.flags = h->flags; r.esde_n = h->esde_n; r.ds_out = ds; r.ws = h->refine_ws;
+    r.nflagged = h->coop ? nullptr : h->refine_status + 1;
     r.delta_mode = delta_mode;
     r.info = h->refine_info; r.status = h->refine_status;
     r.D = h->D; r.n_begin = h->n_begin; r.n_end = h->n_end; r.log_vars = log_vars;
@@ -427,6 +428,7 @@ static int launch_guard_refine(mfvgp_handle *h, const double *mean, int64_t ldm,
     GuardArgs g;
     g.part = h->part; g.obs_times = h->obs_times; g.esde_n = h->esde_n; g.flags = h->flags;
     g.n_begin = h->n_begin; g.n_end = h->n_end; g.ntiles = ntiles;
+    g.nflagged = h->refine_status + 1;
     guard_reduce_kernel<<<(nl * 32 + 255) / 256, 256, 0, st>>>(g);
     h->launches++;
     CK(cudaGetLastError());
@@ -464,6 +466,7 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         c.g.part = h->part; c.g.obs_times = h->obs_times; c.g.esde_n = h->esde_n;
         c.g.flags = h->flags; c.g.n_begin = h->n_begin; c.g.n_end = h->n_end;
         c.g.ntiles = h->ntiles;
+        c.g.nflagged = nullptr;              // the in-kernel adaptive path reads the flag itself
         c.r = refine_args(h, mean, ldm, vars, lds, log_vars, ds, 0);
         c.tickets = h->tickets; c.theta = h->theta_host[0];
     }
@@ -615,7 +618,7 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
             CK(cudaGetLastError());
         }
         ApplyRefineArgs ar;
-        ar.flags = h->flags; ar.delta = h->ds_ws; ar.x = x; ar.gs = f.gs;
+        ar.flags = h->flags; ar.nflagged = h->refine_status + 1; ar.delta = h->ds_ws; ar.x = x; ar.gs = f.gs;
         ar.D = h->D; ar.Nm = h->Nm; ar.Ns = h->Ns; ar.n_begin = h->n_begin; ar.n_end = h->n_end;
         apply_refine_kernel<<<h->n_end - h->n_begin + 1, 256, 0, st>>>(ar);
         h->launches++;
@@ -653,11 +656,13 @@ static int launch_final(mfvgp_handle *h, const double *apart, int napart, double
     f.esde_n = h->esde_n; f.flags = h->flags; f.apart = apart;
     f.out = multi ? h->rec_ws : out; f.status = status;
     f.refine_status = h->refine_status;
+    f.nflagged = h->coop ? nullptr : h->refine_status + 1;
     f.record9 = multi ? 1 : 0;
     f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = napart;
     f.with_e0 = h->n_begin == 0;
     f.eobs_const = h->n_begin == 0 ? h->eobs_const : 0.0;
-    final_kernel<<<1, 256, 0, st>>>(f);
+    if (napart > 2048) final_kernel_wide<<<1, 1024, 0, st>>>(f);
+    else final_kernel<<<1, 256, 0, st>>>(f);
     h->launches++;
     CK(cudaGetLastError());
     if (multi && grad != nullptr && h->one_collective) {
@@ -809,6 +814,7 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
         const int nb = h->tail_grid;
         t.f.esde_n = h->esde_n; t.f.flags = h->flags; t.f.apart = h->apart;
         t.f.out = out_d; t.f.status = status_d; t.f.refine_status = h->refine_status;
+        t.f.nflagged = nullptr;
         t.f.record9 = 0; t.f.n_begin = h->n_begin; t.f.n_end = h->n_end; t.f.D = nb;
         t.f.with_e0 = 1; t.f.eobs_const = h->eobs_const;
         t.ticket = h->tickets + h->L + 1;

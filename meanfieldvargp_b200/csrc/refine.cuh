@@ -40,6 +40,7 @@ struct RefineArgs {
     int64_t ldm, lds;
     const double *obs_times, *sigma, *theta;
     const int32_t *flags;      // [L] bit0: energy, bit1: dS
+    const int32_t *nflagged;   // [1] number of flagged intervals (nullptr: scan the flags)
     double *esde_n;            // [L]   overwritten for refined energy integrals
     double *ds_out;            // [L][D][3] overwritten for refined dS integrals (or nullptr)
     double *ws;                // [gridDim.x][2][D*kMaxNE] scratch: elementwise integral, and
@@ -404,6 +405,11 @@ template <int SYS>
 __global__ void __launch_bounds__(kRefThreads)
 refine_kernel(const RefineArgs a) {
     const int nl = a.n_end - a.n_begin;
+    if (a.nflagged != nullptr && a.nflagged[0] == 0) {        // the common case: nothing to do
+        for (int w = blockIdx.x * kRefThreads + threadIdx.x; w < 2 * nl; w += gridDim.x * kRefThreads)
+            a.info[2 * a.n_begin + w] = 0;
+        return;
+    }
     double *ws = a.ws + (int64_t)blockIdx.x * 2 * a.D * kMaxNE;
     double *ws_fixed = ws + (int64_t)a.D * kMaxNE;
     for (int w = blockIdx.x; w < 2 * nl; w += gridDim.x) {
@@ -422,6 +428,7 @@ refine_kernel(const RefineArgs a) {
 // writer and a fixed order of its (at most two) addends.
 struct ApplyRefineArgs {
     const int32_t *flags;      // [L]
+    const int32_t *nflagged;   // [1] or nullptr
     const double *delta;       // [L][D][3]  (refined - fixed), already * 1/2 / Sigma
     const double *x;           // optimisation vector (log-variances after D*Nm)
     double *gs;                // gradient, variance block [D][Ns]
@@ -430,6 +437,7 @@ struct ApplyRefineArgs {
 
 __global__ void __launch_bounds__(256)
 apply_refine_kernel(const ApplyRefineArgs a) {
+    if (a.nflagged != nullptr && a.nflagged[0] == 0) return;
     const int n = a.n_begin + blockIdx.x;             // n_end itself: last shared column only
     const bool f_own = n < a.n_end && (a.flags[n] & 2);
     const bool f_prev = n > a.n_begin && (a.flags[n - 1] & 2);
