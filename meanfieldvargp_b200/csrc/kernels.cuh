@@ -413,347 +413,6 @@ esde_l96_split_kernel(const EsdeArgs a) {
 
 
 // ---------------------------------------------------------------------------
-// Lorenz 96, fused E_cost kernel: split rule + gradient assembly in one launch.
-// A CTA owns TE extended dimensions x TN consecutive intervals.  The input
-// tile (mean columns 3n0..3(n0+TN), log-variance columns 2n0..2(n0+TN)) is
-// staged through shared memory with coalesced row reads and exp() applied once
-// per support point; the per-interval gradients are stitched in shared memory
-// (free_energy.py:715-728: shared end points add), E0 (:733-734) and the
-// observation terms (:737-738) are added, the log-variance chain rule (:743)
-// is applied and the tile is written straight into the gradient with
-// coalesced row writes.  Only the one column a tile shares with the NEXT tile
-// needs another CTA's contribution: it goes to a small edge buffer and
-// edge_fixup_kernel adds it afterwards (deterministic, no atomics).
-// ---------------------------------------------------------------------------
-struct FusedArgs {
-    double *gm, *gs;             // gradient blocks [D][Nm], [D][Ns] (nullptr: value only)
-    const double *mu0, *tau0, *obs_values, *obs_noise;
-    const int32_t *obs_idx;
-    double *edge_m, *edge_s;     // [ntn][D]: k=3 / k=2 part of each tile's last interval
-    double *apart;               // [gridDim.x][4]: sum log(tau0/s0), kl0 quad, obs, -
-    int M, d, Nm, Ns, L, ntn, with_e0;
-};
-
-template <int TE, int TN>
-struct FusedSmem {
-    static constexpr int CM = (3 * TN + 8) | 1, CS = (2 * TN + 6) | 1;   // odd: no bank conflicts
-    double om[TE][CM], os[TE][CS];     // stitched gradient tile (incl. tail columns)
-    double ex[6][TN][TE];              // neighbour exchange: m, s, A, B, C, D
-    double red[9][TN][TE / 32];        // per-row guard partials
-    double red2[3][TE * TN / 32];
-    int jrow[TE];
-};
-
-template <int TE, int TN>
-__global__ void __launch_bounds__(TE * TN)
-esde_l96_fused_kernel(const EsdeArgs a, const FusedArgs f) {
-    using SM = FusedSmem<TE, TN>;
-    constexpr int TD = TE - 6, CM = SM::CM, CS = SM::CS, NT = TE * TN, NW = NT / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SM &sm = *reinterpret_cast<SM *>(smem_raw);
-
-    const int e = threadIdx.x, nl = threadIdx.y, tid = nl * TE + e;
-    const int tile = blockIdx.x % a.ntiles, tn = blockIdx.x / a.ntiles;
-    const int n0 = a.n_begin + tn * TN;
-    const int tnv = min(TN, a.n_end - n0);              // valid intervals in this tile
-    const bool valid = nl < tnv;
-    const int n = valid ? n0 + nl : n0;
-    const int d0 = tile * TD, D = a.D;
-    int j = (d0 - 3 + e) % D;
-    if (j < 0) j += D;
-    const bool has_energy = valid && (e >= 2) && (e <= TE - 2);
-    const bool is_out = valid && (e >= 3) && (e <= TE - 4) && (d0 + e - 3 < D);
-    const bool last_tile = n0 + tnv == a.n_end;         // last tile of this shard
-    const bool last_shard = a.n_end == f.L;
-    const bool want_grad = f.gm != nullptr;
-    // gradient columns this tile writes: [3 n0, cend_m) and [2 n0, cend_s)
-    const int cend_m = !last_tile ? 3 * (n0 + tnv) : (last_shard ? f.Nm : 3 * a.n_end + 1);
-    const int cend_s = !last_tile ? 2 * (n0 + tnv) : (last_shard ? f.Ns : 2 * a.n_end + 1);
-    const int ncm = cend_m - 3 * n0, ncs = cend_s - 2 * n0;
-
-    // ---- loads: everything this thread will ever need, issued up front -------------
-    const double ti = a.obs_times[n], tj = a.obs_times[n + 1];
-    const double *mp = a.mean + (int64_t)j * a.ldm + 3 * (int64_t)n;
-    const double *sp = a.vars + (int64_t)j * a.lds + 2 * (int64_t)n;
-    const double P0 = mp[0], P1 = mp[1], P2 = mp[2], P3 = mp[3];
-    double S0 = sp[0], S1 = sp[1], S2 = sp[2];
-    const double Sig = a.sigma[j];
-    const double theta = a.theta[0];
-    const int jo = is_out ? f.obs_idx[j] : -1;
-    const bool end_thread = is_out && n == a.n_end - 1;  // also owns the shard's end column
-    double Ri = 0.0, y0 = 0.0, y1 = 0.0, y2 = 0.0, mu0 = 0.0, tau0 = 1.0, mT = 0.0, sT = 1.0;
-    if (jo >= 0) {
-        Ri = f.obs_noise[jo];
-        if (n >= 1) y0 = f.obs_values[(int64_t)(n - 1) * f.d + jo];          // obs at column 3n
-        if (end_thread && last_shard) {                                      // tail: k = M-1, M
-            y1 = f.obs_values[(int64_t)(f.M - 2) * f.d + jo];
-            y2 = f.obs_values[(int64_t)(f.M - 1) * f.d + jo];
-            mT = a.mean[(int64_t)j * a.ldm + 3 * f.M];
-            sT = a.vars[(int64_t)j * a.lds + 2 * f.M];
-        }
-    }
-    if (is_out && n == 0 && f.with_e0) { mu0 = f.mu0[j]; tau0 = f.tau0[j]; }
-    if (nl == 0) sm.jrow[e] = j;
-    for (int idx = tid; idx < TE * CM; idx += NT) (&sm.om[0][0])[idx] = 0.0;
-    for (int idx = tid; idx < TE * CS; idx += NT) (&sm.os[0][0])[idx] = 0.0;
-
-    if (a.log_vars) { S0 = exp(S0); S1 = exp(S1); S2 = exp(S2); sT = exp(sT); }
-    if (jo >= 0) Ri = 1.0 / Ri;
-    const double dt = fabs(tj - ti);
-    const double inv_dt = 1.0 / dt;
-    const double inv_sig = 1.0 / Sig;
-
-    // ---- (A) rational part (see esde_l96_split_kernel) ---------------------------
-    double aE = 0.0, eE1 = 0.0, eE2 = 0.0, eS1 = 0.0, eS2 = 0.0, m1S1 = 0.0, m1S2 = 0.0;
-    double aSv[3] = {0, 0, 0}, aSd[3] = {0, 0, 0};
-    if (is_out) {
-        const double a0 = S0, a1 = -3.0 * S0 + 4.0 * S1 - S2, a2 = 2.0 * (S0 - 2.0 * S1 + S2);
-        const double b0 = a1 * inv_dt - Sig, b1 = 2.0 * a2 * inv_dt;
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            double kE = 0.0, gE = 0.0, mSv = 0.0, mSd = 0.0;
-            double kSv[3] = {0, 0, 0}, kSd[3] = {0, 0, 0}, gSv[3] = {0, 0, 0}, gSd[3] = {0, 0, 0};
-#pragma unroll
-            for (int r = 0; r < kNodesPerPanel; ++r) {
-                const double *T = c_rat + (p * kNodesPerPanel + r) * kTabStride;
-                const double tau = T[R_TAU];
-                const double s = fma(fma(a2, tau, a1), tau, a0);
-                const double qq = fma(b1, tau, b0);
-                const double qi = qq * fast_rcp3(s);
-                const double t = qq * qi;
-                const double qi2 = qi * qi;
-                kE = fma(T[R_V], t, kE);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    kSv[k] = fma(T[R_VB + k], qi2, kSv[k]);
-                    kSd[k] = fma(T[R_VD + k], qi, kSd[k]);
-                }
-                mSv = fma(c_vxB[p * kNodesPerPanel + r], qi2, mSv);
-                mSd = fma(c_vxD[p * kNodesPerPanel + r], qi, mSd);
-                if (r & 1) {
-                    gE = fma(T[R_W], t, gE);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        gSv[k] = fma(T[R_WB + k], qi2, gSv[k]);
-                        gSd[k] = fma(T[R_WD + k], qi, gSd[k]);
-                    }
-                }
-            }
-            const double dE = 0.25 * (kE - gE);
-            double eS = 0.0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double kg = fma(0.5 * inv_dt, kSd[k] - gSd[k], -0.25 * (kSv[k] - gSv[k]));
-                eS = fma(kg, kg, eS);
-                aSv[k] += kSv[k];
-                aSd[k] += kSd[k];
-            }
-            aE += kE;
-            const double m1 = fma(0.5 * inv_dt, mSd, -0.25 * mSv)
-                              + fma(c_m1poly[2 * p + 1], inv_dt, c_m1poly[2 * p]);
-            if (p == 0) { eE1 = dE * dE; eS1 = eS; m1S1 = m1 * m1; }
-            else { eE2 = dE * dE; eS2 = eS; m1S2 = m1 * m1; }
-        }
-    }
-
-    // ---- (B) coupled polynomial part, 7 Gauss-Legendre nodes ---------------------
-    double accM[4] = {0, 0, 0, 0}, accS[3] = {0, 0, 0}, accE = 0.0;
-#pragma unroll
-    for (int g = 0; g < kGL; ++g) {
-        const double *T = c_gl + g * kTabStride;
-        const double m = P0 * T[T_B3] + P1 * T[T_B3 + 1] + P2 * T[T_B3 + 2] + P3 * T[T_B3 + 3];
-        const double dm = (P0 * T[T_DB3] + P1 * T[T_DB3 + 1] + P2 * T[T_DB3 + 2]
-                           + P3 * T[T_DB3 + 3]) * inv_dt;
-        const double s = S0 * T[T_B2] + S1 * T[T_B2 + 1] + S2 * T[T_B2 + 2];
-        sm.ex[0][nl][e] = m;
-        sm.ex[1][nl][e] = s;
-        __syncthreads();
-        double own_m = 0.0;
-        if (has_energy) {
-            const double ma = sm.ex[0][nl][e + 1], mb = sm.ex[0][nl][e - 1], mc = sm.ex[0][nl][e - 2];
-            const double sa = sm.ex[1][nl][e + 1], sb = sm.ex[1][nl][e - 1], sc = sm.ex[1][nl][e - 2];
-            const double u = ma - mc, su = sa + sc;
-            const double R = fma(u, mb, theta - m) - dm;
-            const double t1 = sb * u, t2 = mb * su;
-            const double Ec = fma(R, R, fma(t1, u, fma(t2, mb, su * sb)));
-            const double w = T[T_V] * inv_sig, w2 = w + w;
-            const double wR2 = w2 * R;
-            sm.ex[2][nl][e] = fma(wR2, mb, w2 * t1);
-            sm.ex[3][nl][e] = fma(wR2, u, w2 * t2);
-            sm.ex[4][nl][e] = w * fma(mb, mb, sb);
-            sm.ex[5][nl][e] = w * fma(u, u, su);
-            own_m = -wR2;
-            accE = fma(w, Ec, accE);
-        }
-        __syncthreads();
-        if (is_out) {
-            const double Gm = own_m + sm.ex[2][nl][e - 1] + sm.ex[3][nl][e + 1] - sm.ex[2][nl][e + 2];
-            const double Gs = sm.ex[4][nl][e - 1] + sm.ex[5][nl][e + 1] + sm.ex[4][nl][e + 2];
-            const double Hm = own_m * inv_dt;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                accM[k] += Gm * T[T_B3 + k] + Hm * T[T_DB3 + k];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) accS[k] = fma(Gs, T[T_B2 + k], accS[k]);
-        }
-    }
-
-    // ---- per-interval results (same algebra as the split kernel) ------------------
-    const double four_inv_dt = 4.0 * inv_dt;
-    const double own_poly = dt * (S0 + 4.0 * S1 + S2) * (1.0 / 6.0) + (S2 - S0) - Sig * dt;
-    const double ksum_E = 0.25 * aE + 4.0 * accE * Sig + four_inv_dt * own_poly;
-    double kS[3], dmv[4], dsv[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) kS[k] = fma(0.5 * inv_dt, aSd[k], -0.25 * aSv[k]);
-    {
-        const double sc_gl = 0.5 * dt, sc_gk = 0.5 * 0.25 * dt * inv_sig;
-        const double polyS[3] = {dt * (1.0 / 6.0) - 1.0, dt * (4.0 / 6.0), dt * (1.0 / 6.0) + 1.0};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dmv[k] = sc_gl * accM[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            dsv[k] = sc_gl * accS[k] + sc_gk * kS[k] + 0.5 * inv_sig * polyS[k];
-    }
-    double own2 = 0.0;
-    {
-        const double polyK[3] = {four_inv_dt * (dt * (1.0 / 6.0) - 1.0), four_inv_dt * dt * (4.0 / 6.0),
-                                 four_inv_dt * (dt * (1.0 / 6.0) + 1.0)};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const double o = kS[k] + polyK[k];
-            own2 = fma(o, o, own2);
-        }
-    }
-    // guard partials, reduced over the TE threads of each interval row
-    {
-        double red[9] = {ksum_E * inv_sig, ksum_E * ksum_E, eE1, eE2, eS1, eS2, own2, m1S1, m1S2};
-        const int lane = e & 31, w = e >> 5;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            double v = is_out ? red[i] : 0.0;
-            v = warp_sum(v);
-            if (lane == 0) sm.red[i][nl][w] = v;
-        }
-    }
-
-    // ---- stitch the tile in shared memory (free_energy.py:715-728) --------------------
-    if (is_out && want_grad) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) sm.om[e][3 * nl + k] = dmv[k];
-        sm.os[e][2 * nl] = dsv[0];
-        sm.os[e][2 * nl + 1] = dsv[1];
-    }
-    __syncthreads();
-    if (is_out && want_grad) {
-        if (nl < tnv - 1 || last_tile) {
-            sm.om[e][3 * nl + 3] += dmv[3];       // next interval's first column (or the
-            sm.os[e][2 * nl + 2] += dsv[2];       // shard's end column)
-        } else {
-            f.edge_m[(int64_t)tn * D + j] = dmv[3];
-            f.edge_s[(int64_t)tn * D + j] = dsv[2];
-        }
-    }
-    if (valid && e == 0) {                        // finish the guard partials of this row
-        double *p = a.part + ((int64_t)(n - a.n_begin) * a.ntiles + tile) * kPartStride;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            double v = sm.red[i][nl][0];
-            for (int w = 1; w < TE / 32; ++w) v += sm.red[i][nl][w];
-            p[i] = v;
-        }
-    }
-    __syncthreads();
-
-    // ---- owner threads: + dE0 (:733-734), + dEobs (:737-738), x exp(x) (:743) ----------
-    double acc[3] = {0.0, 0.0, 0.0};
-    if (is_out) {
-        double gm0 = sm.om[e][3 * nl], gs0 = sm.os[e][2 * nl];
-        if (n == 0 && f.with_e0) {
-            const double z0 = P0 - mu0;
-            gm0 += z0 / tau0;
-            gs0 += 0.5 * (1.0 / tau0 - 1.0 / S0);
-            acc[0] += log(tau0 / S0);
-            acc[1] += (z0 * z0 + S0 - tau0) / tau0;
-        }
-        if (jo >= 0 && n >= 1) {
-            const double rr = y0 - P0;
-            gm0 -= Ri * rr;
-            gs0 += 0.5 * Ri;
-            acc[2] += Ri * (rr * rr + S0);
-        }
-        sm.om[e][3 * nl] = gm0;
-        sm.os[e][2 * nl] = gs0 * S0;
-        sm.os[e][2 * nl + 1] *= S1;
-        if (end_thread) {                         // the shard's end column 3 n_end / 2 n_end
-            double gme = sm.om[e][3 * nl + 3], gse = sm.os[e][2 * nl + 2];
-            if (last_shard && jo >= 0) {          // observation M-1 sits on it, M three columns on
-                const double rr = y1 - P3;
-                gme -= Ri * rr;
-                gse += 0.5 * Ri;
-                acc[2] += Ri * (rr * rr + S2);
-                const double r2 = y2 - mT;
-                sm.om[e][3 * nl + 6] = -Ri * r2;
-                sm.os[e][2 * nl + 4] = 0.5 * Ri * sT;
-                acc[2] += Ri * (r2 * r2 + sT);
-            }
-            sm.om[e][3 * nl + 3] = gme;
-            sm.os[e][2 * nl + 2] = gse * S2;
-        }
-    }
-    __syncthreads();
-
-    // ---- coalesced copy-out: one warp per row, lanes along the columns -------------------
-    if (want_grad) {
-        const int lane = tid & 31, w = tid >> 5;
-        const int rows = min(TD, D - d0);
-        for (int r = w; r < rows; r += NW) {
-            const int row = r + 3, jj = sm.jrow[row];
-            if (lane < ncm) f.gm[(int64_t)jj * f.Nm + 3 * n0 + lane] = sm.om[row][lane];
-            if (lane < ncs) f.gs[(int64_t)jj * f.Ns + 2 * n0 + lane] = sm.os[row][lane];
-        }
-    }
-    {
-        const int lane = tid & 31, w = tid >> 5;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double v = warp_sum(acc[i]);
-            if (lane == 0) sm.red2[i][w] = v;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double *p = f.apart + (int64_t)blockIdx.x * 4;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double v = sm.red2[i][0];
-                for (int w2 = 1; w2 < NW; ++w2) v += sm.red2[i][w2];
-                p[i] = v;
-            }
-            p[3] = 0.0;
-        }
-    }
-}
-
-// adds the edge buffers (last interval of tile t-1) into the first column of tile t
-struct FixupArgs {
-    const double *x;             // for the chain rule: s = exp(log-variance)
-    double *gm, *gs;
-    const double *edge_m, *edge_s;
-    int D, Nm, Ns, n_begin, ntn, TN;
-};
-
-__global__ void __launch_bounds__(256)
-edge_fixup_kernel(const FixupArgs a) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y + 1;                     // tile receiving the edge of tile t-1
-    if (j >= a.D || t >= a.ntn) return;
-    const int n0 = a.n_begin + t * a.TN;
-    const int64_t im = (int64_t)j * a.Nm + 3 * n0, is = (int64_t)j * a.Ns + 2 * n0;
-    a.gm[im] += a.edge_m[(int64_t)(t - 1) * a.D + j];
-    const double s = exp(a.x[(int64_t)a.D * a.Nm + is]);
-    a.gs[is] += a.edge_s[(int64_t)(t - 1) * a.D + j] * s;
-}
-
-// ---------------------------------------------------------------------------
 // DW / OU / L63 (D <= 3): one CTA per interval, one thread per quadrature
 // node; each thread evaluates all dimensions at its node, the 42 node values
 // are then summed in scipy's order (panel 1 then panel 2, r = 0..20).

@@ -54,8 +54,8 @@ struct mfvgp_handle {
     int tail_grid = 1;
     double theta_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int rule = 1;     // 1: split rule (default), 0: 42-node coupled rule (MFVGP_RULE=gk42)
-    // fused E_cost kernel (L96, split rule): TE x TN tile, grid = fntn * fntiles
-    // (fused = 2: walk kernel, l96_walk.cuh -- a CTA walks along ftn consecutive intervals)
+    // walk kernel (l96_walk.cuh; fused = 2): dim tile fte, ftn consecutive intervals per run,
+    // grid = fntn runs x fntiles tiles.  fused = 0: split / coop kernels with a workspace
     int fte = 64, ftn = 1, fntiles = 1, fntn = 1, fused = 0;
     double *fedge_m = nullptr, *fedge_s = nullptr, *fapart = nullptr;
     bool have_sde = false, have_prior = false, have_obs = false;
@@ -132,7 +132,6 @@ extern "C" int mfvgp_describe(const mfvgp_handle *h, char *buf, int buflen) {
     if (h->system == MFVGP_SYS_L96) {
         if (h->rule == 0) { path = "gk42"; kern = "esde_l96_kernel"; te = h->te; nt = h->ntiles; }
         else if (h->fused == 2) { path = "walk"; kern = "esde_l96_walk_kernel"; te = h->fte; tn = h->ftn; nt = h->fntiles; nr = h->fntn; }
-        else if (h->fused == 1) { path = "fused"; kern = "esde_l96_fused_kernel"; te = h->fte; tn = h->ftn; nt = h->fntiles; nr = h->fntn; }
         else if (h->coop) { path = "coop"; kern = "esde_l96_coop_kernel"; te = h->te; nt = h->ntiles; }
         else { path = "split"; kern = "esde_l96_split_kernel"; te = h->te; nt = h->ntiles; }
     }
@@ -177,18 +176,16 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         h->ntiles = (D + h->te - 7) / (h->te - 6);
     }
     const int nl = n_end - n_begin;
-    // E_cost path for L96 (MFVGP_PATH=split|fused|walk; MFVGP_FUSE=1 = fused):
-    //   split: esde_l96_split_kernel + assemble_kernel   (default for small problems)
-    //   walk : esde_l96_walk_kernel, gradient written directly (default for large ones)
-    //   fused: esde_l96_fused_kernel (round-1 experiment, kept for comparison)
+    // E_cost path for L96 (MFVGP_PATH=split|walk):
+    //   split: esde_l96_coop_kernel (or esde_l96_split_kernel) + workspace + assembly (small)
+    //   walk : esde_l96_walk_kernel, gradient written directly (default for large problems)
     const char *path_env = getenv("MFVGP_PATH");
-    const char *fuse_env = getenv("MFVGP_FUSE");
     const char *rule_env = getenv("MFVGP_RULE");
     h->rule = (rule_env && std::string(rule_env) == "gk42") ? 0 : 1;
     if (system == MFVGP_SYS_L96 && h->rule == 1) {
-        std::string path = path_env ? path_env : (fuse_env && fuse_env[0] == '1' ? "fused" : "");
-        if (path.empty()) path = cells > 148 * 512 ? "walk" : "split";
-        h->fused = path == "walk" ? 2 : (path == "fused" ? 1 : 0);
+        std::string path = path_env ? path_env : "";
+        if (path != "walk" && path != "split") path = cells > 148 * 512 ? "walk" : "split";
+        h->fused = path == "walk" ? 2 : 0;
     }
     if (system == MFVGP_SYS_L96 && h->rule == 1 && h->fused == 0 && cells <= 148 * 512) {
         const char *coop_env = getenv("MFVGP_COOP");
@@ -220,15 +217,10 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
             const int64_t target = 148LL * (512 / h->fte) * 8;       // ~8 waves of resident CTAs
             int64_t tn = (int64_t)nl * nt / target;
             h->ftn = (int)(tn < 1 ? 1 : (tn > 32 ? 32 : tn));
-        } else {
-            h->fte = D <= 26 ? 32 : 64;
-            h->ftn = (h->fte == 64 && cells > 148 * 512) ? 4 : 1;
-        }
-        if (const char *ft = getenv("MFVGP_FTILE")) {       // experiments: "TE,TN"
-            int te = 0, tn = 0;
-            if (sscanf(ft, "%d,%d", &te, &tn) == 2) { h->fte = te; h->ftn = tn; }
-        }
-        if (h->fused == 2) {
+            if (const char *ft = getenv("MFVGP_FTILE")) {   // experiments: "TE,TN"
+                int te = 0, tn = 0;
+                if (sscanf(ft, "%d,%d", &te, &tn) == 2) { h->fte = te; h->ftn = tn; }
+            }
             ARG(h->fte == 32 || h->fte == 64 || h->fte == 128, "MFVGP_FTILE: walk TE must be 32|64|128");
             ARG(h->ftn >= 1 && h->ftn <= kWalkMaxTN, "MFVGP_FTILE: walk TN must be 1..64");
         }
@@ -512,22 +504,6 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
     return launch_guard_refine(h, mean, ldm, vars, lds, log_vars, ds, h->ntiles, 0, st);
 }
 
-template <int TE, int TN>
-static int launch_fused_kernel(const EsdeArgs &a, const FusedArgs &f, unsigned grid,
-                               cudaStream_t st) {
-    static uint64_t configured = 0;                 // one bit per device (attribute is per device)
-    const size_t smem = sizeof(FusedSmem<TE, TN>);
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    if (!(configured >> (dev & 63) & 1)) {
-        CK(cudaFuncSetAttribute(esde_l96_fused_kernel<TE, TN>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured |= 1ull << (dev & 63);
-    }
-    esde_l96_fused_kernel<TE, TN><<<grid, dim3(TE, TN), smem, st>>>(a, f);
-    return MFVGP_OK;
-}
-
 template <int TE>
 static int launch_walk_kernel(const WalkArgs &w, unsigned grid, cudaStream_t st) {
     static uint64_t configured = 0;                 // one bit per device (attribute is per device)
@@ -543,21 +519,10 @@ static int launch_walk_kernel(const WalkArgs &w, unsigned grid, cudaStream_t st)
     return MFVGP_OK;
 }
 
-// L96, split rule: E_cost in one main kernel (esde_l96_fused_kernel) + small follow-ups
-static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStream_t st) {
+// L96 walk path: E_cost in one main kernel (l96_walk.cuh) + guard / adaptive path follow-ups
+static int launch_walk(mfvgp_handle *h, const double *x, double *grad, cudaStream_t st) {
     const double *lvar = x + (int64_t)h->D * h->Nm;
-    EsdeArgs a;
-    a.mean = x; a.vars = lvar; a.ldm = h->Nm; a.lds = h->Ns;
-    a.obs_times = h->obs_times; a.sigma = h->sigma; a.theta = h->theta;
-    a.dm_out = nullptr; a.ds_out = nullptr; a.part = h->part;
-    a.D = h->D; a.n_begin = h->n_begin; a.n_end = h->n_end; a.ntiles = h->fntiles;
-    a.log_vars = 1;
-    FusedArgs f;
-    f.gm = grad; f.gs = grad ? grad + (int64_t)h->D * h->Nm : nullptr;
-    f.mu0 = h->mu0; f.tau0 = h->tau0; f.obs_values = h->obs_values; f.obs_noise = h->obs_noise;
-    f.obs_idx = h->obs_idx; f.edge_m = h->fedge_m; f.edge_s = h->fedge_s; f.apart = h->fapart;
-    f.M = h->M; f.d = h->d; f.Nm = h->Nm; f.Ns = h->Ns; f.L = h->L; f.ntn = h->fntn;
-    f.with_e0 = h->n_begin == 0;
+    double *gs = grad ? grad + (int64_t)h->D * h->Nm : nullptr;
     const unsigned grid = (unsigned)h->fntn * h->fntiles;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (h->timing) {
@@ -565,37 +530,22 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
         CK(cudaEventCreate(&ev1));
         CK(cudaEventRecord(ev0, st));
     }
-    int rc = MFVGP_OK;
-    if (h->fused == 2) {
-        WalkArgs w;
-        w.x = x; w.obs_times = h->obs_times; w.sigma = h->sigma; w.theta = h->theta_host[0];
-        w.mu0 = h->mu0; w.tau0 = h->tau0; w.obs_values = h->obs_values;
-        w.obs_noise = h->obs_noise; w.obs_idx = h->obs_idx;
-        w.gm = f.gm; w.gs = f.gs; w.head_m = h->fedge_m; w.head_s = h->fedge_s;
-        w.head_flag = h->head_flag; w.run_ticket = h->tickets + h->L + 2;
-        w.status = h->refine_status; w.epoch = ++h->walk_epoch;
-        w.part = h->part; w.apart = h->fapart;
-        w.D = h->D; w.M = h->M; w.d = h->d; w.Nm = h->Nm; w.Ns = h->Ns; w.L = h->L;
-        w.n_begin = h->n_begin; w.n_end = h->n_end;
-        w.ntiles = h->fntiles; w.nruns = h->fntn; w.TN = h->ftn;
-        w.with_e0 = h->n_begin == 0;
-        if (h->fte == 32) rc = launch_walk_kernel<32>(w, grid, st);
-        else if (h->fte == 64) rc = launch_walk_kernel<64>(w, grid, st);
-        else rc = launch_walk_kernel<128>(w, grid, st);
-    } else {
-    const int key = h->fte * 100 + h->ftn;
-    switch (key) {
-        case 3201: rc = launch_fused_kernel<32, 1>(a, f, grid, st); break;
-        case 3204: rc = launch_fused_kernel<32, 4>(a, f, grid, st); break;
-        case 3208: rc = launch_fused_kernel<32, 8>(a, f, grid, st); break;
-        case 6401: rc = launch_fused_kernel<64, 1>(a, f, grid, st); break;
-        case 6402: rc = launch_fused_kernel<64, 2>(a, f, grid, st); break;
-        case 6404: rc = launch_fused_kernel<64, 4>(a, f, grid, st); break;
-        case 12801: rc = launch_fused_kernel<128, 1>(a, f, grid, st); break;
-        case 12802: rc = launch_fused_kernel<128, 2>(a, f, grid, st); break;
-        default: g_err = "unsupported fused tile"; return MFVGP_ERR_ARG;
-    }
-    }
+    WalkArgs w;
+    w.x = x; w.obs_times = h->obs_times; w.sigma = h->sigma; w.theta = h->theta_host[0];
+    w.mu0 = h->mu0; w.tau0 = h->tau0; w.obs_values = h->obs_values;
+    w.obs_noise = h->obs_noise; w.obs_idx = h->obs_idx;
+    w.gm = grad; w.gs = gs; w.head_m = h->fedge_m; w.head_s = h->fedge_s;
+    w.head_flag = h->head_flag; w.run_ticket = h->tickets + h->L + 2;
+    w.status = h->refine_status; w.epoch = ++h->walk_epoch;
+    w.part = h->part; w.apart = h->fapart;
+    w.D = h->D; w.M = h->M; w.d = h->d; w.Nm = h->Nm; w.Ns = h->Ns; w.L = h->L;
+    w.n_begin = h->n_begin; w.n_end = h->n_end;
+    w.ntiles = h->fntiles; w.nruns = h->fntn; w.TN = h->ftn;
+    w.with_e0 = h->n_begin == 0;
+    int rc;
+    if (h->fte == 32) rc = launch_walk_kernel<32>(w, grid, st);
+    else if (h->fte == 64) rc = launch_walk_kernel<64>(w, grid, st);
+    else rc = launch_walk_kernel<128>(w, grid, st);
     if (rc) return rc;
     h->launches++;
     CK(cudaGetLastError());
@@ -608,17 +558,9 @@ static int launch_fused(mfvgp_handle *h, const double *x, double *grad, cudaStre
                              h->fntiles, 1, st);
     if (rc) return rc;
     if (grad != nullptr) {
-        if (h->fntn > 1 && h->fused != 2) {       // the walk kernel stitches its runs itself
-            FixupArgs fx;
-            fx.x = x; fx.gm = f.gm; fx.gs = f.gs; fx.edge_m = h->fedge_m; fx.edge_s = h->fedge_s;
-            fx.D = h->D; fx.Nm = h->Nm; fx.Ns = h->Ns; fx.n_begin = h->n_begin; fx.ntn = h->fntn;
-            fx.TN = h->ftn;
-            edge_fixup_kernel<<<dim3((h->D + 255) / 256, h->fntn - 1), 256, 0, st>>>(fx);
-            h->launches++;
-            CK(cudaGetLastError());
-        }
         ApplyRefineArgs ar;
-        ar.flags = h->flags; ar.nflagged = h->refine_status + 1; ar.delta = h->ds_ws; ar.x = x; ar.gs = f.gs;
+        ar.flags = h->flags; ar.nflagged = h->refine_status + 1; ar.delta = h->ds_ws; ar.x = x;
+        ar.gs = gs;
         ar.D = h->D; ar.Nm = h->Nm; ar.Ns = h->Ns; ar.n_begin = h->n_begin; ar.n_end = h->n_end;
         apply_refine_kernel<<<h->n_end - h->n_begin + 1, 256, 0, st>>>(ar);
         h->launches++;
@@ -788,7 +730,7 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
     const double *lvar = x_d + (int64_t)h->D * h->Nm;
     int rc;
     if (h->fused) {
-        rc = launch_fused(h, x_d, want_grad ? grad_d : nullptr, st);
+        rc = launch_walk(h, x_d, want_grad ? grad_d : nullptr, st);
         if (rc) return rc;
         if (h->world > 1 && want_grad && !h->one_collective) {
             rc = exchange_edges(h, grad_d, st);

@@ -186,17 +186,6 @@ def _check_path_equals_split(path, D, M, rough, monkeypatch, ftile=None):
         assert abs(F1 - Fo) <= RTOL * abs(Fo) and rel_err(g1, go) <= RTOL
 
 
-@pytest.mark.parametrize("D,M,rough", [(40, 7, False), (67, 12, True), (300, 300, False),
-                                       (300, 290, True), (64, 1500, True)])
-def test_fused_ecost_equals_unfused(D, M, rough, monkeypatch):
-    """
-    The fused kernel (MFVGP_PATH=fused: esde_l96_fused_kernel + edge fix-up + refine
-    deltas) against the split kernel + assemble_kernel, which the golden tests pin to
-    the reference.  `rough` makes some variance triples steep so intervals get refined.
-    """
-    _check_path_equals_split("fused", D, M, rough, monkeypatch)
-
-
 @pytest.mark.parametrize("D,M,rough,ftile", [
     (4, 2, False, None), (5, 3, False, "32,1"), (26, 9, False, "32,3"), (27, 5, True, None),
     (40, 7, False, "64,2"), (67, 12, True, "64,5"), (123, 40, True, "128,7"),
