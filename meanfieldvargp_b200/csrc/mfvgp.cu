@@ -172,7 +172,7 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     h->Nm = 3 * M + 4; h->Ns = 2 * M + 3;
     const int64_t cells = (int64_t)D * (n_end - n_begin);
     if (system == MFVGP_SYS_L96) {
-        h->te = D <= 26 ? 32 : (cells <= 148 * 512 ? 64 : 128);
+        h->te = D <= 26 ? 32 : (cells <= 148 * 256 ? 64 : 128);
         h->ntiles = (D + h->te - 7) / (h->te - 6);
     }
     const int nl = n_end - n_begin;
@@ -182,12 +182,16 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     const char *path_env = getenv("MFVGP_PATH");
     const char *rule_env = getenv("MFVGP_RULE");
     h->rule = (rule_env && std::string(rule_env) == "gk42") ? 0 : 1;
+    // measured crossover (L96, one B200): up to ~40 k (dimension, interval) cells the
+    // latency-oriented kernels of l96_coop.cuh win, above that the walk kernel
+    int64_t small_cells = 148 * 256;
+    if (const char *e = getenv("MFVGP_SMALL_CELLS")) small_cells = atoll(e);
     if (system == MFVGP_SYS_L96 && h->rule == 1) {
         std::string path = path_env ? path_env : "";
-        if (path != "walk" && path != "split") path = cells > 148 * 512 ? "walk" : "split";
+        if (path != "walk" && path != "split") path = cells > small_cells ? "walk" : "split";
         h->fused = path == "walk" ? 2 : 0;
     }
-    if (system == MFVGP_SYS_L96 && h->rule == 1 && h->fused == 0 && cells <= 148 * 512) {
+    if (system == MFVGP_SYS_L96 && h->rule == 1 && h->fused == 0 && cells <= small_cells) {
         const char *coop_env = getenv("MFVGP_COOP");
         h->coop = (coop_env && coop_env[0] == '0') ? 0 : 1;
         if (h->coop) {
@@ -214,9 +218,15 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
             }
             h->fte = best;
             const int nt = (D + h->fte - 7) / (h->fte - 6);
-            const int64_t target = 148LL * (512 / h->fte) * 8;       // ~8 waves of resident CTAs
-            int64_t tn = (int64_t)nl * nt / target;
-            h->ftn = (int)(tn < 1 ? 1 : (tn > 32 ? 32 : tn));
+            // intervals per run TN: every run pays a prologue (un-prefetched loads, three exp, a
+            // mailbox hand-over) ~ 0.4 interval, so cost ~ 0.4/TN; fewer, longer CTAs lose
+            // ~ half a wave at the end, cost ~ 0.5 TN R / (nl nt) with R resident CTAs.  The
+            // minimum is at TN = sqrt(0.8 nl nt / R); never below 2.  (Measured, us: D=4000
+            // L=250 167 at TN=1, 120 at 4; D=8192 L=512 463 at 7, 488 at 23; L=4096 flat 16..32.)
+            const double resident = 148.0 * (512 / h->fte);
+            const int tn = (int)lround(sqrt(0.8 * (double)nl * nt / resident));
+            h->ftn = tn < 2 ? 2 : (tn > 32 ? 32 : tn);
+            if (h->ftn > nl) h->ftn = nl;
             if (const char *ft = getenv("MFVGP_FTILE")) {   // experiments: "TE,TN"
                 int te = 0, tn = 0;
                 if (sscanf(ft, "%d,%d", &te, &tn) == 2) { h->fte = te; h->ftn = tn; }
