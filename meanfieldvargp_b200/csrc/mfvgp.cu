@@ -210,6 +210,9 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     if (system == MFVGP_SYS_L96) {
         if (h->fused == 2) {
             // dim tile: the TE in {32, 64, 128} that wastes the fewest threads on halo / padding
+            // (TE=64 measures 1.5 % faster in the main kernel at D=8192 but doubles the tile
+            // partials the guard / final kernels read: a wash end to end; 96 and 160 -- 3 / 5
+            // warps over 4 schedulers -- are 8-20 % slower)
             int best = 128;
             int64_t best_thr = (int64_t)((D + 121) / 122) * 128;
             for (int te : {64, 32}) {
