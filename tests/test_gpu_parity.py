@@ -238,3 +238,43 @@ def test_walk_matches_reference_golden(name, monkeypatch):
     assert rel_err(grad, g["grad"]) <= RTOL
     for k in ("E0", "Esde", "Eobs"):
         assert abs(fe.last_terms[k] - g[k]) <= RTOL * abs(g["F"])
+
+
+def test_integration_stub_of_the_docs():
+    """
+    INTEGRATION.md section 3: the few lines of ctypes a maintainer of the reference would add
+    (mfvgp_create / set_* / mfvgp_ecost_host on plain numpy buffers) -- exercised verbatim.
+    """
+    import ctypes
+    from meanfieldvargp_b200 import _lib
+    g = load_golden("eval", "L96_40")
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    P = ctypes.c_void_p
+    D, M = g["sigma"].size, len(g["obs_times"])
+    h = P()
+    assert lib.mfvgp_create(ctypes.byref(h), 3, D, M, D, 0, 0, -1) == 0
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)          # noqa: E731
+    s, t = f64(g["sigma"]), f64(g["theta"])
+    assert lib.mfvgp_set_sde(h, P(s.ctypes.data), P(t.ctypes.data), t.size) == 0
+    mu0, tau0 = f64(np.broadcast_to(g["mu0"], (D,))), f64(np.broadcast_to(g["tau0"], (D,)))
+    assert lib.mfvgp_set_prior(h, P(mu0.ctypes.data), P(tau0.ctypes.data)) == 0
+    ot, ov = f64(g["obs_times"]), f64(g["obs_values"]).reshape(M, D)
+    on = f64(np.broadcast_to(g["obs_noise"], (D,)))
+    assert lib.mfvgp_set_obs(h, P(ot.ctypes.data), P(ov.ctypes.data), P(on.ctypes.data), None) == 0
+    x = f64(g["x0"])
+    out, grad, st = np.empty(4), np.empty_like(x), ctypes.c_int32()
+    rc = lib.mfvgp_ecost_host(h, P(x.ctypes.data), 1, P(out.ctypes.data), P(grad.ctypes.data),
+                              ctypes.byref(st))
+    assert rc == 0 and (st.value & 7) == 0
+    assert abs(out[0] - g["F"]) <= RTOL * abs(g["F"]) and rel_err(grad, g["grad"]) <= RTOL
+    # value only: the gradient buffer may be NULL
+    rc = lib.mfvgp_ecost_host(h, P(x.ctypes.data), 0, P(out.ctypes.data), None, ctypes.byref(st))
+    assert rc == 0 and abs(out[0] - g["F"]) <= RTOL * abs(g["F"])
+    # calls in the wrong order fail with a message instead of computing garbage
+    h2 = P()
+    assert lib.mfvgp_create(ctypes.byref(h2), 3, D, M, D, 0, 0, -1) == 0
+    assert lib.mfvgp_ecost_host(h2, P(x.ctypes.data), 0, P(out.ctypes.data), None,
+                                ctypes.byref(st)) == -3
+    lib.mfvgp_last_error.restype = ctypes.c_char_p
+    assert b"not called" in lib.mfvgp_last_error()
+    assert lib.mfvgp_destroy(h) == 0 and lib.mfvgp_destroy(h2) == 0
