@@ -15,10 +15,14 @@ M=16 observation times (examples/example_500D.ipynb), synthetic state
   roofline   the dominant kernel (esde_l96_kernel) against the FP64 pipe
              (DFMA micro-benchmark measured in this run) and HBM
   cpu_baseline  the numpy/scipy oracle port on the host cores (bounded sample)
+  c_abi_back_to_back  mfvgp_ecost on device pointers in a loop, no flush (what SCG sees)
   scg        device SCG iterations per second on the same configuration
   large      Lorenz '96 D=8192, M=4097 (L=4096 intervals) long horizon: at
              N ranks the intervals are sharded (strong scaling); this is the
              configuration on which the roofline fraction is meaningful.
+  next_posterior / next_trajectory  the rows of SURVEY.md 8(f) built so far:
+             posterior reconstruction (HBM roofline) and the bit-identical
+             Lorenz 96 sample path (latency bound), each with its CPU port timed.
 
 With N > 1 (torchrun, one rank per GPU) the D=500 evaluation is far below one
 wave of one GPU, so it does not shard: ``value`` is N independent replicas
