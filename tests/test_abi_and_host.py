@@ -99,3 +99,33 @@ def test_shard_intervals_partition():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_reference_objects_are_accepted_by_name():
+    """
+    The drop-in takes the reference's own DoubleWell / OrnsteinUhlenbeck / Lorenz63 / Lorenz96
+    instances (selected by class name, theta / sigma read through their accessors); anything
+    else is refused loudly -- there is no silent fallback.  Live check where /root/reference
+    exists (this container); the name table is checked everywhere.
+    """
+    import meanfieldvargp_b200 as mf
+    from meanfieldvargp_b200.systems import system_of
+
+    class Lorenz96(object):                      # a foreign class with the reference's name
+        theta, sigma = np.array(8.0), 40.0 * np.ones(5)
+    assert system_of(Lorenz96()) == "L96"
+
+    class Brusselator(object):
+        theta, sigma = np.array(1.0), np.ones(2)
+    with pytest.raises(NotImplementedError, match="no CUDA drift plug-in"):
+        system_of(Brusselator())
+
+    from oracle.ref_harness import harness
+    if not harness.available():
+        pytest.skip("reference not present (GPU box)")
+    cls = harness.reference_classes()
+    ref = cls["Lorenz96"](40.0, 8.0, dim_D=6, r_seed=1)
+    assert system_of(ref) == "L96" and np.allclose(ref.sigma, 40.0) and float(ref.theta) == 8.0
+    assert system_of(cls["DoubleWell"](0.8, 1.0, r_seed=1)) == "DW"
+    assert system_of(cls["Lorenz63"]([40, 40, 40], [10, 28, 2.66667], 1)) == "L63"
+    assert system_of(cls["OrnsteinUhlenbeck"](1.0, [2.0, 0.5], r_seed=1)) == "OU"
