@@ -710,6 +710,8 @@ struct FinalArgs {
     int32_t *status;          // [1]
     int32_t *refine_status;   // [1] bits set by refine_kernel, consumed here
     int32_t *nflagged;        // [1] GuardArgs::nflagged, reset here (or nullptr)
+    unsigned *gbar;           // refine_kernel's group counters, zeroed here for the next evaluation
+    int ngbar;
     int record9;              // out has 9 slots (multi-GPU record)
     int n_begin, n_end, D;    // D = number of apart rows (state dims, or CTAs of the fused kernel)
     int with_e0;
@@ -758,7 +760,11 @@ __device__ __forceinline__ void final_body(const FinalArgs &a) {
         if (sh_flag) st |= 8;
         st |= a.refine_status[0];
         a.refine_status[0] = 0;
-        if (a.nflagged != nullptr) a.nflagged[0] = 0;
+        if (a.nflagged != nullptr) {
+            if (a.nflagged[0] != 0)
+                for (int i = 0; i < a.ngbar; ++i) a.gbar[i] = 0u;
+            a.nflagged[0] = 0;
+        }
         // record[0..3] = F, E0, Esde, Eobs; record[4..8] = status bits as 0/1 so
         // that shards can be combined by summation (combine_record_kernel)
         a.out[0] = E0 + Esde + Eobs;

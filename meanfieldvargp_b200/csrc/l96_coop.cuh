@@ -267,8 +267,9 @@ esde_l96_coop_kernel(const CoopArgs ca) {
         if (f) {
             double *ws = ca.r.ws + (int64_t)(n - a.n_begin) * 2 * D * kMaxNE;
             double *ws_fixed = ws + (int64_t)D * kMaxNE;
-            if (f & 1) refine_item<3, true, kCoopNT>(ca.r, n, ws, ws_fixed);
-            if ((f & 2) && ca.r.want_grad) refine_item<3, false, kCoopNT>(ca.r, n, ws, ws_fixed);
+            GroupCtx gc{1, 0, nullptr, nullptr, 0u, ca.r.status};
+            if (f & 1) refine_item<3, true, kCoopNT>(ca.r, n, ws, ws_fixed, gc);
+            if ((f & 2) && ca.r.want_grad) refine_item<3, false, kCoopNT>(ca.r, n, ws, ws_fixed, gc);
         }
     }
 }
@@ -305,8 +306,9 @@ esde_small_inkernel(const SmallArgs sa) {
     if (tid == 0) sa.c.r.info[2 * n + y] = 0;
     double *ws = sa.c.r.ws + ((int64_t)(n - a.n_begin) * 2 + y) * 2 * a.D * kMaxNE;
     double *ws_fixed = ws + (int64_t)a.D * kMaxNE;
-    if (y == 0 && (f & 1)) refine_item<SYS, true, 64>(sa.c.r, n, ws, ws_fixed);
-    if (y == 1 && (f & 2) && sa.c.r.want_grad) refine_item<SYS, false, 64>(sa.c.r, n, ws, ws_fixed);
+    GroupCtx gc{1, 0, nullptr, nullptr, 0u, sa.c.r.status};
+    if (y == 0 && (f & 1)) refine_item<SYS, true, 64>(sa.c.r, n, ws, ws_fixed, gc);
+    if (y == 1 && (f & 2) && sa.c.r.want_grad) refine_item<SYS, false, 64>(sa.c.r, n, ws, ws_fixed, gc);
 }
 
 // ---------------------------------------------------------------------------

@@ -71,7 +71,9 @@ struct mfvgp_handle {
     // adaptive refinement (refine.cuh)
     double *refine_ws = nullptr;
     int32_t *refine_info = nullptr, *refine_status = nullptr;   // refine_status[1] = flagged count
-    int refine_grid = 1;
+    int refine_grid = 1, refine_group = 1;      // CTAs per flagged item (refine.cuh GroupCtx)
+    double *refine_gpart = nullptr;
+    unsigned *refine_gbar = nullptr;
     // host-API staging
     double *x_dev = nullptr, *grad_dev = nullptr;
     double *pin = nullptr;   // pinned: out[4] + status
@@ -282,11 +284,24 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         dev_alloc(&h->esde_n, L) || dev_alloc(&h->apart, (size_t)(D > h->tail_grid ? D : h->tail_grid) * 4) ||
         dev_alloc(&h->out_ws, 16) || dev_alloc(&h->rec_ws, 16))
         return MFVGP_ERR_CUDA;
-    h->refine_grid = 2 * nl < 296 ? 2 * nl : 296;
-    {   // scratch of the adaptive path: one slot per refine CTA, or per interval (coop path)
-        const int need = system == MFVGP_SYS_L96 ? nl : 2 * nl;      // in-kernel adaptive path
-        const int slots = h->coop && need > h->refine_grid ? need : h->refine_grid;
+    // adaptive path: groups of G co-resident CTAs share a flagged item; 252 registers x 128
+    // threads => two CTAs per SM, so at most 296 CTAs in all
+    h->refine_group = D >= 8192 ? 16 : (D >= 4096 ? 8 : (D >= 2048 ? 4 : (D >= 1024 ? 2 : 1)));
+    if (const char *e = getenv("MFVGP_REFINE_GROUP")) {
+        const int gsz = atoi(e);
+        if (gsz >= 1 && gsz <= 64) h->refine_group = gsz;
+    }
+    {
+        int groups = 296 / h->refine_group;
+        if (groups > 2 * nl) groups = 2 * nl;
+        h->refine_grid = groups * h->refine_group;
+        // scratch of the adaptive path: one slot per group, or per interval (in-kernel callers)
+        const int need = system == MFVGP_SYS_L96 ? nl : 2 * nl;
+        const int slots = h->coop && need > groups ? need : groups;
         if (dev_alloc(&h->refine_ws, (size_t)slots * 2 * D * kMaxNE)) return MFVGP_ERR_CUDA;
+        if (dev_alloc(&h->refine_gpart, (size_t)groups * 2 * h->refine_group * 8)) return MFVGP_ERR_CUDA;
+        CK(cudaMalloc((void **)&h->refine_gbar, (size_t)groups * sizeof(unsigned)));
+        CK(cudaMemset(h->refine_gbar, 0, (size_t)groups * sizeof(unsigned)));
     }
     if (h->coop && (dev_alloc(&h->y_dense, (size_t)M * D) || dev_alloc(&h->rinv_row, D)))
         return MFVGP_ERR_CUDA;
@@ -322,7 +337,8 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal,
                     h->refine_ws, h->refine_info, h->refine_status, h->edge_send, h->edge_recv,
                     h->gather, h->xchg_send, h->xchg_gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
-                    h->y_dense, h->rinv_row, h->esde_n2, h->flags2, h->head_flag};
+                    h->y_dense, h->rinv_row, h->esde_n2, h->flags2, h->head_flag, h->refine_gpart,
+                    h->refine_gbar};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
@@ -419,6 +435,7 @@ static RefineArgs refine_args(mfvgp_handle *h, const double *mean, int64_t ldm, 
     r.obs_times = h->obs_times; r.sigma = h->sigma; r.theta = h->theta;
     r.flags = h->flags; r.esde_n = h->esde_n; r.ds_out = ds; r.ws = h->refine_ws;
     r.nflagged = h->coop ? nullptr : h->refine_status + 1;
+    r.group = h->refine_group; r.gpart = h->refine_gpart; r.gbar = h->refine_gbar;
     r.delta_mode = delta_mode;
     r.info = h->refine_info; r.status = h->refine_status;
     r.D = h->D; r.n_begin = h->n_begin; r.n_end = h->n_end; r.log_vars = log_vars;
@@ -612,6 +629,7 @@ static int launch_final(mfvgp_handle *h, const double *apart, int napart, double
     f.out = multi ? h->rec_ws : out; f.status = status;
     f.refine_status = h->refine_status;
     f.nflagged = h->coop ? nullptr : h->refine_status + 1;
+    f.gbar = h->refine_gbar; f.ngbar = h->refine_grid / h->refine_group;
     f.record9 = multi ? 1 : 0;
     f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = napart;
     f.with_e0 = h->n_begin == 0;
@@ -769,7 +787,7 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
         const int nb = h->tail_grid;
         t.f.esde_n = h->esde_n; t.f.flags = h->flags; t.f.apart = h->apart;
         t.f.out = out_d; t.f.status = status_d; t.f.refine_status = h->refine_status;
-        t.f.nflagged = nullptr;
+        t.f.nflagged = nullptr; t.f.gbar = nullptr; t.f.ngbar = 0;
         t.f.record9 = 0; t.f.n_begin = h->n_begin; t.f.n_end = h->n_end; t.f.D = nb;
         t.f.with_e0 = 1; t.f.eobs_const = h->eobs_const;
         t.ticket = h->tickets + h->L + 1;

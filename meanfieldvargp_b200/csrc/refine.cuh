@@ -49,6 +49,9 @@ struct RefineArgs {
     int32_t *info;             // [L][2] number of bisections done (0 = not refined)
     int32_t *status;           // OR-ed MFVGP_ST_REFINE_LIMIT
     int D, n_begin, n_end, log_vars, want_grad;
+    int group;                 // CTAs per item in refine_kernel (GroupCtx)
+    double *gpart;             // [groups][2][group][8]
+    unsigned *gbar;            // [groups] arrival counters, zero at kernel start
 };
 
 __device__ __forceinline__ void basis3(double tau, double *B, double *dB) {
@@ -174,6 +177,58 @@ template <> struct RowEval<0> : RowEvalDense<0> {};
 template <> struct RowEval<1> : RowEvalDense<1> {};
 template <> struct RowEval<2> : RowEvalDense<2> {};
 
+// A flagged (interval, integrand) item may be shared by a GROUP of G co-resident CTAs
+// (refine_kernel at large D: one CTA would walk 8192 rows alone for milliseconds).  The rows
+// are dealt round-robin over the group's threads; every reduction of the scalar control loop
+// goes through global memory -- each CTA's partial, a group barrier, then every CTA folds the
+// G partials in rank order -- so all CTAs see identical scalars and run quad_vec's heap logic
+// redundantly, in lock step, with no leader.  G = 1 (the in-kernel callers) costs nothing.
+struct GroupCtx {
+    int G, rank;               // CTAs in the group, this CTA's rank
+    double *part;              // [2][G][8] partial sums (double buffered by the barrier count)
+    unsigned *bar;             // monotone arrival counter of the group (0 at kernel start)
+    unsigned seq;              // barriers this CTA has passed
+    int32_t *status;           // OR-ed 32 if a barrier wait gives up
+};
+
+__device__ __forceinline__ void group_barrier(GroupCtx &gc) {
+    __syncthreads();
+    if (gc.G > 1) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(gc.bar, 1u);
+            const unsigned target = (gc.seq + 1u) * (unsigned)gc.G;
+            long spin = 0;
+            while (*((volatile unsigned *)gc.bar) < target) {
+                __nanosleep(40);
+                if (++spin > (1L << 25)) { atomicOr(gc.status, 32); break; }   // never expected
+            }
+            __threadfence();
+        }
+        gc.seq++;
+        __syncthreads();
+    }
+}
+
+// block_sum over the group: result valid in thread 0 of EVERY CTA of the group
+template <int NV, int NT>
+__device__ __forceinline__ void group_sum(double (&v)[NV], double *sh, GroupCtx &gc) {
+    block_sum<NV, NT>(v, sh);
+    if (gc.G == 1) return;
+    double *slot = gc.part + (int64_t)(gc.seq & 1u) * gc.G * 8;
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) slot[gc.rank * 8 + i] = v[i];
+    group_barrier(gc);
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double t = __ldcg(slot + i);
+            for (int r = 1; r < gc.G; ++r) t += __ldcg(slot + r * 8 + i);
+            v[i] = t;
+        }
+}
+
 // _quadrature_gk on [pa, pb] (local coordinates) for one row, NE elements.
 // integ[e] = h*s_k ; acc[0..2] += squared contributions to the three norms.
 template <int SYS, int NE, bool ENERGY>
@@ -232,7 +287,8 @@ __device__ __forceinline__ void gk_error(double n_kg2, double n_dabs2, double n_
 }
 
 template <int SYS, bool ENERGY, int NT = kRefThreads>
-__device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_fixed) {
+__device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_fixed,
+                            GroupCtx &gc) {
     using RE = RowEval<SYS>;
     constexpr int NE = ENERGY ? 1 : RE::NJ * 3;
     __shared__ double h_err[kHeapCap], h_a[kHeapCap], h_b[kHeapCap];
@@ -248,7 +304,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
     // ---- initial panel [0,1] ------------------------------------------------
     {
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int i = threadIdx.x; i < D; i += NT) {
+        for (int i = gc.rank * NT + threadIdx.x; i < D; i += gc.G * NT) {
             RE ev;
             ev.load(a, n, i, dt);
             double integ[NE];
@@ -259,7 +315,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
                 acc[3] += integ[e] * integ[e];
             }
         }
-        block_sum<7, NT>(acc, sh_red);
+        group_sum<7, NT>(acc, sh_red, gc);
         if (threadIdx.x == 0) {
             double e0, r0;
             gk_error(acc[0], acc[1], acc[2], e0, r0);
@@ -305,7 +361,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
         for (int t = 0; t < nb; ++t) {
             const double pa = b_a[t], pb = b_b[t], pc = 0.5 * (pa + pb);
             double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-            for (int i = threadIdx.x; i < D; i += NT) {
+            for (int i = gc.rank * NT + threadIdx.x; i < D; i += gc.G * NT) {
                 RE ev;
                 ev.load(a, n, i, dt);
                 double i_old[NE], i_l[NE], i_r[NE], dummy[3] = {0, 0, 0};
@@ -320,7 +376,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
                     if (!ENERGY && pa == 0.0 && pb == 1.0) ws_fixed[(int64_t)i * NE + e] = i_l[e] + i_r[e];
                 }
             }
-            block_sum<7, NT>(acc, sh_red);
+            group_sum<7, NT>(acc, sh_red, gc);
             if (threadIdx.x == 0) {
                 double e1, r1, e2, r2;
                 gk_error(acc[0], acc[1], acc[2], e1, r1);
@@ -337,13 +393,13 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
         // |global_integral| after the batch
         {
             double acc[1] = {0.0};
-            for (int i = threadIdx.x; i < D; i += NT)
+            for (int i = gc.rank * NT + threadIdx.x; i < D; i += gc.G * NT)
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     const double g = ws[(int64_t)i * NE + e];
                     acc[0] += g * g;
                 }
-            block_sum<1, NT>(acc, sh_red);
+            group_sum<1, NT>(acc, sh_red, gc);
             if (threadIdx.x == 0) {
                 normG = sqrt(acc[0]);
                 if (h_cnt >= 2) {
@@ -356,7 +412,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
             __syncthreads();
         }
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && gc.rank == 0) {
         a.info[2 * n + (ENERGY ? 0 : 1)] = nbis;
         if (stop_flag == 0 && h_cnt >= kLimit) atomicOr(a.status, 16);
     }
@@ -364,12 +420,12 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
     // ---- write the refined integral back ---------------------------------------
     if (ENERGY) {
         double acc[1] = {0.0};
-        for (int i = threadIdx.x; i < D; i += NT) acc[0] += ws[i] / a.sigma[i];
-        block_sum<1, NT>(acc, sh_red);
-        if (threadIdx.x == 0) a.esde_n[n] = 0.5 * acc[0];
+        for (int i = gc.rank * NT + threadIdx.x; i < D; i += gc.G * NT) acc[0] += ws[i] / a.sigma[i];
+        group_sum<1, NT>(acc, sh_red, gc);
+        if (threadIdx.x == 0 && gc.rank == 0) a.esde_n[n] = 0.5 * acc[0];
     } else if (a.ds_out != nullptr) {
-        __syncthreads();
-        for (int j = threadIdx.x; j < D; j += NT) {
+        group_barrier(gc);                 // the neighbours' rows may belong to other CTAs
+        for (int j = gc.rank * NT + threadIdx.x; j < D; j += gc.G * NT) {
             double o[3] = {0.0, 0.0, 0.0};
             if (SYS == 3) {
                 const int src[4] = {j, (j + D - 1) % D, (j + 1) % D, (j + 2) % D};
@@ -380,7 +436,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const int64_t q = (int64_t)i * NE + slot * 3 + k;
-                        o[k] += is * (a.delta_mode ? ws[q] - ws_fixed[q] : ws[q]);
+                        o[k] += is * (a.delta_mode ? __ldcg(ws + q) - __ldcg(ws_fixed + q) : __ldcg(ws + q));   // other CTAs' rows: through L2
                     }
                 }
             } else {
@@ -389,7 +445,7 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const int64_t q = (int64_t)i * NE + j * 3 + k;
-                        o[k] += is * (a.delta_mode ? ws[q] - ws_fixed[q] : ws[q]);
+                        o[k] += is * (a.delta_mode ? __ldcg(ws + q) - __ldcg(ws_fixed + q) : __ldcg(ws + q));   // other CTAs' rows: through L2
                     }
                 }
             }
@@ -400,7 +456,8 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
     __syncthreads();
 }
 
-// grid.x persistent CTAs; work item w = (interval, integrand)
+// persistent CTAs in groups of a.group (co-resident: the grid never exceeds one wave);
+// work item w = (interval, integrand), one group per item at a time
 template <int SYS>
 __global__ void __launch_bounds__(kRefThreads)
 refine_kernel(const RefineArgs a) {
@@ -410,15 +467,21 @@ refine_kernel(const RefineArgs a) {
             a.info[2 * a.n_begin + w] = 0;
         return;
     }
-    double *ws = a.ws + (int64_t)blockIdx.x * 2 * a.D * kMaxNE;
+    const int G = a.group, grp = blockIdx.x / G, ngrp = gridDim.x / G;
+    GroupCtx gc;
+    gc.G = G; gc.rank = blockIdx.x % G;
+    gc.part = a.gpart + (int64_t)grp * 2 * G * 8;
+    gc.bar = a.gbar + grp;
+    gc.seq = 0; gc.status = a.status;
+    double *ws = a.ws + (int64_t)grp * 2 * a.D * kMaxNE;
     double *ws_fixed = ws + (int64_t)a.D * kMaxNE;
-    for (int w = blockIdx.x; w < 2 * nl; w += gridDim.x) {
+    for (int w = grp; w < 2 * nl; w += ngrp) {
         const int n = a.n_begin + (w >> 1);
         const int which = w & 1;
         const int f = a.flags[n];
-        if (threadIdx.x == 0) a.info[2 * n + which] = 0;
-        if (which == 0 && (f & 1)) refine_item<SYS, true>(a, n, ws, ws_fixed);
-        if (which == 1 && (f & 2) && a.want_grad) refine_item<SYS, false>(a, n, ws, ws_fixed);
+        if (threadIdx.x == 0 && gc.rank == 0) a.info[2 * n + which] = 0;
+        if (which == 0 && (f & 1)) refine_item<SYS, true>(a, n, ws, ws_fixed, gc);
+        if (which == 1 && (f & 2) && a.want_grad) refine_item<SYS, false>(a, n, ws, ws_fixed, gc);
     }
 }
 

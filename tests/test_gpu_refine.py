@@ -85,3 +85,55 @@ def test_limit_is_reported_not_hidden():
     assert fe.last_status & 16 and fe.last_status & 8
     assert np.isfinite(F) and np.all(np.isfinite(grad))
     assert fe.refine_info().max() >= 99
+
+
+@pytest.mark.parametrize("D,group", [(130, 3), (1100, None), (2100, None)])
+def test_refine_groups_match_oracle(D, group, monkeypatch):
+    """
+    At large D a flagged interval is shared by a group of CTAs (refine.cuh GroupCtx: rows dealt
+    over the group, reductions through global memory + group barrier).  Same decisions and
+    values as scipy's quad_vec; `group` forces a group size on a small problem.
+    """
+    from helpers import synthetic_l96
+    M = 4
+    g = synthetic_l96(D, M, seed=D)
+    x = g["x0"].copy()
+    sp = x[D * (3 * M + 4):].reshape(D, 2 * M + 3)
+    sp[:, [1, 4]] = np.log(0.2)                 # steep variance triples in two intervals
+    if group:
+        monkeypatch.setenv("MFVGP_REFINE_GROUP", str(group))
+    monkeypatch.setenv("MFVGP_PATH", "walk")     # refine_kernel (the coop path refines in-kernel)
+    fe = make_free_energy(g)
+    monkeypatch.delenv("MFVGP_PATH")
+    monkeypatch.delenv("MFVGP_REFINE_GROUP", raising=False)
+    F, grad = fe.E_cost(x)
+    info = fe.refine_info()
+    assert info.max() >= 2
+    o = make_oracle(g, adaptive=True)
+    Fo, go = o.E_cost(x)
+    nev = np.array(o.neval)
+    assert np.array_equal(_neval_from_info(info[:, 0]), nev[:, 0])
+    assert np.array_equal(_neval_from_info(info[:, 1]), nev[:, 2])
+    assert abs(F - Fo) <= RTOL * abs(Fo) and rel_err(grad, go) <= RTOL
+    assert not (fe.last_status & 32)
+
+
+def test_refine_groups_of_16_equal_single_cta(monkeypatch):
+    """D = 8192: groups of 16 CTAs against one CTA per item (same kernel, MFVGP_REFINE_GROUP=1)."""
+    import torch
+    from helpers import synthetic_l96_device
+    D, M = 8192, 41
+    g = synthetic_l96_device(torch, D, M, seed=5)
+    x = g["x0"].clone()
+    sp = x[D * (3 * M + 4):].view(D, 2 * M + 3)
+    sp[:, [5, 21, 40]] = float(np.log(0.25))
+    fe16 = make_free_energy(g)
+    F16, g16 = fe16.E_cost(x)
+    info16 = fe16.refine_info()
+    monkeypatch.setenv("MFVGP_REFINE_GROUP", "1")
+    fe1 = make_free_energy(g)
+    monkeypatch.delenv("MFVGP_REFINE_GROUP")
+    F1, g1 = fe1.E_cost(x)
+    assert info16.max() >= 2 and np.array_equal(fe1.refine_info(), info16)
+    assert abs(F16.item() - F1.item()) <= 1e-13 * abs(F1.item())
+    assert rel_err(g16.cpu().numpy(), g1.cpu().numpy()) <= 1e-12
