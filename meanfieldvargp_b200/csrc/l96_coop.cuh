@@ -8,9 +8,9 @@
 //       4-6; all seven nodes travel through shared memory at once (two barriers per cell
 //       instead of 14); lane 0 ends with dEsde_dm, lane 1 with dEsde_ds and the energy.
 // Same [L][D][4] / [L][D][3] outputs and guard partials as esde_l96_split_kernel.
-// The last CTA of an interval (atomic ticket) folds the tile partials, applies the guard
-// (guard_interval, kernels.cuh) and -- when the fixed rule is not provably quad_vec's
-// answer -- runs the adaptive path (refine.cuh) on the spot: no guard / refine launches.
+// The last CTA of an interval (atomic ticket) folds the tile partials and applies the guard
+// (guard_interval, kernels.cuh): no guard launch.  Flagged intervals are counted and handed
+// to refine_kernel, which follows in the stream and exits at once when there are none.
 // (A first version with 8 lanes per cell was shuffle-bound: 19 us; see profiles/.)
 #pragma once
 
@@ -25,21 +25,10 @@ constexpr int kCoopNT = kCoopTE * kCoopW;   // 64 threads
 
 struct CoopArgs {
     EsdeArgs a;
-    GuardArgs g;
-    RefineArgs r;             // adaptive path of a flagged interval, run by its last CTA
+    GuardArgs g;              // g.nflagged counts the flagged intervals for refine_kernel
     unsigned *tickets;        // [n_end - n_begin], zero between launches
     double theta;
 };
-
-// Programmatic dependent launch (sm_90+): a kernel launched with the
-// programmatic-stream-serialization attribute may be scheduled while its predecessor in
-// the stream is still running; pdl_wait() blocks until that predecessor has completed and
-// its writes are visible (no-op for a normal launch), pdl_launch_dependents() lets the
-// successor's CTAs be scheduled early.  Hides ~2 us of launch latency per kernel.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
     return __shfl_xor_sync(0xffffffffu, v, m);
@@ -254,61 +243,29 @@ esde_l96_coop_kernel(const CoopArgs ca) {
         if (sh_last) ca.tickets[n - a.n_begin] = 0u;
     }
     __syncthreads();
-    if (sh_last) {                                 // CTA-uniform
-        if (tid < 32) {
-            __threadfence();
-            guard_interval(ca.g, n, tid);
-        }
-        __syncthreads();
-        // quad_vec keeps bisecting where the fixed rule is not provably its answer
-        // (refine.cuh); rare, so the interval's last CTA does it on the spot
-        const int f = ca.g.flags[n];
-        if (tid == 0) ca.r.info[2 * n] = ca.r.info[2 * n + 1] = 0;
-        if (f) {
-            double *ws = ca.r.ws + (int64_t)(n - a.n_begin) * 2 * D * kMaxNE;
-            double *ws_fixed = ws + (int64_t)D * kMaxNE;
-            GroupCtx gc{1, 0, nullptr, nullptr, 0u, ca.r.status};
-            if (f & 1) refine_item<3, true, kCoopNT>(ca.r, n, ws, ws_fixed, gc);
-            if ((f & 2) && ca.r.want_grad) refine_item<3, false, kCoopNT>(ca.r, n, ws, ws_fixed, gc);
-        }
+    if (sh_last && tid < 32) {
+        // quad_vec keeps bisecting where the fixed rule is not provably its answer: the guard
+        // flags the interval and counts it; refine_kernel (next in the stream, exits at once
+        // when the count is zero) takes it from there
+        __threadfence();
+        guard_interval(ca.g, n, tid);
     }
 }
 
 // ---------------------------------------------------------------------------
-// DW / OU / L63: esde_small_kernel with the guard and the adaptive path folded in.
-// Two CTAs per interval (blockIdx.y) integrate it redundantly -- it is tiny -- so that,
-// when quad_vec would refine, the energy integrand (CTA 0, which owns dEsde_dm and the
-// interval's Esde) and the dS integrand (CTA 1, which owns dEsde_ds) are refined side by
-// side, as refine_kernel does; both reach the same guard decision from identical sums.
-// g2: CTA 1's private guard outputs.
+// DW / OU / L63: esde_small_kernel with the guard folded in (one CTA per interval owns the
+// whole interval, so no ticket is needed); flagged intervals go to refine_kernel.
 // ---------------------------------------------------------------------------
-struct SmallArgs {
-    CoopArgs c;
-    double *part2, *esde_n2;
-    int32_t *flags2;
-};
-
 template <int SYS>
 __global__ void __launch_bounds__(64)
-esde_small_inkernel(const SmallArgs sa) {
-    const EsdeArgs &a = sa.c.a;
-    const int n = a.n_begin + blockIdx.x, tid = threadIdx.x, y = blockIdx.y;
+esde_small_inkernel(const CoopArgs ca) {
+    const EsdeArgs &a = ca.a;
+    const int n = a.n_begin + blockIdx.x, tid = threadIdx.x;
     pdl_wait();
-    pdl_launch_dependents();        // only now: the tail kernel reads x before ITS wait
-    EsdeArgs mine = a;
-    GuardArgs g = sa.c.g;
-    if (y == 1) { mine.part = sa.part2; g.part = sa.part2; g.esde_n = sa.esde_n2; g.flags = sa.flags2; }
-    esde_small_body<SYS>(mine, y == 0 ? 1 : 2);
+    pdl_launch_dependents();        // only now: the successors read x before THEIR wait
+    esde_small_body<SYS>(a);
     __syncthreads();
-    if (tid < 32) guard_interval(g, n, tid);
-    __syncthreads();
-    const int f = g.flags[n];
-    if (tid == 0) sa.c.r.info[2 * n + y] = 0;
-    double *ws = sa.c.r.ws + ((int64_t)(n - a.n_begin) * 2 + y) * 2 * a.D * kMaxNE;
-    double *ws_fixed = ws + (int64_t)a.D * kMaxNE;
-    GroupCtx gc{1, 0, nullptr, nullptr, 0u, sa.c.r.status};
-    if (y == 0 && (f & 1)) refine_item<SYS, true, 64>(sa.c.r, n, ws, ws_fixed, gc);
-    if (y == 1 && (f & 2) && sa.c.r.want_grad) refine_item<SYS, false, 64>(sa.c.r, n, ws, ws_fixed, gc);
+    if (tid < 32) guard_interval(ca.g, n, tid);
 }
 
 // ---------------------------------------------------------------------------

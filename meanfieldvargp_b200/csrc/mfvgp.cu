@@ -49,8 +49,6 @@ struct mfvgp_handle {
     int *head_flag = nullptr;     // walk kernel mailbox flags [fntn][fntiles]
     int walk_epoch = 0;
     double *y_dense = nullptr, *rinv_row = nullptr;   // row tables of assemble_tail_kernel
-    double *esde_n2 = nullptr;                        // esde_small_inkernel: CTA 1's guard outputs
-    int32_t *flags2 = nullptr;
     int tail_grid = 1;
     double theta_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int rule = 1;     // 1: split rule (default), 0: 42-node coupled rule (MFVGP_RULE=gk42)
@@ -71,6 +69,7 @@ struct mfvgp_handle {
     // adaptive refinement (refine.cuh)
     double *refine_ws = nullptr;
     int32_t *refine_info = nullptr, *refine_status = nullptr;   // refine_status[1] = flagged count
+    bool refine_warp = true;
     int refine_grid = 1, refine_group = 1;      // CTAs per flagged item (refine.cuh GroupCtx)
     double *refine_gpart = nullptr;
     unsigned *refine_gbar = nullptr;
@@ -278,27 +277,36 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         dev_alloc(&h->part, (size_t)nl * (h->ntiles > h->fntiles ? (h->ntiles > 2 ? h->ntiles : 2)
                                                                    : (h->fntiles > 2 ? h->fntiles : 2)) *
                                 kPartStride) ||
-        dev_alloc(&h->esde_n2, L) ||
+
         dev_alloc(&h->fedge_m, (size_t)h->fntn * D) || dev_alloc(&h->fedge_s, (size_t)h->fntn * D) ||
         dev_alloc(&h->fapart, (size_t)h->fntn * h->fntiles * 4) ||
         dev_alloc(&h->esde_n, L) || dev_alloc(&h->apart, (size_t)(D > h->tail_grid ? D : h->tail_grid) * 4) ||
         dev_alloc(&h->out_ws, 16) || dev_alloc(&h->rec_ws, 16))
         return MFVGP_ERR_CUDA;
-    // adaptive path: groups of G co-resident CTAs share a flagged item; 252 registers x 128
-    // threads => two CTAs per SM, so at most 296 CTAs in all
-    h->refine_group = D >= 8192 ? 16 : (D >= 4096 ? 8 : (D >= 2048 ? 4 : (D >= 1024 ? 2 : 1)));
-    if (const char *e = getenv("MFVGP_REFINE_GROUP")) {
-        const int gsz = atoi(e);
-        if (gsz >= 1 && gsz <= 64) h->refine_group = gsz;
-    }
+    // adaptive path (refine.cuh): a flagged item is shared by a group of G co-resident CTAs.
+    // D < 1024: rows are scarce and latency decides -- one WARP per state dimension (nodes
+    // across the lanes), G ~ D/8 (two rows per warp).  D >= 1024: throughput decides -- one
+    // THREAD per state dimension, groups of 2-16 CTAs.  (Measured at D=8192, forty flagged
+    // intervals: 3.4 ms per evaluation with threads per row, 36 ms with warps per row; at
+    // D=500, one flagged interval: 175 us with warps per row, 320 us with threads per row.)
+    // At most two CTAs per SM fit (registers), so the grid never exceeds 296 CTAs.
     {
-        int groups = 296 / h->refine_group;
+        h->refine_warp = D < 1024;
+        if (const char *e = getenv("MFVGP_REFINE_WARP")) h->refine_warp = e[0] == '1';
+        int gsz = h->refine_warp ? (D + 7) / 8
+                                 : (D >= 8192 ? 16 : (D >= 4096 ? 8 : (D >= 2048 ? 4 : 2)));
+        h->refine_group = gsz < 1 ? 1 : (gsz > 64 ? 64 : gsz);
+        if (const char *e = getenv("MFVGP_REFINE_GROUP")) {
+            const int v = atoi(e);
+            if (v >= 1 && v <= 64) h->refine_group = v;
+        }
+        int max_ctas = 296;
+        if (const char *e = getenv("MFVGP_REFINE_CTAS")) max_ctas = atoi(e);
+        int groups = max_ctas / h->refine_group;
+        if (groups < 1) groups = 1;
         if (groups > 2 * nl) groups = 2 * nl;
         h->refine_grid = groups * h->refine_group;
-        // scratch of the adaptive path: one slot per group, or per interval (in-kernel callers)
-        const int need = system == MFVGP_SYS_L96 ? nl : 2 * nl;
-        const int slots = h->coop && need > groups ? need : groups;
-        if (dev_alloc(&h->refine_ws, (size_t)slots * 2 * D * kMaxNE)) return MFVGP_ERR_CUDA;
+        if (dev_alloc(&h->refine_ws, (size_t)groups * 2 * D * kMaxNE)) return MFVGP_ERR_CUDA;
         if (dev_alloc(&h->refine_gpart, (size_t)groups * 2 * h->refine_group * 8)) return MFVGP_ERR_CUDA;
         CK(cudaMalloc((void **)&h->refine_gbar, (size_t)groups * sizeof(unsigned)));
         CK(cudaMemset(h->refine_gbar, 0, (size_t)groups * sizeof(unsigned)));
@@ -316,7 +324,7 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     CK(cudaMemset(h->tickets, 0, (L + 4) * sizeof(unsigned)));
     CK(cudaMalloc((void **)&h->obs_idx, D * sizeof(int32_t)));
     CK(cudaMalloc((void **)&h->flags, L * sizeof(int32_t)));
-    CK(cudaMalloc((void **)&h->flags2, L * sizeof(int32_t)));
+
     CK(cudaMalloc((void **)&h->status_ws, sizeof(int32_t)));
     CK(cudaMemset(h->flags, 0, L * sizeof(int32_t)));
     CK(cudaMemset(h->esde_n, 0, L * sizeof(double)));
@@ -337,7 +345,7 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->scg_vec[5], h->scg_vec[6], h->scg_part, h->scg_scal,
                     h->refine_ws, h->refine_info, h->refine_status, h->edge_send, h->edge_recv,
                     h->gather, h->xchg_send, h->xchg_gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
-                    h->y_dense, h->rinv_row, h->esde_n2, h->flags2, h->head_flag, h->refine_gpart,
+                    h->y_dense, h->rinv_row, h->head_flag, h->refine_gpart,
                     h->refine_gbar};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -434,13 +442,30 @@ static RefineArgs refine_args(mfvgp_handle *h, const double *mean, int64_t ldm, 
     r.mean = mean; r.vars = vars; r.ldm = ldm; r.lds = lds;
     r.obs_times = h->obs_times; r.sigma = h->sigma; r.theta = h->theta;
     r.flags = h->flags; r.esde_n = h->esde_n; r.ds_out = ds; r.ws = h->refine_ws;
-    r.nflagged = h->coop ? nullptr : h->refine_status + 1;
+    r.nflagged = h->refine_status + 1;
     r.group = h->refine_group; r.gpart = h->refine_gpart; r.gbar = h->refine_gbar;
     r.delta_mode = delta_mode;
     r.info = h->refine_info; r.status = h->refine_status;
     r.D = h->D; r.n_begin = h->n_begin; r.n_end = h->n_end; r.log_vars = log_vars;
     r.want_grad = ds != nullptr;
     return r;
+}
+
+// adaptive path for the flagged (interval, integrand) pairs; exits at once when none is flagged
+static int launch_refine(mfvgp_handle *h, const double *mean, int64_t ldm, const double *vars,
+                         int64_t lds, int log_vars, double *ds, int delta_mode, cudaStream_t st) {
+    const RefineArgs r = refine_args(h, mean, ldm, vars, lds, log_vars, ds, delta_mode);
+    const dim3 grid(h->refine_grid);
+    switch (h->system) {
+        case MFVGP_SYS_DW: CK(launch_pdl(refine_kernel<0, true>, grid, kRefThreads, st, r)); break;
+        case MFVGP_SYS_OU: CK(launch_pdl(refine_kernel<1, true>, grid, kRefThreads, st, r)); break;
+        case MFVGP_SYS_L63: CK(launch_pdl(refine_kernel<2, true>, grid, kRefThreads, st, r)); break;
+        default:
+            if (h->refine_warp) CK(launch_pdl(refine_kernel<3, true>, grid, kRefThreads, st, r));
+            else CK(launch_pdl(refine_kernel<3, false>, grid, kRefThreads, st, r));
+    }
+    h->launches++;
+    return MFVGP_OK;
 }
 
 static int launch_guard_refine(mfvgp_handle *h, const double *mean, int64_t ldm,
@@ -454,17 +479,7 @@ static int launch_guard_refine(mfvgp_handle *h, const double *mean, int64_t ldm,
     guard_reduce_kernel<<<(nl * 32 + 255) / 256, 256, 0, st>>>(g);
     h->launches++;
     CK(cudaGetLastError());
-    // adaptive path for the flagged (interval, integrand) pairs; unflagged CTAs exit at once
-    const RefineArgs r = refine_args(h, mean, ldm, vars, lds, log_vars, ds, delta_mode);
-    switch (h->system) {
-        case MFVGP_SYS_DW: refine_kernel<0><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
-        case MFVGP_SYS_OU: refine_kernel<1><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
-        case MFVGP_SYS_L63: refine_kernel<2><<<h->refine_grid, kRefThreads, 0, st>>>(r); break;
-        default: refine_kernel<3><<<h->refine_grid, kRefThreads, 0, st>>>(r);
-    }
-    h->launches++;
-    CK(cudaGetLastError());
-    return MFVGP_OK;
+    return launch_refine(h, mean, ldm, vars, lds, log_vars, ds, delta_mode, st);
 }
 
 static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const double *vars,
@@ -482,31 +497,26 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         CK(cudaEventCreate(&ev1));
         CK(cudaEventRecord(ev0, st));
     }
-    CoopArgs c;                               // small-problem kernels: guard + refine inside
+    CoopArgs c;                               // small-problem kernels: guard inside
     if (h->coop) {
         c.a = a;
         c.g.part = h->part; c.g.obs_times = h->obs_times; c.g.esde_n = h->esde_n;
         c.g.flags = h->flags; c.g.n_begin = h->n_begin; c.g.n_end = h->n_end;
         c.g.ntiles = h->ntiles;
-        c.g.nflagged = nullptr;              // the in-kernel adaptive path reads the flag itself
-        c.r = refine_args(h, mean, ldm, vars, lds, log_vars, ds, 0);
+        c.g.nflagged = h->refine_status + 1;
         c.tickets = h->tickets; c.theta = h->theta_host[0];
     }
-    SmallArgs sa;
-    sa.c = c;
-    sa.part2 = h->part + (size_t)nl * kPartStride;           // second half of `part`
-    sa.esde_n2 = h->esde_n2; sa.flags2 = h->flags2;
     switch (h->system) {
         case MFVGP_SYS_DW:
-            if (h->coop) CK(launch_pdl(esde_small_inkernel<0>, dim3(nl, 2), 64, st, sa));
+            if (h->coop) CK(launch_pdl(esde_small_inkernel<0>, dim3(nl), 64, st, c));
             else esde_small_kernel<0><<<nl, 64, 0, st>>>(a);
             break;
         case MFVGP_SYS_OU:
-            if (h->coop) CK(launch_pdl(esde_small_inkernel<1>, dim3(nl, 2), 64, st, sa));
+            if (h->coop) CK(launch_pdl(esde_small_inkernel<1>, dim3(nl), 64, st, c));
             else esde_small_kernel<1><<<nl, 64, 0, st>>>(a);
             break;
         case MFVGP_SYS_L63:
-            if (h->coop) CK(launch_pdl(esde_small_inkernel<2>, dim3(nl, 2), 64, st, sa));
+            if (h->coop) CK(launch_pdl(esde_small_inkernel<2>, dim3(nl), 64, st, c));
             else esde_small_kernel<2><<<nl, 64, 0, st>>>(a);
             break;
         default: {
@@ -530,7 +540,8 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         CK(cudaEventRecord(ev1, st));
         h->timing_events.emplace_back(ev0, ev1);
     }
-    if (h->coop) return MFVGP_OK;          // guard and adaptive path ran inside the kernel
+    if (h->coop)                           // the guard ran inside the kernel
+        return launch_refine(h, mean, ldm, vars, lds, log_vars, ds, 0, st);
     return launch_guard_refine(h, mean, ldm, vars, lds, log_vars, ds, h->ntiles, 0, st);
 }
 
@@ -628,7 +639,7 @@ static int launch_final(mfvgp_handle *h, const double *apart, int napart, double
     f.esde_n = h->esde_n; f.flags = h->flags; f.apart = apart;
     f.out = multi ? h->rec_ws : out; f.status = status;
     f.refine_status = h->refine_status;
-    f.nflagged = h->coop ? nullptr : h->refine_status + 1;
+    f.nflagged = h->refine_status + 1;
     f.gbar = h->refine_gbar; f.ngbar = h->refine_grid / h->refine_group;
     f.record9 = multi ? 1 : 0;
     f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = napart;
@@ -787,7 +798,8 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
         const int nb = h->tail_grid;
         t.f.esde_n = h->esde_n; t.f.flags = h->flags; t.f.apart = h->apart;
         t.f.out = out_d; t.f.status = status_d; t.f.refine_status = h->refine_status;
-        t.f.nflagged = nullptr; t.f.gbar = nullptr; t.f.ngbar = 0;
+        t.f.nflagged = h->refine_status + 1;
+        t.f.gbar = h->refine_gbar; t.f.ngbar = h->refine_grid / h->refine_group;
         t.f.record9 = 0; t.f.n_begin = h->n_begin; t.f.n_end = h->n_end; t.f.D = nb;
         t.f.with_e0 = 1; t.f.eobs_const = h->eobs_const;
         t.ticket = h->tickets + h->L + 1;

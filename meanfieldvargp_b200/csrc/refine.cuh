@@ -220,19 +220,24 @@ __device__ __forceinline__ void group_sum(double (&v)[NV], double *sh, GroupCtx 
 #pragma unroll
         for (int i = 0; i < NV; ++i) slot[gc.rank * 8 + i] = v[i];
     group_barrier(gc);
-    if (threadIdx.x == 0)
+    if (threadIdx.x < 32) {            // warp 0: lanes over the ranks, then a butterfly (fixed tree)
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            double t = __ldcg(slot + i);
-            for (int r = 1; r < gc.G; ++r) t += __ldcg(slot + r * 8 + i);
+            double t = 0.0;
+            for (int r = threadIdx.x; r < gc.G; r += 32) t += __ldcg(slot + r * 8 + i);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
             v[i] = t;
         }
+    }
 }
 
-// _quadrature_gk on [pa, pb] (local coordinates) for one row, NE elements.
+// _quadrature_gk on [pa, pb] (local coordinates) for one row, NE elements, by ONE THREAD
+// (large D: a thread per row keeps all 32 lanes on arithmetic; the nodes are walked twice,
+// the second time for the |f - s_k/2| sum).
 // integ[e] = h*s_k ; acc[0..2] += squared contributions to the three norms.
 template <int SYS, int NE, bool ENERGY>
-__device__ __forceinline__ void gk21_row(const RowEval<SYS> &ev, double pa, double pb,
+__device__ __forceinline__ void gk21_row_thread(const RowEval<SYS> &ev, double pa, double pb,
                                          double dt, double *integ, double *acc) {
     const double c = 0.5 * (pa + pb), hl = 0.5 * (pb - pa);
     const double h = hl * dt;
@@ -276,6 +281,58 @@ __device__ __forceinline__ void gk21_row(const RowEval<SYS> &ev, double pa, doub
     }
 }
 
+// _quadrature_gk on [pa, pb] (local coordinates) for one row, NE elements, by ONE WARP
+// (small D, where rows are scarce and latency decides): lane r
+// evaluates Kronrod node r (lanes 21..31 idle), the node sums are butterflies, and the node values
+// stay in registers for the second sum (|f - s_k/2|), so every node is evaluated once.
+// integ[e] = h*s_k (all lanes); acc[0..2] += squared contributions to the three norms (lane 0).
+__device__ __forceinline__ double warp_allsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int SYS, int NE, bool ENERGY>
+__device__ __forceinline__ void gk21_row_warp(const RowEval<SYS> &ev, double pa, double pb,
+                                              double dt, double *integ, double *acc) {
+    const int r = threadIdx.x & 31;
+    const bool node = r < kNodesPerPanel;
+    const double c = 0.5 * (pa + pb), hl = 0.5 * (pb - pa);
+    const double h = hl * dt;
+    double f[NE];
+    {
+        double E, el[kMaxNE];
+        ev.eval(c + hl * c_gk_x[node ? r : 0], E, el);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) f[e] = ENERGY ? E : el[e];
+    }
+    const double v = node ? c_gk_v[r] : 0.0;
+    const double w = (node && (r & 1)) ? c_gk_w[(r - 1) >> 1] : 0.0;
+    const double eps50 = 50.0 * 2.220446049250313e-16;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const double fe = node ? f[e] : 0.0;
+        const double sk = warp_allsum(v * fe);
+        const double sg = warp_allsum(w * fe);
+        const double sabs = warp_allsum(v * fabs(fe));
+        const double sdabs = warp_allsum(v * fabs(fe - 0.5 * sk));
+        integ[e] = h * sk;
+        const double d1 = (sk - sg) * h, d2 = sdabs * h, d3 = eps50 * h * sabs;
+        if (r == 0) {
+            acc[0] += d1 * d1;
+            acc[1] += d2 * d2;
+            acc[2] += d3 * d3;
+        }
+    }
+}
+
+template <int SYS, int NE, bool ENERGY, bool WARP>
+__device__ __forceinline__ void gk21_row(const RowEval<SYS> &ev, double pa, double pb,
+                                         double dt, double *integ, double *acc) {
+    if (WARP) gk21_row_warp<SYS, NE, ENERGY>(ev, pa, pb, dt, integ, acc);
+    else gk21_row_thread<SYS, NE, ENERGY>(ev, pa, pb, dt, integ, acc);
+}
+
 // scipy's error model from the three norms of one panel
 __device__ __forceinline__ void gk_error(double n_kg2, double n_dabs2, double n_rnd2,
                                          double &err, double &rnd) {
@@ -286,7 +343,8 @@ __device__ __forceinline__ void gk_error(double n_kg2, double n_dabs2, double n_
     if (rnd > 2.2250738585072014e-308) err = fmax(err, rnd);
 }
 
-template <int SYS, bool ENERGY, int NT = kRefThreads>
+// WARP: one warp per row (nodes across the lanes) instead of one thread per row
+template <int SYS, bool ENERGY, bool WARP, int NT = kRefThreads>
 __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_fixed,
                             GroupCtx &gc) {
     using RE = RowEval<SYS>;
@@ -297,6 +355,11 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
     __shared__ double b_err[kHeapCap], b_a[kHeapCap], b_b[kHeapCap];
 
     const int D = a.D;
+    const int lane = threadIdx.x & 31;
+    // rows of this thread (or of its warp) and who records their results
+    const int wid0 = WARP ? gc.rank * (NT / 32) + (threadIdx.x >> 5) : gc.rank * NT + threadIdx.x;
+    const int wstride = WARP ? gc.G * (NT / 32) : gc.G * NT;
+    const bool writer = WARP ? lane == 0 : true;
     const double dt = fabs(a.obs_times[n + 1] - a.obs_times[n]);
     double gerr = 0.0, rnd = 0.0, normG = 0.0;   // meaningful in thread 0
     int nbis = 0;
@@ -304,16 +367,17 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
     // ---- initial panel [0,1] ------------------------------------------------
     {
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int i = gc.rank * NT + threadIdx.x; i < D; i += gc.G * NT) {
+        for (int i = wid0; i < D; i += wstride) {          // one warp per row
             RE ev;
             ev.load(a, n, i, dt);
             double integ[NE];
-            gk21_row<SYS, NE, ENERGY>(ev, 0.0, 1.0, dt, integ, acc);
+            gk21_row<SYS, NE, ENERGY, WARP>(ev, 0.0, 1.0, dt, integ, acc);
+            if (writer)
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                ws[(int64_t)i * NE + e] = integ[e];
-                acc[3] += integ[e] * integ[e];
-            }
+                for (int e = 0; e < NE; ++e) {
+                    ws[(int64_t)i * NE + e] = integ[e];
+                    acc[3] += integ[e] * integ[e];
+                }
         }
         group_sum<7, NT>(acc, sh_red, gc);
         if (threadIdx.x == 0) {
@@ -361,21 +425,24 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
         for (int t = 0; t < nb; ++t) {
             const double pa = b_a[t], pb = b_b[t], pc = 0.5 * (pa + pb);
             double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-            for (int i = gc.rank * NT + threadIdx.x; i < D; i += gc.G * NT) {
+            for (int i = wid0; i < D; i += wstride) {      // one warp per row
                 RE ev;
                 ev.load(a, n, i, dt);
                 double i_old[NE], i_l[NE], i_r[NE], dummy[3] = {0, 0, 0};
-                gk21_row<SYS, NE, ENERGY>(ev, pa, pc, dt, i_l, acc);
-                gk21_row<SYS, NE, ENERGY>(ev, pc, pb, dt, i_r, acc + 3);
-                gk21_row<SYS, NE, ENERGY>(ev, pa, pb, dt, i_old, dummy);   // interval_cache value
+                gk21_row<SYS, NE, ENERGY, WARP>(ev, pa, pc, dt, i_l, acc);
+                gk21_row<SYS, NE, ENERGY, WARP>(ev, pc, pb, dt, i_r, acc + 3);
+                gk21_row<SYS, NE, ENERGY, WARP>(ev, pa, pb, dt, i_old, dummy);   // interval_cache value
+                if (writer)
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    const double dint = i_l[e] + i_r[e] - i_old[e];
-                    ws[(int64_t)i * NE + e] += dint;
-                    // the root panel's two halves are the fixed 42-node rule
-                    if (!ENERGY && pa == 0.0 && pb == 1.0) ws_fixed[(int64_t)i * NE + e] = i_l[e] + i_r[e];
-                }
+                    for (int e = 0; e < NE; ++e) {
+                        const double dint = i_l[e] + i_r[e] - i_old[e];
+                        ws[(int64_t)i * NE + e] += dint;
+                        // the root panel's two halves are the fixed 42-node rule
+                        if (!ENERGY && pa == 0.0 && pb == 1.0)
+                            ws_fixed[(int64_t)i * NE + e] = i_l[e] + i_r[e];
+                    }
             }
+            __syncthreads();       // ws of this CTA's rows: written by lanes 0, read thread-strided below
             group_sum<7, NT>(acc, sh_red, gc);
             if (threadIdx.x == 0) {
                 double e1, r1, e2, r2;
@@ -393,12 +460,20 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
         // |global_integral| after the batch
         {
             double acc[1] = {0.0};
-            for (int i = gc.rank * NT + threadIdx.x; i < D; i += gc.G * NT)
+            for (int i = wid0; i < D; i += wstride) {      // own rows only
+                if (WARP) {                                 // lanes over the elements
+                    if (lane < NE) {
+                        const double g = ws[(int64_t)i * NE + lane];
+                        acc[0] += g * g;
+                    }
+                } else {
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    const double g = ws[(int64_t)i * NE + e];
-                    acc[0] += g * g;
+                    for (int e = 0; e < NE; ++e) {
+                        const double g = ws[(int64_t)i * NE + e];
+                        acc[0] += g * g;
+                    }
                 }
+            }
             group_sum<1, NT>(acc, sh_red, gc);
             if (threadIdx.x == 0) {
                 normG = sqrt(acc[0]);
@@ -420,7 +495,8 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
     // ---- write the refined integral back ---------------------------------------
     if (ENERGY) {
         double acc[1] = {0.0};
-        for (int i = gc.rank * NT + threadIdx.x; i < D; i += gc.G * NT) acc[0] += ws[i] / a.sigma[i];
+        for (int i = wid0; i < D; i += wstride)
+            if (writer) acc[0] += ws[i] / a.sigma[i];
         group_sum<1, NT>(acc, sh_red, gc);
         if (threadIdx.x == 0 && gc.rank == 0) a.esde_n[n] = 0.5 * acc[0];
     } else if (a.ds_out != nullptr) {
@@ -458,10 +534,12 @@ __device__ void refine_item(const RefineArgs &a, int n, double *ws, double *ws_f
 
 // persistent CTAs in groups of a.group (co-resident: the grid never exceeds one wave);
 // work item w = (interval, integrand), one group per item at a time
-template <int SYS>
+template <int SYS, bool WARP>
 __global__ void __launch_bounds__(kRefThreads)
 refine_kernel(const RefineArgs a) {
     const int nl = a.n_end - a.n_begin;
+    pdl_wait();                      // flags, partials and x belong to the predecessor until here
+    pdl_launch_dependents();
     if (a.nflagged != nullptr && a.nflagged[0] == 0) {        // the common case: nothing to do
         for (int w = blockIdx.x * kRefThreads + threadIdx.x; w < 2 * nl; w += gridDim.x * kRefThreads)
             a.info[2 * a.n_begin + w] = 0;
@@ -480,8 +558,8 @@ refine_kernel(const RefineArgs a) {
         const int which = w & 1;
         const int f = a.flags[n];
         if (threadIdx.x == 0 && gc.rank == 0) a.info[2 * n + which] = 0;
-        if (which == 0 && (f & 1)) refine_item<SYS, true>(a, n, ws, ws_fixed, gc);
-        if (which == 1 && (f & 2) && a.want_grad) refine_item<SYS, false>(a, n, ws, ws_fixed, gc);
+        if (which == 0 && (f & 1)) refine_item<SYS, true, WARP>(a, n, ws, ws_fixed, gc);
+        if (which == 1 && (f & 2) && a.want_grad) refine_item<SYS, false, WARP>(a, n, ws, ws_fixed, gc);
     }
 }
 
