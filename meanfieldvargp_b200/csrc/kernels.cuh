@@ -722,6 +722,8 @@ struct FinalArgs {
     int32_t *nflagged;        // [1] GuardArgs::nflagged, reset here (or nullptr)
     unsigned *gbar;           // refine_kernel's group counters, zeroed here for the next evaluation
     int ngbar;
+    int32_t *info;            // [L][2] bisection counts: zeroed here when nothing was flagged and
+                              //        refine_kernel may not have been launched (or nullptr)
     int record9;              // out has 9 slots (multi-GPU record)
     int n_begin, n_end, D;    // D = number of apart rows (state dims, or CTAs of the fused kernel)
     int with_e0;
@@ -749,6 +751,8 @@ __device__ __forceinline__ void final_body(const FinalArgs &a) {
             acc[3] += __ldcg(a.apart + (int64_t)j * 4 + 2);
         }
     if (anyflag) atomicOr(&sh_flag, anyflag);
+    if (a.info != nullptr && a.nflagged != nullptr && __ldcg(a.nflagged) == 0)
+        for (int w = 2 * a.n_begin + threadIdx.x; w < 2 * a.n_end; w += NT) a.info[w] = 0;
     block_sum<4, NT>(acc, sh_red);
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -48,6 +48,9 @@ struct mfvgp_handle {
     unsigned *tickets = nullptr;
     int *head_flag = nullptr;     // walk kernel mailbox flags [fntn][fntiles]
     int walk_epoch = 0;
+    // optimistic evaluation (no refine_kernel launch) pays only while flagged intervals are rare:
+    // after a flagged evaluation the next 16 are run with the adaptive path in the chain
+    int opt_cooldown = 0;
     double *y_dense = nullptr, *rinv_row = nullptr;   // row tables of assemble_tail_kernel
     int tail_grid = 1;
     double theta_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -483,7 +486,8 @@ static int launch_guard_refine(mfvgp_handle *h, const double *mean, int64_t ldm,
 }
 
 static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const double *vars,
-                       int64_t lds, int log_vars, double *dm, double *ds, cudaStream_t st) {
+                       int64_t lds, int log_vars, double *dm, double *ds, cudaStream_t st,
+                       bool skip_refine = false) {
     EsdeArgs a;
     a.mean = mean; a.vars = vars; a.ldm = ldm; a.lds = lds;
     a.obs_times = h->obs_times; a.sigma = h->sigma; a.theta = h->theta;
@@ -541,7 +545,7 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         h->timing_events.emplace_back(ev0, ev1);
     }
     if (h->coop)                           // the guard ran inside the kernel
-        return launch_refine(h, mean, ldm, vars, lds, log_vars, ds, 0, st);
+        return skip_refine ? MFVGP_OK : launch_refine(h, mean, ldm, vars, lds, log_vars, ds, 0, st);
     return launch_guard_refine(h, mean, ldm, vars, lds, log_vars, ds, h->ntiles, 0, st);
 }
 
@@ -641,6 +645,7 @@ static int launch_final(mfvgp_handle *h, const double *apart, int napart, double
     f.refine_status = h->refine_status;
     f.nflagged = h->refine_status + 1;
     f.gbar = h->refine_gbar; f.ngbar = h->refine_grid / h->refine_group;
+    f.info = nullptr;
     f.record9 = multi ? 1 : 0;
     f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = napart;
     f.with_e0 = h->n_begin == 0;
@@ -758,8 +763,20 @@ extern "C" int mfvgp_esde(mfvgp_handle *h, const double *mean_pts_d, int64_t ldm
     return MFVGP_OK;
 }
 
+// optimistic: small problems only -- skip the refine_kernel launch.  The guard still flags the
+// intervals and the status word still carries MFVGP_ST_REFINED, so a caller that reads the
+// status before using the result (the host-buffer entries, the SCG loop) can evaluate
+// optimistically and redo the rare flagged evaluation with the adaptive path.
+static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double *out_d,
+                      double *grad_d, int32_t *status_d, void *cuda_stream, bool optimistic);
+
 extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, double *out_d,
                            double *grad_d, int32_t *status_d, void *cuda_stream) {
+    return ecost_impl(h, x_d, want_grad, out_d, grad_d, status_d, cuda_stream, false);
+}
+
+static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double *out_d,
+                      double *grad_d, int32_t *status_d, void *cuda_stream, bool optimistic) {
     ARG(h && x_d && out_d && status_d, "mfvgp_ecost: NULL argument");
     ARG(!want_grad || grad_d, "mfvgp_ecost: gradient buffer is NULL");
     if (!h->have_sde || !h->have_obs || !h->have_prior) {
@@ -782,7 +799,7 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
                             want_grad ? grad_d : nullptr);
     }
     rc = launch_esde(h, mean, h->Nm, lvar, h->Ns, 1, want_grad ? h->dm_ws : nullptr,
-                     want_grad ? h->ds_ws : nullptr, st);
+                     want_grad ? h->ds_ws : nullptr, st, optimistic && h->coop && h->world == 1);
     if (rc) return rc;
     AssembleArgs a;
     a.x = x_d; a.dm = want_grad ? h->dm_ws : nullptr; a.ds = want_grad ? h->ds_ws : nullptr;
@@ -800,6 +817,7 @@ extern "C" int mfvgp_ecost(mfvgp_handle *h, const double *x_d, int want_grad, do
         t.f.out = out_d; t.f.status = status_d; t.f.refine_status = h->refine_status;
         t.f.nflagged = h->refine_status + 1;
         t.f.gbar = h->refine_gbar; t.f.ngbar = h->refine_grid / h->refine_group;
+        t.f.info = h->refine_info;
         t.f.record9 = 0; t.f.n_begin = h->n_begin; t.f.n_end = h->n_end; t.f.D = nb;
         t.f.with_e0 = 1; t.f.eobs_const = h->eobs_const;
         t.ticket = h->tickets + h->L + 1;
@@ -907,8 +925,21 @@ extern "C" int mfvgp_ecost_host_packed(mfvgp_handle *h, const double *x_h, int w
             cudaGetLastError();
         if (direct) {
             double *buf_d = static_cast<double *>(attr.devicePointer);
-            rc = mfvgp_ecost(h, h->x_dev, want_grad, buf_d + nx, buf_d,
-                             reinterpret_cast<int32_t *>(buf_d + nx + 4), h->stream);
+            // optimistic (while flagged intervals are rare): no refine_kernel launch; the
+            // status word comes back with the result
+            const bool optimistic = h->opt_cooldown == 0;
+            rc = ecost_impl(h, h->x_dev, want_grad, buf_d + nx, buf_d,
+                            reinterpret_cast<int32_t *>(buf_d + nx + 4), h->stream, optimistic);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(h->stream));
+            int32_t st0;
+            memcpy(&st0, buf_h + nx + 4, sizeof(st0));
+            if (st0 & MFVGP_ST_REFINED) h->opt_cooldown = 16;
+            else if (h->opt_cooldown > 0) h->opt_cooldown--;
+            if (!optimistic || !(st0 & MFVGP_ST_REFINED)) return MFVGP_OK;
+            // the guard flagged an interval: evaluate again, this time with the adaptive path
+            rc = ecost_impl(h, h->x_dev, want_grad, buf_d + nx, buf_d,
+                            reinterpret_cast<int32_t *>(buf_d + nx + 4), h->stream, false);
             if (rc) return rc;
         }
     }
@@ -1176,8 +1207,10 @@ struct ScgRun {
         status_or |= stt;
         return MFVGP_OK;
     }
-    int eval(const double *x, double *g) {
-        return mfvgp_ecost(h, x, 1, h->scg_scal + 4, g, h->status_ws, st);
+    // optimistic: without the refine_kernel launch (small problems); the caller checks
+    // MFVGP_ST_REFINED in the status it reads back and redoes the evaluation if it is set
+    int eval(const double *x, double *g, bool optimistic = false) {
+        return ecost_impl(h, x, 1, h->scg_scal + 4, g, h->status_ws, st, optimistic);
     }
     int direction(double *d, const double *g, double gamma, int restart) {
         CK(launch_pdl(scg_direction_kernel, dim3(h->scg_nblk), kRedBlock, st, d, g, gamma, restart,
@@ -1194,21 +1227,21 @@ struct ScgRun {
     // update, sigma step, theta, alpha step, trial statistics -- sigma and alpha stay on the
     // device (FoldArgs modes 1-3); the host reads ONE record at the end instead of three.
     int chain(double *d, const double *g, double gamma, int restart, double beta, double *x,
-              double *xt, double *gp, double *gnow) {
+              double *xt, double *gp, double *gnow, bool optimistic) {
         const double *ctrl = h->scg_scal + 16;
         CK(launch_pdl(scg_direction_kernel, dim3(h->scg_nblk), kRedBlock, st, d, g, gamma, restart,
                       n, h->scg_part, fold_args(1)));
         h->launches++;
         int rc = axpy(xt, x, d, 0.0, ctrl + 0);
         if (rc) return rc;
-        rc = eval(xt, gp);
+        rc = eval(xt, gp, optimistic);
         if (rc) return rc;
         CK(launch_pdl(scg_theta_kernel, dim3(h->scg_nblk), kRedBlock, st, (const double *)d,
                       (const double *)gp, g, n, h->scg_part, fold_args(2, beta)));
         h->launches++;
         rc = axpy(xt, x, d, 0.0, ctrl + 1);
         if (rc) return rc;
-        rc = eval(xt, gnow);
+        rc = eval(xt, gnow, optimistic);
         if (rc) return rc;
         CK(launch_pdl(scg_stats_kernel, dim3(h->scg_nblk), kRedBlock, st, (const double *)gnow, g,
                       (const double *)d, n, h->scg_part, fold_args(3)));
@@ -1324,6 +1357,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     if (failed) { nit = 0; fx = f_now; }
 
     bool chained = false;          // a speculative chain for this iteration is in flight
+    bool chain_optimistic = false; // ... whose evaluations ran without the refine_kernel launch
     double alpha = 0.0;
     for (int j = 0; j < max_it && !done; ++j) {                   // :186
         bool have_stats = false;
@@ -1333,9 +1367,14 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
             RC(R.read16(r16));
             const int flags = (int)r16[15];
             mu = r16[9]; kappa = r16[10];
-            if (flags & 1) {
-                // mu >= 0 (:194-197): rare; the chain's results are void, redo the iteration
-                // on the step-by-step path below (it restarts the direction first)
+            const bool flagged = (((int32_t)r16[11] | (int32_t)r16[8]) & MFVGP_ST_REFINED) != 0;
+            if (flagged) h->opt_cooldown = 16;
+            else if (h->opt_cooldown > 0) h->opt_cooldown--;
+            if ((flags & 1) || ((flags & 2) == 0 && flagged && chain_optimistic)) {
+                // mu >= 0 (:194-197), or the guard flagged an interval in one of the chain's
+                // optimistic evaluations (no refine_kernel): rare; the chain's results are void,
+                // redo the iteration on the step-by-step path below (which restarts the
+                // direction first if mu >= 0 and evaluates with the adaptive path)
             } else if (flags & 2) {                               // :203
                 fx = f_now; nit = j + 1; done = true; break;
             } else {
@@ -1418,7 +1457,8 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         if (count_success == n_total) {
             count_success = 0;
             if (spec) {
-                RC(R.chain(d, gnew, 0.0, 1, beta, x, xt, gp, gnow));
+                chain_optimistic = h->opt_cooldown == 0;
+                RC(R.chain(d, gnew, 0.0, 1, beta, x, xt, gp, gnow, chain_optimistic));
                 chained = true;
             } else {
                 RC(R.direction(d, gnew, 0.0, 1));
@@ -1428,7 +1468,8 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         } else if (success) {
             const double gamma = fmax(prnum / mu, 0.0);
             if (spec) {
-                RC(R.chain(d, gnew, gamma, 0, beta, x, xt, gp, gnow));
+                chain_optimistic = h->opt_cooldown == 0;
+                RC(R.chain(d, gnew, gamma, 0, beta, x, xt, gp, gnow, chain_optimistic));
                 chained = true;
             } else {
                 RC(R.direction(d, gnew, gamma, 0));
