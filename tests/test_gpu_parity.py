@@ -278,3 +278,20 @@ def test_integration_stub_of_the_docs():
     lib.mfvgp_last_error.restype = ctypes.c_char_p
     assert b"not called" in lib.mfvgp_last_error()
     assert lib.mfvgp_destroy(h) == 0 and lib.mfvgp_destroy(h2) == 0
+
+
+def test_single_observed_dimension_and_scalar_noise():
+    """d = 1: obs_values may come as a 1-D array and obs_noise as a scalar (free_energy.py:136-147)."""
+    g = synthetic_l96(12, 5, seed=4)
+    mask = [False] * 12
+    mask[7] = True
+    g["obs_mask"] = mask
+    g["obs_values"] = g["obs_values"][:, 0].copy()          # shape (M,)
+    g["obs_noise"] = np.array(1.7)
+    fe = make_free_energy(g)
+    F, grad = fe.E_cost(g["x0"])
+    g2 = dict(g)
+    g2["obs_values"] = g["obs_values"].reshape(-1, 1)
+    g2["obs_noise"] = np.array([1.7])
+    Fo, go = make_oracle(g2, adaptive=True).E_cost(g["x0"])
+    assert abs(F - Fo) <= RTOL * abs(Fo) and rel_err(grad, go) <= RTOL
