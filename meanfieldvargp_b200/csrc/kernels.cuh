@@ -427,8 +427,7 @@ esde_l96_split_kernel(const EsdeArgs a) {
 // node; each thread evaluates all dimensions at its node, the 42 node values
 // are then summed in scipy's order (panel 1 then panel 2, r = 0..20).
 // ---------------------------------------------------------------------------
-// write_mask: bit 0 dm_out, bit 1 ds_out (esde_small_inkernel runs two CTAs per interval
-// that each own one of the two outputs); slot = row of `part` to write
+// write_mask: bit 0 dm_out, bit 1 ds_out; slot = row of `part` to write (default: the CTA's)
 template <int SYS>
 __device__ __forceinline__ void esde_small_body(const EsdeArgs &a, int write_mask = 3,
                                                 int slot = -1) {
@@ -725,7 +724,7 @@ struct FinalArgs {
     int32_t *info;            // [L][2] bisection counts: zeroed here when nothing was flagged and
                               //        refine_kernel may not have been launched (or nullptr)
     int record9;              // out has 9 slots (multi-GPU record)
-    int n_begin, n_end, D;    // D = number of apart rows (state dims, or CTAs of the fused kernel)
+    int n_begin, n_end, D;    // D = number of apart rows (state dims, or CTAs of the walk / tail kernel)
     int with_e0;
     double eobs_const;        // M (d log 2pi + safe_log(prod R)), 0 on non-owning shards
 };

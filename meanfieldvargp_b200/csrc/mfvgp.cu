@@ -205,7 +205,7 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         }
     }
     if (system != MFVGP_SYS_L96) {
-        // DW / OU / L63: guard + adaptive path inside esde_small_inkernel, one-launch tail
+        // DW / OU / L63: guard inside esde_small_inkernel, refine_kernel, one-launch tail
         const char *coop_env = getenv("MFVGP_COOP");
         h->coop = (coop_env && coop_env[0] == '0') ? 0 : 1;
         if (h->coop)

@@ -45,7 +45,7 @@ struct RefineArgs {
     double *ds_out;            // [L][D][3] overwritten for refined dS integrals (or nullptr)
     double *ws;                // [gridDim.x][2][D*kMaxNE] scratch: elementwise integral, and
                                // (delta mode) the fixed-rule value s1+s2 of the first bisection
-    int delta_mode;            // 1: ds_out receives (refined - fixed rule), for the fused E_cost path
+    int delta_mode;            // 1: ds_out receives (refined - fixed rule), for the walk path (gradient already assembled)
     int32_t *info;             // [L][2] number of bisections done (0 = not refined)
     int32_t *status;           // OR-ed MFVGP_ST_REFINE_LIMIT
     int D, n_begin, n_end, log_vars, want_grad;
@@ -182,7 +182,7 @@ template <> struct RowEval<2> : RowEvalDense<2> {};
 // are dealt round-robin over the group's threads; every reduction of the scalar control loop
 // goes through global memory -- each CTA's partial, a group barrier, then every CTA folds the
 // G partials in rank order -- so all CTAs see identical scalars and run quad_vec's heap logic
-// redundantly, in lock step, with no leader.  G = 1 (the in-kernel callers) costs nothing.
+// redundantly, in lock step, with no leader.  G = 1 (tiny problems) costs nothing.
 struct GroupCtx {
     int G, rank;               // CTAs in the group, this CTA's rank
     double *part;              // [2][G][8] partial sums (double buffered by the barrier count)
