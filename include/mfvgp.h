@@ -207,6 +207,22 @@ int mfvgp_l96_trajectory(int D, double theta, double dt, int dim_t, int nburn, d
                          const double *ek_td_d, double *x_out_d, int32_t *status_h,
                          void *cuda_stream);
 
+/*
+ * Double-well, Ornstein-Uhlenbeck and Lorenz 63 sample paths: DoubleWell.make_trajectory
+ * (src/dynamical_systems/double_well.py:40-91), OrnsteinUhlenbeck.make_trajectory
+ * (ornstein_uhlenbeck.py:38-79), Lorenz63.make_trajectory (lorenz_63.py:102-181).
+ * npaths independent paths per call (one thread each): x0_d [npaths][dims] is the state
+ * before the burn-in (nburn Euler steps of size delta_t; the reference: 5000 x 1e-3 for
+ * L63, none for DW / OU), ek_d [npaths][dim_t][dims] the noise increments (row 0 unused),
+ * x_out_d [npaths][dim_t][dims]; dims = 1 (DW, OU) or 3 (L63).  theta_h: DW (theta),
+ * OU (theta, mu), L63 (sigma, rho, beta).  Bit-identical to the reference's arithmetic.
+ * status_h [npaths]: bit 0 = NaN after the burn-in, bit 1 = NaN drift on the path.
+ */
+int mfvgp_small_trajectory(int sys, const double *theta_h, int ntheta, double dt, int dim_t,
+                           int nburn, double delta_t, int npaths, const double *x0_d,
+                           const double *ek_d, double *x_out_d, int32_t *status_h,
+                           void *cuda_stream);
+
 /* Which kernels this handle runs, as text ("system=L96 path=walk te=128 tn=32
  * ntiles=68 nruns=128 ..."): for benchmark reports and logs.  Returns the
  * length written (excluding the terminating 0).                            */

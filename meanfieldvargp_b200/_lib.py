@@ -47,6 +47,8 @@ SIGNATURES = {
     "mfvgp_reconstruct_host": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P]),
     "mfvgp_l96_trajectory": (c_int, [c_int, c_double, c_double, c_int, c_int, c_double, _P, _P,
                                      POINTER(c_int32), c_void_p]),
+    "mfvgp_small_trajectory": (c_int, [c_int, _P, c_int, c_double, c_int, c_int, c_double, c_int,
+                                       _P, _P, _P, _P, c_void_p]),
     "mfvgp_describe": (c_int, [c_void_p, c_char_p, c_int]),
     "mfvgp_refine_info": (c_int, [c_void_p, _P]),
     "mfvgp_timing": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_int64)]),

@@ -1614,3 +1614,37 @@ extern "C" int mfvgp_l96_trajectory(int D, double theta, double dt, int dim_t, i
     if (a.scratch) CK(cudaFreeAsync(a.scratch, st));
     return MFVGP_OK;
 }
+
+// ---- DW / OU / L63 sample paths, npaths independent ones per call ----------------------------
+template <int SYS>
+static void launch_small_trajectory(const SmallTrajArgs &a, cudaStream_t st) {
+    small_trajectory_kernel<SYS><<<(a.npaths + 127) / 128, 128, 0, st>>>(a);
+}
+
+extern "C" int mfvgp_small_trajectory(int sys, const double *theta_h, int ntheta, double dt,
+                                      int dim_t, int nburn, double delta_t, int npaths,
+                                      const double *x0_d, const double *ek_d, double *x_out_d,
+                                      int32_t *status_h, void *cuda_stream) {
+    ARG(theta_h && x0_d && ek_d && x_out_d && status_h, "mfvgp_small_trajectory: NULL argument");
+    ARG(sys == MFVGP_SYS_DW || sys == MFVGP_SYS_OU || sys == MFVGP_SYS_L63,
+        "mfvgp_small_trajectory: system must be DW, OU or L63");
+    const int want = sys == MFVGP_SYS_DW ? 1 : sys == MFVGP_SYS_OU ? 2 : 3;
+    ARG(ntheta == want, "mfvgp_small_trajectory: wrong number of drift parameters");
+    ARG(dim_t >= 1 && nburn >= 0 && npaths >= 1, "mfvgp_small_trajectory: bad counts");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    SmallTrajArgs a;
+    a.x0 = x0_d; a.ek = ek_d; a.x_out = x_out_d;
+    for (int k = 0; k < 3; ++k) a.theta[k] = k < ntheta ? theta_h[k] : 0.0;
+    a.dt = dt; a.delta_t = delta_t; a.npaths = npaths; a.dim_t = dim_t; a.nburn = nburn;
+    int32_t *status_d = nullptr;
+    CK(cudaMallocAsync((void **)&status_d, (size_t)npaths * sizeof(int32_t), st));
+    a.status = status_d;
+    if (sys == MFVGP_SYS_DW) launch_small_trajectory<0>(a, st);
+    else if (sys == MFVGP_SYS_OU) launch_small_trajectory<1>(a, st);
+    else launch_small_trajectory<2>(a, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(status_h, status_d, (size_t)npaths * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFreeAsync(status_d, st));
+    return MFVGP_OK;
+}

@@ -7,12 +7,13 @@ of the reference's system classes:
   Lorenz63(sigma, theta, r_seed)            lorenz_63.py:42-90
   Lorenz96(sigma, theta, dim_D, r_seed)     lorenz_96.py:42-101
 
-Only what the free-energy path reads is kept (``theta``, ``sigma``,
-``time_window``; stochastic_process.py:58-182).  The energy / gradient
-expressions themselves live in the CUDA kernels (csrc/drift.cuh,
-csrc/kernels.cuh); trajectory simulation is out of scope.
-A reference system object can be passed to ``FreeEnergy`` directly: the
-kernel is selected from the class name.
+What the free-energy path reads is kept (``theta``, ``sigma``, ``time_window``;
+stochastic_process.py:58-182), plus the data-generation step either side of it
+(SURVEY.md 8f-3): ``make_trajectory`` / ``collect_obs`` / ``sample_path`` with the
+reference's signatures, simulated on the device (``trajectory.py``) and stored as numpy
+arrays like the reference's.  The energy / gradient expressions themselves live in the
+CUDA kernels (csrc/drift.cuh, csrc/kernels.cuh).  A reference system object can be
+passed to ``FreeEnergy`` directly: the kernel is selected from the class name.
 """
 import numpy as np
 
@@ -75,6 +76,33 @@ class StochasticProcess(object):
     def rng(self):
         return self._rng
 
+    # stochastic_process.py:130-156
+    @property
+    def sample_path(self):
+        if self.xt is None:
+            raise NotImplementedError(f" {self.__class__.__name__}:"
+                                      f" Sample path has not been created.")
+        return self.xt
+
+    @sample_path.setter
+    def sample_path(self, new_value):
+        self.xt = new_value
+
+    def _store_path(self, tk, x):
+        self.sample_path = x.cpu().numpy()
+        self.time_window = tk.cpu().numpy()
+
+    def collect_obs(self, n_obs, h_mask=None):
+        """stochastic_process.py:211-297 (``trajectory.collect_obs`` on the stored path)."""
+        from .trajectory import collect_obs
+        if (self.tk is None) or (self.xt is None):
+            raise NotImplementedError(f" {self.__class__.__name__}:"
+                                      f" Sample path (or time window) have not been created.")
+        if len(self.tk) != len(self.xt):
+            raise RuntimeError(f" {self.__class__.__name__}:"
+                               f" Sample path and time window do not have the same length.")
+        return collect_obs(self.tk, self.xt, n_obs, h_mask, owner=self.__class__.__name__)
+
 
 class DoubleWell(StochasticProcess):
     system = "DW"
@@ -84,6 +112,11 @@ class DoubleWell(StochasticProcess):
         self.sigma = sigma
         self.theta = theta
 
+    def make_trajectory(self, t0, tf, dt=0.01):
+        """double_well.py:40-91, on the device; draws from ``self.rng`` in the reference's order."""
+        from .trajectory import simulate_dw
+        self._store_path(*simulate_dw(self.sigma, self.theta, t0, tf, dt, rng=self.rng))
+
 
 class OrnsteinUhlenbeck(StochasticProcess):
     system = "OU"
@@ -92,6 +125,11 @@ class OrnsteinUhlenbeck(StochasticProcess):
         super().__init__(r_seed=r_seed)
         self.sigma = sigma
         self.theta = theta
+
+    def make_trajectory(self, t0, tf, dt=0.01):
+        """ornstein_uhlenbeck.py:38-79, on the device."""
+        from .trajectory import simulate_ou
+        self._store_path(*simulate_ou(self.sigma, self.theta, t0, tf, dt, rng=self.rng))
 
 
 def _diag_sigma(cls_name, sigma, dim):
@@ -119,6 +157,11 @@ class Lorenz63(StochasticProcess):
                                f" {theta} is not [3 x 1].")
         self.theta = theta
 
+    def make_trajectory(self, t0, tf, dt=0.01):
+        """lorenz_63.py:102-181, on the device."""
+        from .trajectory import simulate_l63
+        self._store_path(*simulate_l63(self.sigma, self.theta, t0, tf, dt, rng=self.rng))
+
 
 class Lorenz96(StochasticProcess):
     system = "L96"
@@ -131,6 +174,13 @@ class Lorenz96(StochasticProcess):
         self.dim_D = int(dim_D)
         self.sigma = _diag_sigma(self.__class__.__name__, sigma, self.dim_D)
         self.theta = np.asarray(theta, dtype=float)
+
+    def make_trajectory(self, t0, tf, dt=0.01):
+        """lorenz_96.py:103-185, on the device."""
+        from .trajectory import simulate_l96, time_window
+        noise = self.rng.standard_normal((self.dim_D, time_window(t0, tf, dt).size))     # :159-162
+        self._store_path(*simulate_l96(self.sigma, float(self.theta[0]), self.dim_D, t0, tf, dt,
+                                       noise=noise))
 
 
 _BY_CLASS_NAME = {"DoubleWell": "DW", "OrnsteinUhlenbeck": "OU",
