@@ -1,5 +1,6 @@
 // C ABI (include/mfvgp.h) over the kernels in kernels.cuh / scg.cuh.
 // Pure CUDA runtime: no torch types cross this boundary.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -436,6 +437,21 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, unsigned block,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// one thread-block cluster of `nctas` CTAs (the whole grid), programmatic dependent launch
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster(void (*kern)(KArgs...), unsigned nctas, unsigned block,
+                                  cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nctas); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
@@ -1148,23 +1164,87 @@ extern "C" int mfvgp_fp64_peak(int device, double *tflops_out) {
 // ---- scaled conjugate gradient (scaled_cg.py:107-386) -----------------------
 namespace {
 
+// can this device co-schedule a 16-CTA cluster of the 512-thread SCG kernels?  (opt-in cluster
+// size; asked once per device, the kernels are marked on the way)
+static bool scg_cluster16_ok(int device) {
+    static std::map<int, bool> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(device);
+    if (it != cache.end()) return it->second;
+    bool ok = !(getenv("MFVGP_SCG_CLUSTER16") && getenv("MFVGP_SCG_CLUSTER16")[0] == '0');
+    const void *kerns[4] = {(const void *)scg_cl_direction_kernel<512>,
+                            (const void *)scg_cl_theta_kernel<512>,
+                            (const void *)scg_cl_stats_kernel<512>,
+                            (const void *)scg_cl_stats_direction_kernel<512>};
+    for (int i = 0; i < 4 && ok; ++i) {
+        if (cudaFuncSetAttribute(kerns[i], cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+            cudaSuccess) { ok = false; break; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16); cfg.blockDim = dim3(512);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kerns[i], &cfg) != cudaSuccess ||
+            nclusters < 1)
+            ok = false;
+    }
+    if (!ok) cudaGetLastError();
+    cache[device] = ok;
+    return ok;
+}
+
 struct ScgRun {
     mfvgp_handle *h;
     cudaStream_t st;
     VecMap n;          // index map of this rank's part of x (named n: it replaces the length)
     int status_or = 0;
     bool fused = false;          // single GPU: folds in the producers, host-mapped record
+    int cl_ctas = 0;             // > 0: the vector fits one thread-block cluster (scg.cuh)
+    int cl_nt = 1024;            // ... of CTAs this wide (512 with 16-CTA clusters)
+    // cluster path: the statistics kernel that closes a chain is held back until the host knows
+    // whether the next chain's head is enqueued right behind it (then ONE launch does both)
+    struct {
+        bool on = false;
+        const double *gnow = nullptr, *g = nullptr, *d = nullptr;
+        FoldArgs f3;
+    } pend;
+    int flush_stats() {
+        if (!pend.on) return MFVGP_OK;
+        pend.on = false;
+        CK(launch_cluster(cl_nt == 512 ? scg_cl_stats_kernel<512> : scg_cl_stats_kernel<1024>, cl_ctas, cl_nt, st, pend.gnow, pend.g, pend.d,
+                          clvec(), pend.f3));
+        h->launches++;
+        return MFVGP_OK;
+    }
+    ClVec clvec(const double *x = nullptr, double *xt = nullptr) const {
+        ClVec cv;
+        cv.n = (int)n.n; cv.x = x; cv.xt = xt;
+        return cv;
+    }
 
+    long long last_epoch = 0;    // epoch of the last publishing kernel enqueued
+    // the host-mapped record has two slots (epoch & 1): a chain enqueued ahead of its
+    // predecessor's outcome publishes while the host may still be reading the predecessor's
+    double *rec_slot(long long epoch) const { return h->scg_hostrec + 32 * (epoch & 1); }
     FoldArgs fold_args(int mode = 0, double beta_in = 0.0) {
         FoldArgs fa;
         fa.mode = mode; fa.ctrl = h->scg_scal + 16; fa.beta_in = beta_in;
         fa.ticket = nullptr; fa.scal = h->scg_scal; fa.status = h->status_ws;
         fa.host_rec = h->scg_hostrec_dev;
-        fa.host_flag = reinterpret_cast<volatile long long *>(h->scg_hostrec_dev + 16);
+        fa.host_flag = reinterpret_cast<volatile long long *>(h->scg_hostrec_dev + 24);
         fa.epoch = 0;
+        fa.spec = 0; fa.decide = 0; fa.refined_mask = 0;
+        fa.f_old_in = fa.x_tol = fa.f_tol = 0.0;
         if (fused) {
             fa.ticket = h->tickets + h->L;
-            if (mode == 0 || mode == 3) fa.epoch = ++h->scg_epoch;    // only these publish
+            if (mode == 0 || mode == 3) {                             // only these publish
+                fa.epoch = last_epoch = ++h->scg_epoch;
+                fa.host_rec = h->scg_hostrec_dev + 32 * (fa.epoch & 1);
+                fa.host_flag = reinterpret_cast<volatile long long *>(fa.host_rec + 24);
+            }
         }
         return fa;
     }
@@ -1177,24 +1257,41 @@ struct ScgRun {
         if (h->world > 1) return combine_over_ranks(h, h->scg_scal, 4, 3, h->scg_scal, nullptr, st);
         return MFVGP_OK;
     }
+    // waits until the kernel that publishes `epoch` has written its record
+    double t_wait = 0.0, t_chain = 0.0;   // host seconds spent spinning / enqueueing (MFVGP_SCG_TRACE)
+    long n_chain = 0, n_void = 0;
+    int wait_record(long long epoch, const double **rec) {
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc = wait_record_(epoch, rec);
+        t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return rc;
+    }
+    int wait_record_(long long epoch, const double **rec) {
+        const double *slot = rec_slot(epoch);
+        volatile const long long *flag = reinterpret_cast<volatile const long long *>(slot + 24);
+        long spins = 0;
+        while (*flag != epoch) {
+            if ((++spins & 0xfffff) == 0) {                 // a faulted kernel never publishes
+                cudaError_t q = cudaStreamQuery(st);
+                if (q != cudaSuccess && q != cudaErrorNotReady) {
+                    g_err = std::string("mfvgp_scg: ") + cudaGetErrorString(q);
+                    return MFVGP_ERR_CUDA;
+                }
+            }
+        }
+        __sync_synchronize();
+        *rec = slot;
+        return MFVGP_OK;
+    }
     // reads scal[0..3] (fold output), scal[4..7] (E_cost output) and the status
     int read(double *s8) {
         if (fused) {
             // the last reduction kernel publishes the record and then the epoch
-            volatile long long *flag = reinterpret_cast<volatile long long *>(h->scg_hostrec + 16);
-            long spins = 0;
-            while (*flag != h->scg_epoch) {
-                if ((++spins & 0xfffff) == 0) {             // a faulted kernel never publishes
-                    cudaError_t q = cudaStreamQuery(st);
-                    if (q != cudaSuccess && q != cudaErrorNotReady) {
-                        g_err = std::string("mfvgp_scg: ") + cudaGetErrorString(q);
-                        return MFVGP_ERR_CUDA;
-                    }
-                }
-            }
-            __sync_synchronize();
-            memcpy(s8, h->scg_hostrec, 8 * sizeof(double));
-            status_or |= (int32_t)h->scg_hostrec[8];
+            const double *rec;
+            int rc = wait_record(last_epoch, &rec);
+            if (rc) return rc;
+            memcpy(s8, rec, 8 * sizeof(double));
+            status_or |= (int32_t)rec[8];
             return MFVGP_OK;
         }
         CK(cudaMemcpyAsync(h->pin, h->scg_scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1213,65 +1310,123 @@ struct ScgRun {
         return ecost_impl(h, x, 1, h->scg_scal + 4, g, h->status_ws, st, optimistic);
     }
     int direction(double *d, const double *g, double gamma, int restart) {
+        if (cl_ctas) {
+            CK(launch_cluster(cl_nt == 512 ? scg_cl_direction_kernel<512> : scg_cl_direction_kernel<1024>, cl_ctas, cl_nt, st, d, g, gamma, restart,
+                              clvec(), fold_args()));
+            h->launches++;
+            return MFVGP_OK;
+        }
         CK(launch_pdl(scg_direction_kernel, dim3(h->scg_nblk), kRedBlock, st, d, g, gamma, restart,
                       n, h->scg_part, fold_args()));
         h->launches++;
         return fold();
     }
-    int axpy(double *y, const double *x, const double *d, double a, const double *a_dev = nullptr) {
-        CK(launch_pdl(scg_axpy_kernel, dim3(h->scg_nblk), kRedBlock, st, y, x, d, a, a_dev, n));
+    int axpy(double *y, const double *x, const double *d, double a, const double *a_dev = nullptr,
+             const double *void_flag = nullptr) {
+        CK(launch_pdl(scg_axpy_kernel, dim3(h->scg_nblk), kRedBlock, st, y, x, d, a, a_dev,
+                      void_flag, n));
         h->launches++;
         return MFVGP_OK;
     }
     // One successful iteration enqueued in one go (scaled_cg.py:192-247 + :361-369): direction
     // update, sigma step, theta, alpha step, trial statistics -- sigma and alpha stay on the
     // device (FoldArgs modes 1-3); the host reads ONE record at the end instead of three.
+    // The stats kernel also takes the accept / continue decision (FoldArgs::decide), which lets
+    // the host enqueue the chain of iteration j+1 BEFORE it has read the record of iteration j
+    // (spec = true: gamma, beta and f_old come from the device, a void flag stops the chain
+    // if iteration j ends any other way than "accepted, carry on").
     int chain(double *d, const double *g, double gamma, int restart, double beta, double *x,
-              double *xt, double *gp, double *gnow, bool optimistic) {
+              double *xt, double *gp, double *gnow, bool optimistic, bool spec, double f_old,
+              double x_tol, double f_tol) {
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc = chain_(d, g, gamma, restart, beta, x, xt, gp, gnow, optimistic, spec, f_old, x_tol,
+                        f_tol);
+        t_chain += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        n_chain++;
+        return rc;
+    }
+    int chain_(double *d, const double *g, double gamma, int restart, double beta, double *x,
+               double *xt, double *gp, double *gnow, bool optimistic, bool spec, double f_old,
+               double x_tol, double f_tol) {
         const double *ctrl = h->scg_scal + 16;
+        const double *vflag = spec ? ctrl + 10 : nullptr;
+        if (cl_ctas) {
+            // direction + sigma step, [evaluation], theta + alpha step, [evaluation]; the
+            // statistics wait (pend) for the head of the next chain to join them, or flush_stats()
+            FoldArgs f1 = fold_args(1), f2 = fold_args(2, beta);
+            f1.spec = f2.spec = spec;
+            if (spec && pend.on) {
+                pend.on = false;
+                CK(launch_cluster(cl_nt == 512 ? scg_cl_stats_direction_kernel<512> : scg_cl_stats_direction_kernel<1024>, cl_ctas, cl_nt, st, pend.gnow,
+                                  pend.g, d, restart, clvec(x, xt), pend.f3, f1));
+            } else {
+                int rc = flush_stats();
+                if (rc) return rc;
+                CK(launch_cluster(cl_nt == 512 ? scg_cl_direction_kernel<512> : scg_cl_direction_kernel<1024>, cl_ctas, cl_nt, st, d, g, gamma,
+                                  restart, clvec(x, xt), f1));
+            }
+            h->launches++;
+            int rc = eval(xt, gp, optimistic);
+            if (rc) return rc;
+            CK(launch_cluster(cl_nt == 512 ? scg_cl_theta_kernel<512> : scg_cl_theta_kernel<1024>, cl_ctas, cl_nt, st, (const double *)d,
+                              (const double *)gp, g, clvec(x, xt), f2));
+            h->launches++;
+            rc = eval(xt, gnow, optimistic);
+            if (rc) return rc;
+            pend.f3 = fold_args(3);
+            pend.f3.spec = spec; pend.f3.decide = 1;
+            pend.f3.refined_mask = optimistic ? MFVGP_ST_REFINED : 0;
+            pend.f3.f_old_in = f_old; pend.f3.x_tol = x_tol; pend.f3.f_tol = f_tol;
+            pend.gnow = gnow; pend.g = g; pend.d = d;
+            pend.on = true;
+            return MFVGP_OK;
+        }
+        FoldArgs f1 = fold_args(1);
+        f1.spec = spec;
         CK(launch_pdl(scg_direction_kernel, dim3(h->scg_nblk), kRedBlock, st, d, g, gamma, restart,
-                      n, h->scg_part, fold_args(1)));
+                      n, h->scg_part, f1));
         h->launches++;
-        int rc = axpy(xt, x, d, 0.0, ctrl + 0);
+        int rc = axpy(xt, x, d, 0.0, ctrl + 0, vflag);
         if (rc) return rc;
         rc = eval(xt, gp, optimistic);
         if (rc) return rc;
+        FoldArgs f2 = fold_args(2, beta);
+        f2.spec = spec;
         CK(launch_pdl(scg_theta_kernel, dim3(h->scg_nblk), kRedBlock, st, (const double *)d,
-                      (const double *)gp, g, n, h->scg_part, fold_args(2, beta)));
+                      (const double *)gp, g, n, h->scg_part, f2));
         h->launches++;
-        rc = axpy(xt, x, d, 0.0, ctrl + 1);
+        rc = axpy(xt, x, d, 0.0, ctrl + 1, vflag);
         if (rc) return rc;
         rc = eval(xt, gnow, optimistic);
         if (rc) return rc;
+        FoldArgs f3 = fold_args(3);
+        f3.spec = spec; f3.decide = 1;
+        f3.refined_mask = optimistic ? MFVGP_ST_REFINED : 0;
+        f3.f_old_in = f_old; f3.x_tol = x_tol; f3.f_tol = f_tol;
         CK(launch_pdl(scg_stats_kernel, dim3(h->scg_nblk), kRedBlock, st, (const double *)gnow, g,
-                      (const double *)d, n, h->scg_part, fold_args(3)));
+                      (const double *)d, n, h->scg_part, f3));
         h->launches++;
         return MFVGP_OK;
     }
-    // waits for the record of the last publishing kernel; rec16 = host_rec[0..15]
-    int read16(double *rec16) {
-        volatile long long *flag = reinterpret_cast<volatile long long *>(h->scg_hostrec + 16);
-        long spins = 0;
-        while (*flag != h->scg_epoch) {
-            if ((++spins & 0xfffff) == 0) {
-                cudaError_t q = cudaStreamQuery(st);
-                if (q != cudaSuccess && q != cudaErrorNotReady) {
-                    g_err = std::string("mfvgp_scg: ") + cudaGetErrorString(q);
-                    return MFVGP_ERR_CUDA;
-                }
-            }
-        }
-        __sync_synchronize();
-        memcpy(rec16, h->scg_hostrec, 16 * sizeof(double));
-        return MFVGP_OK;
-    }
     int theta(const double *d, const double *gp, const double *g) {
+        if (cl_ctas) {
+            CK(launch_cluster(cl_nt == 512 ? scg_cl_theta_kernel<512> : scg_cl_theta_kernel<1024>, cl_ctas, cl_nt, st, d, gp, g, clvec(),
+                              fold_args()));
+            h->launches++;
+            return MFVGP_OK;
+        }
         CK(launch_pdl(scg_theta_kernel, dim3(h->scg_nblk), kRedBlock, st, d, gp, g, n,
                       h->scg_part, fold_args()));
         h->launches++;
         return fold();
     }
     int stats(const double *g_now, const double *g_new, const double *d) {
+        if (cl_ctas) {
+            CK(launch_cluster(cl_nt == 512 ? scg_cl_stats_kernel<512> : scg_cl_stats_kernel<1024>, cl_ctas, cl_nt, st, g_now, g_new, d, clvec(),
+                              fold_args()));
+            h->launches++;
+            return MFVGP_OK;
+        }
         CK(launch_pdl(scg_stats_kernel, dim3(h->scg_nblk), kRedBlock, st, g_now, g_new, d, n,
                       h->scg_part, fold_args()));
         h->launches++;
@@ -1319,14 +1474,22 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
             return MFVGP_ERR_CUDA;
     }
     if (!h->scg_hostrec) {
-        CK(cudaHostAlloc((void **)&h->scg_hostrec, 32 * sizeof(double), cudaHostAllocMapped));
-        memset(h->scg_hostrec, 0, 32 * sizeof(double));
+        CK(cudaHostAlloc((void **)&h->scg_hostrec, 64 * sizeof(double), cudaHostAllocMapped));
+        memset(h->scg_hostrec, 0, 64 * sizeof(double));
         CK(cudaHostGetDevicePointer((void **)&h->scg_hostrec_dev, h->scg_hostrec, 0));
     }
     ScgRun R{h, st, vm};
     {
         const char *e = getenv("MFVGP_SCG_FUSED");
         R.fused = h->world == 1 && !(e && e[0] == '0');
+        const char *c = getenv("MFVGP_SCG_CLUSTER");
+        if (R.fused && n <= kClMaxElems && !(c && c[0] == '0')) {
+            const bool wide = scg_cluster16_ok(h->device);
+            R.cl_nt = wide ? 512 : 1024;
+            const int max_ctas = wide ? 16 : 8;
+            int64_t want = (n + 4 * R.cl_nt - 1) / (4 * R.cl_nt);
+            R.cl_ctas = (int)(want < 1 ? 1 : want > max_ctas ? max_ctas : want);
+        }
     }
     double *x = h->scg_vec[0], *xt = h->scg_vec[1], *d = h->scg_vec[2];
     double *gnew = h->scg_vec[3], *gold = h->scg_vec[4], *gnow = h->scg_vec[5];
@@ -1358,13 +1521,40 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
 
     bool chained = false;          // a speculative chain for this iteration is in flight
     bool chain_optimistic = false; // ... whose evaluations ran without the refine_kernel launch
+    long long chain_epoch = 0;     // ... and publishes its record under this epoch
+    // pipelining: while the chain of iteration j runs, the chain of iteration j+1 is enqueued
+    // behind it on the assumption that j is accepted and carries on (the device takes the
+    // decision and voids the chain otherwise); only after a run of clean accepted iterations
+    bool ahead = false, ahead_optimistic = false, ahead_valid = false;
+    long long ahead_epoch = 0;
+    int clean_run = 0;
+    bool pipeline = R.fused;
+    {
+        const char *e = getenv("MFVGP_SCG_PIPELINE");
+        if (e && e[0] == '0') pipeline = false;
+    }
     double alpha = 0.0;
     for (int j = 0; j < max_it && !done; ++j) {                   // :186
         bool have_stats = false;
         if (chained) {
             chained = false;
+            ahead = false;
+            if (pipeline && clean_run >= 2 && j + 1 < max_it) {
+                // roles after an accepted iteration j: x <-> xt, (gold, gnew, gnow) rotate
+                const int restart1 = count_success + 1 == n_total;
+                ahead_optimistic = h->opt_cooldown == 0;
+                RC(R.chain(d, gnow, 0.0, restart1, 0.0, xt, x, gp, gold, ahead_optimistic, true,
+                           0.0, x_tol, f_tol));
+                ahead_epoch = R.last_epoch;
+                ahead = true;
+            } else {
+                RC(R.flush_stats());
+            }
+            const double *rec;
+            RC(R.wait_record(chain_epoch, &rec));
             double r16[16];
-            RC(R.read16(r16));
+            memcpy(r16, rec, 16 * sizeof(double));
+            ahead_valid = ahead && rec[17] != 0.0;
             const int flags = (int)r16[15];
             mu = r16[9]; kappa = r16[10];
             const bool flagged = (((int32_t)r16[11] | (int32_t)r16[8]) & MFVGP_ST_REFINED) != 0;
@@ -1422,6 +1612,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         const double f_new = s8[4], sa_now = s8[0], gg = s8[1], prnum = s8[2], maxd = s8[3];
         const double Delta = 2.0 * (f_new - f_old) / (alpha * mu);   // :253
         double total_grad;
+        clean_run = (have_stats && Delta >= 0.0) ? clean_run + 1 : 0;
         if (Delta >= 0.0) {
             success = true;
             count_success++;
@@ -1454,11 +1645,29 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         // :361-369 -- the new direction; on one GPU it opens the speculative chain of the
         // next iteration (direction, sigma step, theta, alpha step, statistics: one host read)
         const bool spec = R.fused && success && j + 1 < max_it;
+        if (ahead) {
+            // the device took the decision above from the same numbers: it must agree
+            ahead = false;
+            if (ahead_valid != (spec && have_stats)) {
+                g_err = "mfvgp_scg: host and device disagree on the outcome of an iteration";
+                return MFVGP_ERR_STATE;
+            }
+            if (ahead_valid) {                                    // iteration j+1 is already running
+                if (count_success == n_total) count_success = 0;
+                chained = true;
+                chain_optimistic = ahead_optimistic;
+                chain_epoch = ahead_epoch;
+                continue;
+            }
+            R.pend.on = false;      // the void chain's statistics would only publish "void"
+        }
         if (count_success == n_total) {
             count_success = 0;
             if (spec) {
                 chain_optimistic = h->opt_cooldown == 0;
-                RC(R.chain(d, gnew, 0.0, 1, beta, x, xt, gp, gnow, chain_optimistic));
+                RC(R.chain(d, gnew, 0.0, 1, beta, x, xt, gp, gnow, chain_optimistic, false, f_old,
+                           x_tol, f_tol));
+                chain_epoch = R.last_epoch;
                 chained = true;
             } else {
                 RC(R.direction(d, gnew, 0.0, 1));
@@ -1469,7 +1678,9 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
             const double gamma = fmax(prnum / mu, 0.0);
             if (spec) {
                 chain_optimistic = h->opt_cooldown == 0;
-                RC(R.chain(d, gnew, gamma, 0, beta, x, xt, gp, gnow, chain_optimistic));
+                RC(R.chain(d, gnew, gamma, 0, beta, x, xt, gp, gnow, chain_optimistic, false,
+                           f_old, x_tol, f_tol));
+                chain_epoch = R.last_epoch;
                 chained = true;
             } else {
                 RC(R.direction(d, gnew, gamma, 0));
@@ -1479,6 +1690,10 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         }
     }
     if (!done) fx = f_old;                                        // :379
+    if (getenv("MFVGP_SCG_TRACE"))
+        fprintf(stderr, "mfvgp_scg: nit=%d chains=%ld (%.1f us host enqueue each), record waits "
+                        "%.1f us per iteration\n", nit, R.n_chain,
+                R.n_chain ? 1e6 * R.t_chain / R.n_chain : 0.0, nit ? 1e6 * R.t_wait / nit : 0.0);
     CK(cudaMemcpyAsync(x_d, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
     result_h[0] = fx;

@@ -37,11 +37,27 @@ struct FoldArgs {
     // sigma = 1e-3/sqrt(kappa) (scaled_cg.py:203-212) -> ctrl.  mode 2 (theta): theta, delta,
     // beta, alpha (:228-239) -> ctrl.  mode 3 (stats): publish sums + ctrl.  ctrl [16]:
     // 0 sigma, 1 alpha, 2 theta, 3 delta, 4 beta, 5 mu, 6 kappa, 7 flags (1: mu >= 0,
-    // 2: kappa < eps), 8 status of the sigma-step evaluation.
+    // 2: kappa < eps), 8 status of the sigma-step evaluation, 9 f_old, 10 void flag,
+    // 11 gamma and 12 beta for the chain that follows (decide, below).
     int mode;
     double *ctrl;
     double beta_in;
+    // Pipelined chains: the stats kernel of a chain also takes the accept / continue decision
+    // (scaled_cg.py:253-369) in the host's arithmetic -- Delta, the two termination tests, the
+    // beta update, gamma for the next direction -- so the host can enqueue the NEXT iteration's
+    // chain before it has read this one's record (spec = 1: gamma, beta, f_old come from ctrl).
+    // If the decision is anything but "accepted, carry on", ctrl[10] voids that next chain: its
+    // vector kernels return at once (x, d untouched) and its stats kernel publishes a void
+    // record.  The host takes the same decision from the same numbers and checks the flag.
+    int spec;                  // this chain was enqueued ahead of its predecessor's outcome
+    int decide;                // mode 3: take the decision
+    int refined_mask;          // status bits that void an optimistic chain (0 if not optimistic)
+    double f_old_in, x_tol, f_tol;
 };
+
+__device__ __forceinline__ bool chain_is_void(const FoldArgs &fa) {
+    return fa.spec && __ldcg(fa.ctrl + 10) != 0.0;
+}
 
 // Index map of the optimisation vector a rank works on.  Single GPU: the whole
 // x.  Sharded: the rank's active columns of the mean block [D][Nm] and of the
@@ -111,6 +127,117 @@ __device__ __forceinline__ void fold_partials(const double *part, int nblk, doub
     }
 }
 
+// scaled_cg.py:228-239 from the folded d.(g+ - g): theta, delta, beta and the step alpha
+__device__ __forceinline__ double chain_alpha(double dot, const FoldArgs &fa, double &theta,
+                                              double &delta, double &beta) {
+    const double *c = fa.ctrl;
+    const double sigma = __ldcg(c + 0), mu = __ldcg(c + 5), kappa = __ldcg(c + 6);
+    theta = dot / sigma;
+    beta = fa.spec ? __ldcg(c + 12) : fa.beta_in;      // 12: written by the previous chain's decision
+    delta = __dadd_rn(theta, __dmul_rn(beta, kappa));
+    if (delta <= 0.0) {
+        delta = __dmul_rn(beta, kappa);
+        beta = __dsub_rn(beta, theta / kappa);
+    }
+    return -(mu / delta);
+}
+
+// The accept / continue decision at the end of a chain (scaled_cg.py:253-369, the host's
+// operations).  stats_decide_calc only reads: 1 if the trial point is accepted and the run
+// carries on, with f_old, gamma and beta for the next chain in nxt[0..2].  stats_decide_commit
+// leaves them in ctrl[9], [11], [12] and sets / clears the void flag ctrl[10].
+__device__ __forceinline__ double stats_decide_calc(const double (&r)[kRedSlots],
+                                                    const FoldArgs &fa, double (&nxt)[3]) {
+    nxt[0] = nxt[1] = nxt[2] = 0.0;
+    if (!fa.decide) return 0.0;
+    const double *c = fa.ctrl;
+    const double f_new = __ldcg(fa.scal + 4);
+    const int stt = (int)__ldcg(fa.status) | (int)__ldcg(c + 8);
+    const double alpha = __ldcg(c + 1), mu = __ldcg(c + 5), flags = __ldcg(c + 7);
+    double beta = __ldcg(c + 4);
+    const double f_old = fa.spec ? __ldcg(c + 9) : fa.f_old_in;
+    if (flags != 0.0 || (stt & 7) != 0 || (stt & fa.refined_mask) != 0) return 0.0;
+    const double Delta = __ddiv_rn(__dmul_rn(2.0, __dsub_rn(f_new, f_old)),
+                                   __dmul_rn(alpha, mu));                       // :253
+    const bool stop = (__dmul_rn(fabs(alpha), r[3]) <= fa.x_tol &&
+                       fabs(__dsub_rn(f_new, f_old)) <= fa.f_tol) ||             // :306
+                      fabs(r[1]) <= 1.0e-8;                                       // :333
+    if (!(Delta >= 0.0) || stop) return 0.0;
+    if (Delta < 0.25) beta = fmin(__dmul_rn(4.0, beta), 1.0e100);                 // :350-356
+    if (Delta > 0.75) beta = fmax(__dmul_rn(0.5, beta), 1.0e-15);
+    nxt[0] = f_new;
+    nxt[1] = fmax(__ddiv_rn(r[2], mu), 0.0);                                      // :367
+    nxt[2] = beta;
+    return 1.0;
+}
+__device__ __forceinline__ void stats_decide_commit(double carry_on, const double (&nxt)[3],
+                                                    const FoldArgs &fa) {
+    if (!fa.decide) return;
+    double *c = fa.ctrl;
+    if (carry_on != 0.0) { c[9] = nxt[0]; c[11] = nxt[1]; c[12] = nxt[2]; }
+    c[10] = carry_on != 0.0 ? 0.0 : 1.0;
+}
+
+// the host record (without the epoch flag that makes it visible)
+constexpr int kRecLen = 18;
+// one warp publishes a staged record: one coalesced store of the kRecLen values into the
+// host-mapped slot, system fence, epoch flag -- beside the rest of the kernel, not in its way
+__device__ __forceinline__ void publish_record(const double *staged, const FoldArgs &fa) {
+    const int lane = threadIdx.x & 31;
+    if (lane < kRecLen) fa.host_rec[lane] = staged[lane];
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) *fa.host_flag = fa.epoch;
+}
+__device__ __forceinline__ void stats_record_to(double *rec, const double (&r)[kRedSlots],
+                                                double carry_on, const FoldArgs &fa) {
+    const double *c = fa.ctrl;
+#pragma unroll
+    for (int i = 0; i < kRedSlots; ++i) rec[i] = r[i];
+#pragma unroll
+    for (int i = 4; i < 8; ++i) rec[i] = __ldcg(fa.scal + i);
+    rec[8] = (double)__ldcg(fa.status);
+    if (fa.mode == 3) {
+        rec[9] = c[5]; rec[10] = c[6]; rec[11] = c[8];
+        rec[12] = c[2]; rec[13] = c[1]; rec[14] = c[4];
+        rec[15] = c[7];
+        rec[16] = 0.0;                         // not a void chain
+        rec[17] = carry_on;
+    }
+}
+__device__ __forceinline__ void stats_record(const double (&r)[kRedSlots], double carry_on,
+                                             const FoldArgs &fa) {
+    stats_record_to(fa.host_rec, r, carry_on, fa);
+}
+
+// What one thread does with the folded sums r (grid path: thread 0 of the last block; cluster
+// path: thread 0 of CTA 0): store them, then -- by mode -- the chain scalars or the host record.
+__device__ __forceinline__ void fold_finish(const double (&r)[kRedSlots], const FoldArgs &fa) {
+#pragma unroll
+    for (int i = 0; i < kRedSlots; ++i) fa.scal[i] = r[i];
+    double *c = fa.ctrl;
+    if (fa.mode == 1) {                    // the host's arithmetic, operation for operation
+        const double mu = r[0], kappa = r[1];
+        c[5] = mu; c[6] = kappa;
+        c[7] = (mu >= 0.0 ? 1.0 : 0.0) + (kappa < 2.220446049250313e-16 ? 2.0 : 0.0);
+        c[0] = 1.0e-3 / sqrt(kappa);
+        return;
+    }
+    if (fa.mode == 2) {
+        double theta, delta, beta;
+        c[1] = chain_alpha(r[0], fa, theta, delta, beta);
+        c[2] = theta; c[3] = delta; c[4] = beta;
+        c[8] = (double)__ldcg(fa.status);
+        return;
+    }
+    double nxt[3], carry_on = 0.0;
+    if (fa.mode == 3) carry_on = stats_decide_calc(r, fa, nxt);
+    stats_record(r, carry_on, fa);
+    if (fa.mode == 3) stats_decide_commit(carry_on, nxt, fa);
+    __threadfence_system();
+    *fa.host_flag = fa.epoch;
+}
+
 __device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part,
                                           const FoldArgs &fa) {
     __shared__ double sh[kRedSlots][kRedBlock / 32];
@@ -147,43 +274,7 @@ __device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part,
     __threadfence();
     double r[kRedSlots];
     fold_partials(part, (int)gridDim.x, r, sh);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < kRedSlots; ++i) fa.scal[i] = r[i];
-        double *c = fa.ctrl;
-        if (fa.mode == 1) {                    // the host's arithmetic, operation for operation
-            const double mu = r[0], kappa = r[1];
-            c[5] = mu; c[6] = kappa;
-            c[7] = (mu >= 0.0 ? 1.0 : 0.0) + (kappa < 2.220446049250313e-16 ? 2.0 : 0.0);
-            c[0] = 1.0e-3 / sqrt(kappa);
-            return;
-        }
-        if (fa.mode == 2) {
-            const double sigma = c[0], mu = c[5], kappa = c[6];
-            const double theta = r[0] / sigma;
-            double beta = fa.beta_in;
-            double delta = __dadd_rn(theta, __dmul_rn(beta, kappa));
-            if (delta <= 0.0) {
-                delta = __dmul_rn(beta, kappa);
-                beta = __dsub_rn(beta, theta / kappa);
-            }
-            c[1] = -(mu / delta); c[2] = theta; c[3] = delta; c[4] = beta;
-            c[8] = (double)__ldcg(fa.status);
-            return;
-        }
-#pragma unroll
-        for (int i = 0; i < kRedSlots; ++i) fa.host_rec[i] = r[i];
-#pragma unroll
-        for (int i = 4; i < 8; ++i) fa.host_rec[i] = __ldcg(fa.scal + i);
-        fa.host_rec[8] = (double)__ldcg(fa.status);
-        if (fa.mode == 3) {
-            fa.host_rec[9] = c[5]; fa.host_rec[10] = c[6]; fa.host_rec[11] = c[8];
-            fa.host_rec[12] = c[2]; fa.host_rec[13] = c[1]; fa.host_rec[14] = c[4];
-            fa.host_rec[15] = c[7];
-        }
-        __threadfence_system();
-        *fa.host_flag = fa.epoch;
-    }
+    if (threadIdx.x == 0) fold_finish(r, fa);
 }
 
 // d = gamma*d - g (gamma = 0 and d arbitrary gives the restart d = -g);
@@ -193,6 +284,10 @@ scg_direction_kernel(double *d, const double *g, double gamma, int restart, cons
                      double *part, const FoldArgs fa) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
     scg_pdl_enter();
+    if (fa.spec) {
+        if (chain_is_void(fa)) return;
+        gamma = __ldcg(fa.ctrl + 11);
+    }
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
          t += (int64_t)gridDim.x * blockDim.x) {
         bool own;
@@ -211,8 +306,9 @@ scg_direction_kernel(double *d, const double *g, double gamma, int restart, cons
 // y = x + a*d                                   (scaled_cg.py:222, :242)
 __global__ void __launch_bounds__(kRedBlock)
 scg_axpy_kernel(double *y, const double *x, const double *d, double a, const double *a_dev,
-                const VecMap vm) {
+                const double *void_flag, const VecMap vm) {
     scg_pdl_enter();
+    if (void_flag != nullptr && __ldcg(void_flag) != 0.0) return;    // void chain: y untouched
     if (a_dev != nullptr) a = __ldcg(a_dev);      // step length computed on the device
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -228,6 +324,7 @@ scg_theta_kernel(const double *d, const double *gp, const double *g, const VecMa
                  double *part, const FoldArgs fa) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
     scg_pdl_enter();
+    if (chain_is_void(fa)) return;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
          t += (int64_t)gridDim.x * blockDim.x) {
         bool own;
@@ -246,6 +343,15 @@ scg_stats_kernel(const double *g_now, const double *g_new, const double *d, cons
                  double *part, const FoldArgs fa) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
     scg_pdl_enter();
+    if (chain_is_void(fa)) {                      // nothing was computed: say so and stop
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            fa.host_rec[16] = 1.0;
+            fa.host_rec[17] = 0.0;
+            __threadfence_system();
+            *fa.host_flag = fa.epoch;
+        }
+        return;
+    }
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
          t += (int64_t)gridDim.x * blockDim.x) {
         bool own;
@@ -258,6 +364,309 @@ scg_stats_kernel(const double *g_now, const double *g_new, const double *d, cons
         v[3] = fmax(v[3], fabs(d[i]));
     }
     red_store(v, part, fa);
+}
+
+// ---- cluster path: the whole vector in ONE thread-block cluster ------------------------------
+// Up to kClMaxElems entries (every notebook size incl. the north-star L96-500: 43 500) fit the
+// registers of one cluster of <= 8 CTAs x 1024 threads.  Then the grid-wide dependency that
+// forces "reduce, then a second kernel for the step" disappears: the block sums cross the
+// cluster through distributed shared memory (every CTA stores its four sums into every CTA's
+// table, ONE cluster barrier, every CTA folds the table in rank order -- fixed order, identical
+// bits in all CTAs, no global partials, no fence, no atomic ticket), and the same kernel goes on
+// to take the step with d still in registers:
+//   scg_cl_direction_kernel : d = gamma d - g, mu, kappa, sigma, then xt = x + sigma d
+//   scg_cl_theta_kernel     : d.(g+ - g), theta / delta / beta / alpha, then xt = x + alpha d
+//   scg_cl_stats_kernel     : trial statistics + the accept / continue decision + host record
+// One SCG iteration is 3 vector launches + 2 evaluations instead of 5 + 2.
+// Two shapes: 16 CTAs x 512 threads where the device schedules 16-CTA clusters (opt-in size;
+// twice the SMs pulling the vectors out of L2, half the shuffles per SM), else 8 x 1024.
+constexpr int kClPerThread = 8;
+constexpr int kClMaxCtas = 16;
+constexpr int64_t kClMaxElems = 8 * 1024 * kClPerThread;
+
+__device__ __forceinline__ unsigned cl_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cl_size() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\t"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cl_store_remote(double *local, unsigned rank, double v) {
+    unsigned la = (unsigned)__cvta_generic_to_shared(local), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
+// v (per-thread) -> r (cluster totals, in every thread of every CTA): slots 0..2 summed, 3 max'ed
+// (round: a kernel that reduces twice uses a fresh table for the second round, because a fast
+// CTA may deliver its second-round sums while a slow one still folds the first table)
+template <int NT>
+__device__ __forceinline__ void cl_reduce(double (&v)[kRedSlots], double (&r)[kRedSlots],
+                                          int round = 0) {
+    __shared__ double sh_w[kRedSlots][32];
+    __shared__ double sh_tabs[2][kClMaxCtas][kRedSlots];
+    double (*sh_tab)[kRedSlots] = sh_tabs[round];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = warp_sum_d(v[i]);
+    v[3] = warp_max_d(v[3]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) sh_w[i][w] = v[i];
+    __syncthreads();
+    const unsigned nc = cl_size(), me = cl_rank();
+    if (w == 0) {
+        double b[kRedSlots];
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) b[i] = lane < NT / 32 ? sh_w[i][lane] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) b[i] = warp_sum_d(b[i]);
+        b[3] = warp_max_d(b[3]);
+        // lane 0 holds this CTA's sums: lanes 0..nc-1 each deliver them to one CTA of the cluster
+#pragma unroll
+        for (int i = 0; i < kRedSlots; ++i) b[i] = __shfl_sync(0xffffffffu, b[i], 0);
+        if ((unsigned)lane < nc)
+#pragma unroll
+            for (int i = 0; i < kRedSlots; ++i) cl_store_remote(&sh_tab[me][i], (unsigned)lane, b[i]);
+    }
+    cl_sync();
+#pragma unroll
+    for (int i = 0; i < kRedSlots; ++i) r[i] = sh_tab[0][i];
+    for (unsigned k = 1; k < nc; ++k) {
+        r[0] += sh_tab[k][0]; r[1] += sh_tab[k][1]; r[2] += sh_tab[k][2];
+        r[3] = fmax(r[3], sh_tab[k][3]);
+    }
+}
+
+struct ClVec {
+    int n;                     // entries (<= kClMaxElems), identity index map (single GPU)
+    const double *x;           // step: xt = x + a d (nullptr: no step in this launch)
+    double *xt;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+scg_cl_direction_kernel(double *d, const double *g, double gamma, int restart, const ClVec cv,
+                        const FoldArgs fa) {
+    double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    double dreg[kClPerThread];
+    scg_pdl_enter();
+    if (fa.spec) {
+        if (chain_is_void(fa)) return;          // every CTA takes this exit: no barrier pending
+        gamma = __ldcg(fa.ctrl + 11);
+    }
+    const int T = (int)cl_size() * NT, t0 = (int)cl_rank() * NT + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kClPerThread; ++k) {
+        const int i = t0 + k * T;
+        dreg[k] = 0.0;
+        if (i < cv.n) {
+            const double gi = g[i];
+            const double di = restart ? -gi : gamma * d[i] - gi;
+            d[i] = di;
+            dreg[k] = di;
+            v[0] = fma(di, gi, v[0]);
+            v[1] = fma(di, di, v[1]);
+        }
+    }
+    double r[kRedSlots];
+    cl_reduce<NT>(v, r);
+    if (cl_rank() == 0 && threadIdx.x == 0) fold_finish(r, fa);
+    if (cv.x != nullptr) {                       // sigma step (scaled_cg.py:203-222)
+        const double sigma = 1.0e-3 / sqrt(r[1]);
+#pragma unroll
+        for (int k = 0; k < kClPerThread; ++k) {
+            const int i = t0 + k * T;
+            if (i < cv.n) cv.xt[i] = cv.x[i] + sigma * dreg[k];
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+scg_cl_theta_kernel(const double *d, const double *gp, const double *g, const ClVec cv,
+                    const FoldArgs fa) {
+    double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    double dreg[kClPerThread];
+    scg_pdl_enter();
+    if (chain_is_void(fa)) return;
+    const int T = (int)cl_size() * NT, t0 = (int)cl_rank() * NT + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kClPerThread; ++k) {
+        const int i = t0 + k * T;
+        dreg[k] = 0.0;
+        if (i < cv.n) {
+            dreg[k] = d[i];
+            v[0] = fma(dreg[k], gp[i] - g[i], v[0]);
+        }
+    }
+    double r[kRedSlots];
+    cl_reduce<NT>(v, r);
+    if (cl_rank() == 0 && threadIdx.x == 0) fold_finish(r, fa);
+    if (cv.x != nullptr) {                       // alpha step (scaled_cg.py:232-247)
+        double theta, delta, beta;
+        const double alpha = chain_alpha(r[0], fa, theta, delta, beta);
+#pragma unroll
+        for (int k = 0; k < kClPerThread; ++k) {
+            const int i = t0 + k * T;
+            if (i < cv.n) cv.xt[i] = cv.x[i] + alpha * dreg[k];
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+scg_cl_stats_kernel(const double *g_now, const double *g_new, const double *d, const ClVec cv,
+                    const FoldArgs fa) {
+    double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    scg_pdl_enter();
+    if (chain_is_void(fa)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            fa.host_rec[16] = 1.0;
+            fa.host_rec[17] = 0.0;
+            __threadfence_system();
+            *fa.host_flag = fa.epoch;
+        }
+        return;
+    }
+    const int T = (int)cl_size() * NT, t0 = (int)cl_rank() * NT + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kClPerThread; ++k) {
+        const int i = t0 + k * T;
+        if (i < cv.n) {
+            const double a = g_now[i];
+            v[0] += fabs(a);
+            v[1] = fma(a, a, v[1]);
+            v[2] = fma(a, g_new[i] - a, v[2]);
+            v[3] = fmax(v[3], fabs(d[i]));
+        }
+    }
+    double r[kRedSlots];
+    cl_reduce<NT>(v, r);
+    if (cl_rank() == 0 && threadIdx.x == 0) fold_finish(r, fa);
+}
+
+// Pipelined runs: the statistics + decision that close iteration j and the direction + sigma
+// step that open iteration j+1 in one launch (the gradient of the trial point is both the
+// g_now of the statistics and the g of the new direction, so it is loaded once).  CTA 0 decides,
+// the decision and gamma cross the cluster through distributed shared memory; if iteration j is
+// not "accepted, carry on" the kernel stops after the statistics and the rest of chain j+1 is
+// void (ctrl[10]).  fa3: the statistics' fold (mode 3, decide), fa1: the direction's (mode 1).
+template <int NT>
+__global__ void __launch_bounds__(NT)
+scg_cl_stats_direction_kernel(const double *g_now, const double *g_new, double *d, int restart_next,
+                              const ClVec cv, const FoldArgs fa3, const FoldArgs fa1) {
+    __shared__ double sh_dec[2];
+    __shared__ double sh_rec[kRecLen];      // the host record, staged (lead CTA)
+    double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
+    double dreg[kClPerThread], greg[kClPerThread];
+#ifdef MFVGP_PHASE_TRACE
+    unsigned long long tq[10];
+    int nq = 0;
+#define TQ() do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[nq])); ++nq; } while (0)
+    TQ();
+#else
+#define TQ() do { } while (0)
+#endif
+    scg_pdl_enter();
+    TQ();
+    const bool lead = cl_rank() == 0 && threadIdx.x == 0;
+    if (chain_is_void(fa3)) {
+        if (lead) {
+            fa3.host_rec[16] = 1.0;
+            fa3.host_rec[17] = 0.0;
+            __threadfence_system();
+            *fa3.host_flag = fa3.epoch;
+        }
+        return;
+    }
+    const int T = (int)cl_size() * NT, t0 = (int)cl_rank() * NT + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < kClPerThread; ++k) {
+        const int i = t0 + k * T;
+        dreg[k] = greg[k] = 0.0;
+        if (i < cv.n) {
+            const double a = g_now[i];
+            greg[k] = a;
+            dreg[k] = d[i];
+            v[0] += fabs(a);
+            v[1] = fma(a, a, v[1]);
+            v[2] = fma(a, g_new[i] - a, v[2]);
+            v[3] = fmax(v[3], fabs(dreg[k]));
+        }
+    }
+    double r[kRedSlots];
+    TQ();
+    cl_reduce<NT>(v, r, 0);
+    TQ();
+    // every CTA takes the decision from the same numbers (no broadcast across the cluster);
+    // the lead commits it only after the second reduction's barrier, when all have read ctrl
+    double nxt[3];
+    if (threadIdx.x == 0) {
+        const double carry = stats_decide_calc(r, fa3, nxt);
+        sh_dec[0] = carry;
+        sh_dec[1] = nxt[1];
+        if (lead) {
+#pragma unroll
+            for (int i = 0; i < kRedSlots; ++i) fa3.scal[i] = r[i];
+            stats_record_to(sh_rec, r, carry, fa3);  // published by warp 1 after the last barrier
+            if (carry == 0.0) stats_decide_commit(carry, nxt, fa3);
+        }
+    }
+    TQ();
+    __syncthreads();
+    TQ();
+    const bool carry_on = sh_dec[0] != 0.0;
+    if (carry_on) {
+        const double gamma = sh_dec[1];
+        v[0] = v[1] = v[2] = v[3] = 0.0;
+#pragma unroll
+        for (int k = 0; k < kClPerThread; ++k) {
+            const int i = t0 + k * T;
+            if (i < cv.n) {
+                const double gi = greg[k];
+                const double di = restart_next ? -gi : gamma * dreg[k] - gi;
+                d[i] = di;
+                dreg[k] = di;
+                v[0] = fma(di, gi, v[0]);
+                v[1] = fma(di, di, v[1]);
+            }
+        }
+        cl_reduce<NT>(v, r, 1);
+        TQ();
+        if (cl_rank() == 0 && (threadIdx.x >> 5) == 1) publish_record(sh_rec, fa3);
+        if (lead) {
+            stats_decide_commit(1.0, nxt, fa3);
+            fold_finish(r, fa1);
+        }
+        const double sigma = 1.0e-3 / sqrt(r[1]);
+#pragma unroll
+        for (int k = 0; k < kClPerThread; ++k) {
+            const int i = t0 + k * T;
+            if (i < cv.n) cv.xt[i] = cv.x[i] + sigma * dreg[k];
+        }
+        TQ();
+    } else if (cl_rank() == 0 && (threadIdx.x >> 5) == 1) {
+        publish_record(sh_rec, fa3);
+    }
+    if (lead) {
+        TQ();
+#ifdef MFVGP_PHASE_TRACE
+        if ((fa3.epoch & 15) == 0) {
+            printf("phase trace (ns since entry):");
+            for (int q = 1; q < nq; ++q) printf(" %llu", tq[q] - tq[0]);
+            printf("\n");
+        }
+#endif
+    }
+#undef TQ
 }
 
 // Second stage: one block folds the per-block partials in a fixed order.
