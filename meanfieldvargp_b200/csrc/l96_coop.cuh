@@ -28,6 +28,8 @@ struct CoopArgs {
     GuardArgs g;              // g.nflagged counts the flagged intervals for refine_kernel
     unsigned *tickets;        // [n_end - n_begin], zero between launches
     double theta;
+    int guard_later;          // optimistic evaluations: the tail kernel folds the tiles and applies
+                              // the guard in CTAs of its own (no ticket, no fold here)
 };
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
@@ -233,8 +235,9 @@ esde_l96_coop_kernel(const CoopArgs ca) {
         }
         const double x = (x0 + x1) + (x2 + x3);
         a.part[(int64_t)cta * kPartStride + tid] = x;
-        __threadfence();                           // the writers publish their partials
+        if (!ca.guard_later) __threadfence();      // the writers publish their partials
     }
+    if (ca.guard_later) return;
     // ---- last CTA of this interval: fold the tiles, apply the guard ---------------------------------
     __syncthreads();
     if (tid == 0) {
@@ -282,6 +285,9 @@ struct TailArgs {
     const double *y_dense;     // [M][D] observation of state dimension j at time k (0 if unobserved)
     const double *rinv_row;    // [D] 1 / obs_noise of dimension j, 0 if unobserved
     unsigned *ticket;          // [1], zero between launches
+    GuardArgs g;               // guard_ctas > 0: the last guard_ctas CTAs of the grid fold the
+    int guard_ctas;            // main kernel's tile partials and apply the guard, a warp per
+                               // interval, beside the CTAs that assemble the gradient
 };
 
 constexpr int kTailThreads = 256;
@@ -294,10 +300,17 @@ assemble_tail_kernel(const TailArgs t) {
     // small problems only: the element count fits 32 bits (mfvgp_create checks)
     const unsigned idx = blockIdx.x * kTailThreads + threadIdx.x;
     const unsigned nm = (unsigned)a.D * a.Nm, ntot = nm + (unsigned)a.D * a.Ns;
+    const bool guard_cta = blockIdx.x >= gridDim.x - (unsigned)t.guard_ctas;
     double acc[3] = {0.0, 0.0, 0.0};
     pdl_launch_dependents();
     if (idx >= ntot) pdl_wait();
-    if (idx < ntot) {
+    if (guard_cta) {
+        const int nwarps = t.guard_ctas * (kTailThreads / 32);
+        const int w = (int)(blockIdx.x - (gridDim.x - (unsigned)t.guard_ctas)) * (kTailThreads / 32)
+                      + (int)(threadIdx.x >> 5);
+        for (int n = t.g.n_begin + w; n < t.g.n_end; n += nwarps)
+            guard_interval(t.g, n, (int)(threadIdx.x & 31));
+    } else if (idx < ntot) {
         const bool is_mean = idx < nm;
         const unsigned r = is_mean ? idx : idx - nm;
         const unsigned W = is_mean ? a.Nm : a.Ns;
@@ -351,8 +364,10 @@ assemble_tail_kernel(const TailArgs t) {
     }
     block_sum<3, kTailThreads>(acc, sh_red);
     if (threadIdx.x == 0) {
-        double *p = a.apart + (int64_t)blockIdx.x * 4;
-        p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = 0.0;
+        if (!guard_cta) {
+            double *p = a.apart + (int64_t)blockIdx.x * 4;
+            p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = 0.0;
+        }
         __threadfence();
         const unsigned k = atomicAdd(t.ticket, 1u);
         sh_last = (k == gridDim.x - 1u);

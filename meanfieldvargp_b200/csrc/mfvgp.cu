@@ -52,6 +52,7 @@ struct mfvgp_handle {
     // optimistic evaluation (no refine_kernel launch) pays only while flagged intervals are rare:
     // after a flagged evaluation the next 16 are run with the adaptive path in the chain
     int opt_cooldown = 0;
+    bool guard_in_tail = true;   // MFVGP_GUARD_IN_TAIL=0: keep the guard in the main kernel
     double *y_dense = nullptr, *rinv_row = nullptr;   // row tables of assemble_tail_kernel
     int tail_grid = 1;
     double theta_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -200,6 +201,8 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         const char *coop_env = getenv("MFVGP_COOP");
         h->coop = (coop_env && coop_env[0] == '0') ? 0 : 1;
         if (h->coop) {
+            const char *git = getenv("MFVGP_GUARD_IN_TAIL");
+            h->guard_in_tail = !(git && git[0] == '0');
             h->te = kCoopTE;
             h->ntiles = (D + kCoopTE - 7) / (kCoopTE - 6);
             h->tail_grid = (int)(((int64_t)D * (h->Nm + h->Ns) + kTailThreads - 1) / kTailThreads);
@@ -503,7 +506,7 @@ static int launch_guard_refine(mfvgp_handle *h, const double *mean, int64_t ldm,
 
 static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const double *vars,
                        int64_t lds, int log_vars, double *dm, double *ds, cudaStream_t st,
-                       bool skip_refine = false) {
+                       bool skip_refine = false, bool guard_later = false) {
     EsdeArgs a;
     a.mean = mean; a.vars = vars; a.ldm = ldm; a.lds = lds;
     a.obs_times = h->obs_times; a.sigma = h->sigma; a.theta = h->theta;
@@ -525,6 +528,7 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
         c.g.ntiles = h->ntiles;
         c.g.nflagged = h->refine_status + 1;
         c.tickets = h->tickets; c.theta = h->theta_host[0];
+        c.guard_later = guard_later ? 1 : 0;
     }
     switch (h->system) {
         case MFVGP_SYS_DW:
@@ -814,8 +818,12 @@ static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double 
         return launch_final(h, h->fapart, h->fntn * h->fntiles, out_d, status_d, st,
                             want_grad ? grad_d : nullptr);
     }
+    // optimistic L96 evaluations: no refine launch, and the guard moves from the main kernel's
+    // last CTAs (ticket + fold on its critical path) into CTAs of the tail kernel
+    const bool opt = optimistic && h->coop && h->world == 1;
+    const bool guard_later = opt && h->system == MFVGP_SYS_L96 && h->guard_in_tail;
     rc = launch_esde(h, mean, h->Nm, lvar, h->Ns, 1, want_grad ? h->dm_ws : nullptr,
-                     want_grad ? h->ds_ws : nullptr, st, optimistic && h->coop && h->world == 1);
+                     want_grad ? h->ds_ws : nullptr, st, opt, guard_later);
     if (rc) return rc;
     AssembleArgs a;
     a.x = x_d; a.dm = want_grad ? h->dm_ws : nullptr; a.ds = want_grad ? h->ds_ws : nullptr;
@@ -837,7 +845,16 @@ static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double 
         t.f.record9 = 0; t.f.n_begin = h->n_begin; t.f.n_end = h->n_end; t.f.D = nb;
         t.f.with_e0 = 1; t.f.eobs_const = h->eobs_const;
         t.ticket = h->tickets + h->L + 1;
-        CK(launch_pdl(assemble_tail_kernel, dim3(nb), kTailThreads, st, t));
+        t.guard_ctas = 0;
+        if (guard_later) {
+            t.g.part = h->part; t.g.obs_times = h->obs_times; t.g.esde_n = h->esde_n;
+            t.g.flags = h->flags; t.g.n_begin = h->n_begin; t.g.n_end = h->n_end;
+            t.g.ntiles = h->ntiles; t.g.nflagged = h->refine_status + 1;
+            const int per_cta = kTailThreads / 32, nl = h->n_end - h->n_begin;
+            t.guard_ctas = (nl + per_cta - 1) / per_cta;
+            if (t.guard_ctas > 64) t.guard_ctas = 64;
+        }
+        CK(launch_pdl(assemble_tail_kernel, dim3(nb + t.guard_ctas), kTailThreads, st, t));
         h->launches++;
         CK(cudaGetLastError());
         return MFVGP_OK;
@@ -1529,9 +1546,11 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     long long ahead_epoch = 0;
     int clean_run = 0;
     bool pipeline = R.fused;
+    int clean_needed = 2;
     {
-        const char *e = getenv("MFVGP_SCG_PIPELINE");
+        const char *e = getenv("MFVGP_SCG_PIPELINE");       // 0: off, 2: after every chain (tests)
         if (e && e[0] == '0') pipeline = false;
+        if (e && e[0] == '2') clean_needed = 0;
     }
     double alpha = 0.0;
     for (int j = 0; j < max_it && !done; ++j) {                   // :186
@@ -1539,7 +1558,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         if (chained) {
             chained = false;
             ahead = false;
-            if (pipeline && clean_run >= 2 && j + 1 < max_it) {
+            if (pipeline && clean_run >= clean_needed && j + 1 < max_it) {
                 // roles after an accepted iteration j: x <-> xt, (gold, gnew, gnow) rotate
                 const int restart1 = count_success + 1 == n_total;
                 ahead_optimistic = h->opt_cooldown == 0;

@@ -52,3 +52,88 @@ def test_scg_decreases_energy_full_size():
     assert fx < F0
     hist = stats["fx"][:stats["nit"]]
     assert np.all(np.diff(hist) <= 1e-9 * abs(F0))
+
+
+# ---- pipelined chains, cluster kernels, guard in the tail kernel ---------------------------------
+ROUGH = {"rough_L63": ("L63_T5", 3, 2.5, 4), "rough_L96": ("L96_8", 8, 2.0, 1),
+         "rough_DW": ("DW", 1, 1.0, 3)}
+
+
+def _rough(case):
+    """Golden problems started from scattered log-variances (x0 + base N(0,1)): the quadratic
+    model of the sigma step is far off there and SCG REJECTS most trial points (Delta < 0,
+    scaled_cg.py:254-279).  The reference goldens never do (func_eval = 3 nit + 1 in all of them)
+    and sane starts never did in a search either; these starts are numerically wild (interpolated
+    variances near zero), so they pin the control flow -- rejected trial points void the chain
+    enqueued ahead, the step-by-step path takes over -- not values against the oracle."""
+    name, dims, base, seed = ROUGH[case]
+    g = dict(load_golden("scg", name))
+    n = g["x0"].size
+    nm = dims * (3 * int(g["obs_times"].size) + 4)
+    x0 = g["x0"].copy()
+    x0[nm:] = x0[nm:] + base * np.random.default_rng(seed).normal(0.0, 1.0, n - nm)
+    g["x0"] = x0
+    return g
+
+
+@pytest.mark.parametrize("case", ["L96_8", "L96_40", "rough_L63", "rough_L96", "rough_DW"])
+def test_scg_switches_agree(case, monkeypatch):
+    """pipelining on/off is bit-identical; cluster and grid reductions agree to rounding and take
+    the same branches"""
+    from helpers import synthetic_l96
+    rough = case.startswith("rough")
+    if rough:
+        g, iters = _rough(case), 40
+    elif case == "L96_40":
+        g, iters = synthetic_l96(40, 20, seed=5), 60
+    else:
+        g, iters = load_golden("scg", case), 15
+    res = {}
+    for pipe in ("0", "1", "2"):                  # 2: a chain is enqueued ahead after EVERY chain
+        for cl in ("0", "1"):
+            monkeypatch.setenv("MFVGP_SCG_PIPELINE", pipe)
+            monkeypatch.setenv("MFVGP_SCG_CLUSTER", cl)
+            fe = make_free_energy(g)
+            x, fx, st = fe.find_minimum(g["x0"].copy(), max_iter=iters)
+            res[pipe, cl] = (x, fx, st["nit"], st["func_eval"], st["fx"].copy())
+    for cl in ("0", "1"):
+        for pipe in ("1", "2"):
+            a, b = res["0", cl], res[pipe, cl]
+            assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2:4] == b[2:4]
+    if rough:                                     # there ARE rejected iterations
+        assert res["1", "1"][3] < 3 * res["1", "1"][2] + 1
+        return
+    a, b = res["1", "0"], res["1", "1"]
+    assert a[2:4] == b[2:4]
+    assert rel_err(a[4], b[4]) <= 1.0e-10 and rel_err(a[0], b[0]) <= 1.0e-8
+
+
+def test_scg_converges_with_a_chain_in_flight():
+    """loose tolerances: the run stops (scaled_cg.py:306) while the next chain is already
+    enqueued; that chain must be void and the result the accepted point"""
+    g = load_golden("scg", "L96_8")
+    xo, fxo, so = make_oracle(g, adaptive=False).find_minimum(g["x0"].copy(), max_iter=200,
+                                                              x_tol=5.0e-2, f_tol=5.0e-2)
+    assert so["nit"] < 200
+    fe = make_free_energy(g)
+    x, fx, st = fe.find_minimum(g["x0"].copy(), max_iter=200, x_tol=5.0e-2, f_tol=5.0e-2)
+    assert st["nit"] == so["nit"] and st["func_eval"] == so["func_eval"]
+    assert abs(fx - fxo) <= 1.0e-8 * abs(fxo) and rel_err(x, xo) <= 1.0e-6
+    F, _ = fe.E_cost(x)
+    assert abs(F - fx) <= 1.0e-12 * abs(fx)
+
+
+@pytest.mark.parametrize("name", ["L96_8", "L96_40", "L96_6_refine", "L96_500p"])
+def test_guard_in_tail_kernel_equals_guard_in_main_kernel(name, monkeypatch):
+    """optimistic evaluations (host buffers) fold the tile partials and apply the guard in CTAs of
+    the tail kernel instead of the main kernel's last CTAs: same bits, same flags"""
+    kind = "scg" if name == "L96_8" else "eval"
+    g = load_golden(kind, name)
+    x0 = g["x0"] if "x0" in g else g["x"]
+    out = {}
+    for v in ("0", "1"):
+        monkeypatch.setenv("MFVGP_GUARD_IN_TAIL", v)
+        fe = make_free_energy(g)
+        F, grad = fe.E_cost(np.array(x0, dtype=float))
+        out[v] = (F, grad.copy())
+    assert out["0"][0] == out["1"][0] and np.array_equal(out["0"][1], out["1"][1])
