@@ -407,7 +407,8 @@ __device__ __forceinline__ void cl_store_remote(double *local, unsigned rank, do
 // v (per-thread) -> r (cluster totals, in every thread of every CTA): slots 0..2 summed, 3 max'ed
 // (round: a kernel that reduces twice uses a fresh table for the second round, because a fast
 // CTA may deliver its second-round sums while a slow one still folds the first table)
-template <int NT>
+// NS: the first NS slots are live sums, MAXS: slot 3 (a max) is live; dead slots cost nothing
+template <int NT, int NS = 3, bool MAXS = true>
 __device__ __forceinline__ void cl_reduce(double (&v)[kRedSlots], double (&r)[kRedSlots],
                                           int round = 0) {
     __shared__ double sh_w[kRedSlots][32];
@@ -415,33 +416,37 @@ __device__ __forceinline__ void cl_reduce(double (&v)[kRedSlots], double (&r)[kR
     double (*sh_tab)[kRedSlots] = sh_tabs[round];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) v[i] = warp_sum_d(v[i]);
-    v[3] = warp_max_d(v[3]);
-    if (lane == 0)
+    for (int i = 0; i < NS; ++i) v[i] = warp_sum_d(v[i]);
+    if (MAXS) v[3] = warp_max_d(v[3]);
+    if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < kRedSlots; ++i) sh_w[i][w] = v[i];
+        for (int i = 0; i < NS; ++i) sh_w[i][w] = v[i];
+        if (MAXS) sh_w[3][w] = v[3];
+    }
     __syncthreads();
     const unsigned nc = cl_size(), me = cl_rank();
     if (w == 0) {
-        double b[kRedSlots];
+        double b[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int i = 0; i < kRedSlots; ++i) b[i] = lane < NT / 32 ? sh_w[i][lane] : 0.0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) b[i] = warp_sum_d(b[i]);
-        b[3] = warp_max_d(b[3]);
+        for (int i = 0; i < NS; ++i) b[i] = warp_sum_d(lane < NT / 32 ? sh_w[i][lane] : 0.0);
+        if (MAXS) b[3] = warp_max_d(lane < NT / 32 ? sh_w[3][lane] : 0.0);
         // lane 0 holds this CTA's sums: lanes 0..nc-1 each deliver them to one CTA of the cluster
 #pragma unroll
-        for (int i = 0; i < kRedSlots; ++i) b[i] = __shfl_sync(0xffffffffu, b[i], 0);
+        for (int i = 0; i < kRedSlots; ++i)
+            if (i < NS || (MAXS && i == 3)) b[i] = __shfl_sync(0xffffffffu, b[i], 0);
         if ((unsigned)lane < nc)
 #pragma unroll
-            for (int i = 0; i < kRedSlots; ++i) cl_store_remote(&sh_tab[me][i], (unsigned)lane, b[i]);
+            for (int i = 0; i < kRedSlots; ++i)
+                if (i < NS || (MAXS && i == 3))
+                    cl_store_remote(&sh_tab[me][i], (unsigned)lane, b[i]);
     }
     cl_sync();
 #pragma unroll
-    for (int i = 0; i < kRedSlots; ++i) r[i] = sh_tab[0][i];
+    for (int i = 0; i < kRedSlots; ++i) r[i] = (i < NS || (MAXS && i == 3)) ? sh_tab[0][i] : 0.0;
     for (unsigned k = 1; k < nc; ++k) {
-        r[0] += sh_tab[k][0]; r[1] += sh_tab[k][1]; r[2] += sh_tab[k][2];
-        r[3] = fmax(r[3], sh_tab[k][3]);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) r[i] += sh_tab[k][i];
+        if (MAXS) r[3] = fmax(r[3], sh_tab[k][3]);
     }
 }
 
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(NT)
 scg_cl_direction_kernel(double *d, const double *g, double gamma, int restart, const ClVec cv,
                         const FoldArgs fa) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
-    double dreg[kClPerThread];
+    double dreg[kClPerThread], xreg[kClPerThread];     // x rides along: no load after the reduction
     scg_pdl_enter();
     if (fa.spec) {
         if (chain_is_void(fa)) return;          // every CTA takes this exit: no barrier pending
@@ -466,8 +471,9 @@ scg_cl_direction_kernel(double *d, const double *g, double gamma, int restart, c
 #pragma unroll
     for (int k = 0; k < kClPerThread; ++k) {
         const int i = t0 + k * T;
-        dreg[k] = 0.0;
+        dreg[k] = xreg[k] = 0.0;
         if (i < cv.n) {
+            if (cv.x != nullptr) xreg[k] = cv.x[i];
             const double gi = g[i];
             const double di = restart ? -gi : gamma * d[i] - gi;
             d[i] = di;
@@ -477,14 +483,14 @@ scg_cl_direction_kernel(double *d, const double *g, double gamma, int restart, c
         }
     }
     double r[kRedSlots];
-    cl_reduce<NT>(v, r);
+    cl_reduce<NT, 2, false>(v, r);
     if (cl_rank() == 0 && threadIdx.x == 0) fold_finish(r, fa);
     if (cv.x != nullptr) {                       // sigma step (scaled_cg.py:203-222)
         const double sigma = 1.0e-3 / sqrt(r[1]);
 #pragma unroll
         for (int k = 0; k < kClPerThread; ++k) {
             const int i = t0 + k * T;
-            if (i < cv.n) cv.xt[i] = cv.x[i] + sigma * dreg[k];
+            if (i < cv.n) cv.xt[i] = xreg[k] + sigma * dreg[k];
         }
     }
 }
@@ -494,21 +500,22 @@ __global__ void __launch_bounds__(NT)
 scg_cl_theta_kernel(const double *d, const double *gp, const double *g, const ClVec cv,
                     const FoldArgs fa) {
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
-    double dreg[kClPerThread];
+    double dreg[kClPerThread], xreg[kClPerThread];
     scg_pdl_enter();
     if (chain_is_void(fa)) return;
     const int T = (int)cl_size() * NT, t0 = (int)cl_rank() * NT + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < kClPerThread; ++k) {
         const int i = t0 + k * T;
-        dreg[k] = 0.0;
+        dreg[k] = xreg[k] = 0.0;
         if (i < cv.n) {
+            if (cv.x != nullptr) xreg[k] = cv.x[i];
             dreg[k] = d[i];
             v[0] = fma(dreg[k], gp[i] - g[i], v[0]);
         }
     }
     double r[kRedSlots];
-    cl_reduce<NT>(v, r);
+    cl_reduce<NT, 1, false>(v, r);
     if (cl_rank() == 0 && threadIdx.x == 0) fold_finish(r, fa);
     if (cv.x != nullptr) {                       // alpha step (scaled_cg.py:232-247)
         double theta, delta, beta;
@@ -516,7 +523,7 @@ scg_cl_theta_kernel(const double *d, const double *gp, const double *g, const Cl
 #pragma unroll
         for (int k = 0; k < kClPerThread; ++k) {
             const int i = t0 + k * T;
-            if (i < cv.n) cv.xt[i] = cv.x[i] + alpha * dreg[k];
+            if (i < cv.n) cv.xt[i] = xreg[k] + alpha * dreg[k];
         }
     }
 }
@@ -549,7 +556,7 @@ scg_cl_stats_kernel(const double *g_now, const double *g_new, const double *d, c
         }
     }
     double r[kRedSlots];
-    cl_reduce<NT>(v, r);
+    cl_reduce<NT, 3, true>(v, r);
     if (cl_rank() == 0 && threadIdx.x == 0) fold_finish(r, fa);
 }
 
@@ -566,7 +573,7 @@ scg_cl_stats_direction_kernel(const double *g_now, const double *g_new, double *
     __shared__ double sh_dec[2];
     __shared__ double sh_rec[kRecLen];      // the host record, staged (lead CTA)
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
-    double dreg[kClPerThread], greg[kClPerThread];
+    double dreg[kClPerThread], greg[kClPerThread], xreg[kClPerThread];
 #ifdef MFVGP_PHASE_TRACE
     unsigned long long tq[10];
     int nq = 0;
@@ -591,8 +598,9 @@ scg_cl_stats_direction_kernel(const double *g_now, const double *g_new, double *
 #pragma unroll
     for (int k = 0; k < kClPerThread; ++k) {
         const int i = t0 + k * T;
-        dreg[k] = greg[k] = 0.0;
+        dreg[k] = greg[k] = xreg[k] = 0.0;
         if (i < cv.n) {
+            xreg[k] = cv.x[i];
             const double a = g_now[i];
             greg[k] = a;
             dreg[k] = d[i];
@@ -604,7 +612,7 @@ scg_cl_stats_direction_kernel(const double *g_now, const double *g_new, double *
     }
     double r[kRedSlots];
     TQ();
-    cl_reduce<NT>(v, r, 0);
+    cl_reduce<NT, 3, true>(v, r, 0);
     TQ();
     // every CTA takes the decision from the same numbers (no broadcast across the cluster);
     // the lead commits it only after the second reduction's barrier, when all have read ctrl
@@ -639,7 +647,7 @@ scg_cl_stats_direction_kernel(const double *g_now, const double *g_new, double *
                 v[1] = fma(di, di, v[1]);
             }
         }
-        cl_reduce<NT>(v, r, 1);
+        cl_reduce<NT, 2, false>(v, r, 1);
         TQ();
         if (cl_rank() == 0 && (threadIdx.x >> 5) == 1) publish_record(sh_rec, fa3);
         if (lead) {
@@ -650,7 +658,7 @@ scg_cl_stats_direction_kernel(const double *g_now, const double *g_new, double *
 #pragma unroll
         for (int k = 0; k < kClPerThread; ++k) {
             const int i = t0 + k * T;
-            if (i < cv.n) cv.xt[i] = cv.x[i] + sigma * dreg[k];
+            if (i < cv.n) cv.xt[i] = xreg[k] + sigma * dreg[k];
         }
         TQ();
     } else if (cl_rank() == 0 && (threadIdx.x >> 5) == 1) {
