@@ -427,13 +427,18 @@ extern "C" int mfvgp_set_obs(mfvgp_handle *h, const double *obs_times_h,
 // ---- launch helpers ---------------------------------------------------------
 // launch that may overlap the tail of its predecessor in the stream (the kernel calls
 // pdl_wait() before touching global data); MFVGP_PDL=0 falls back to a plain launch
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, unsigned block, cudaStream_t st,
-                              Args &&...args) {
+static bool pdl_enabled() {
     static const bool enabled = [] {
         const char *e = getenv("MFVGP_PDL");
         return !(e && e[0] == '0');
     }();
+    return enabled;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, unsigned block, cudaStream_t st,
+                              Args &&...args) {
+    const bool enabled = pdl_enabled();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -454,7 +459,7 @@ static cudaError_t launch_cluster(void (*kern)(KArgs...), unsigned nctas, unsign
     attr[0].val.clusterDim.x = nctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 2;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
