@@ -195,6 +195,18 @@ int mfvgp_reconstruct_host(int device, int D, int M, int num, const double *Tx_h
                            double *tt_h, double *mt_h, double *st_h);
 
 /*
+ * Batched evaluation: B independent states x_d [B][n] of the SAME problem in two launches
+ * (out_d [B][8]: F, E0, Esde, Eobs; grad_d [B][n]; status_d [B]).  Serves the n + 1 evaluations
+ * scipy.optimize.check_grad makes behind find_minimum(check_gradients=True)
+ * (src/var_bayes/free_energy.py:805, :858) and multi-start runs.  Lorenz 96 on the cooperative
+ * small-problem path, one GPU.  Fixed rule + guard only: an entry whose status has
+ * MFVGP_ST_REFINED set holds the fixed-rule value of a state on which quad_vec would bisect
+ * further -- re-evaluate it with mfvgp_ecost.  Workspaces grow to the largest B seen.
+ */
+int mfvgp_ecost_batch(mfvgp_handle *h, int B, const double *x_d, int want_grad, double *out_d,
+                      double *grad_d, int32_t *status_d, void *cuda_stream);
+
+/*
  * Lorenz 96 sample path: Lorenz96.make_trajectory
  * (src/dynamical_systems/lorenz_96.py:103-185) -- burn-in of nburn Euler steps of size
  * delta_t from x = theta (+0.01 at D/2), then dim_t - 1 Euler-Maruyama steps of size dt

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mfvgp_esde": (c_int, [c_void_p, _P, c_int64, _P, c_int64, c_int, _P, _P, _P, _P, c_void_p]),
     "mfvgp_ecost": (c_int, [c_void_p, _P, c_int, _P, _P, _P, c_void_p]),
     "mfvgp_esde_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P, _P, _P]),
+    "mfvgp_ecost_batch": (c_int, [c_void_p, c_int, _P, c_int, _P, _P, _P, c_void_p]),
     "mfvgp_ecost_host": (c_int, [c_void_p, _P, c_int, _P, _P, _P]),
     "mfvgp_ecost_host_packed": (c_int, [c_void_p, _P, c_int, _P]),
     "mfvgp_host_alloc": (c_void_p, [c_int64]),

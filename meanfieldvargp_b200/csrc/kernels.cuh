@@ -246,8 +246,7 @@ __device__ __forceinline__ double fast_rcp3(double x) {
 }
 
 template <int TE>
-__global__ void __launch_bounds__(TE, 640 / TE)
-esde_l96_split_kernel(const EsdeArgs a) {
+__device__ __forceinline__ void esde_l96_split_body(const EsdeArgs &a) {
     constexpr int TD = TE - 6;
     __shared__ double sh_m[TE], sh_s[TE];
     __shared__ double sh_A[TE], sh_B[TE], sh_C[TE], sh_Dv[TE];
@@ -419,6 +418,30 @@ esde_l96_split_kernel(const EsdeArgs a) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) p[i] = red[i];
     }
+}
+
+template <int TE>
+__global__ void __launch_bounds__(TE, 640 / TE)
+esde_l96_split_kernel(const EsdeArgs a) { esde_l96_split_body<TE>(a); }
+
+// Batched evaluation (mfvgp_ecost_batch): one of B independent states of the SAME problem per
+// blockIdx.y / blockIdx.z; every per-evaluation buffer is rebased by these strides (doubles).
+struct BatchStrides {
+    int64_t x, dm, ds, part;          // state / gradient, per-interval workspaces, tile partials
+    int64_t apart, esde_n, out;       // tail: partial rows, per-interval energies, [8] records
+};
+
+// one thread per cell: the throughput shape (the cooperative kernel's two lanes per cell and
+// 250 registers are for latency); used when the batch alone fills the GPU
+template <int TE>
+__global__ void __launch_bounds__(TE, 640 / TE)
+esde_l96_split_batch_kernel(const EsdeArgs a0, const BatchStrides bs) {
+    EsdeArgs a = a0;
+    const int64_t z = blockIdx.y;
+    a.mean += z * bs.x; a.vars += z * bs.x;
+    if (a.dm_out != nullptr) { a.dm_out += z * bs.dm; a.ds_out += z * bs.ds; }
+    a.part += z * bs.part;
+    esde_l96_split_body<TE>(a);
 }
 
 

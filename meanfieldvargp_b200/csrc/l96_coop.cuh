@@ -36,8 +36,7 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) {
     return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
-__global__ void __launch_bounds__(kCoopNT)
-esde_l96_coop_kernel(const CoopArgs ca) {
+__device__ __forceinline__ void esde_l96_coop_body(const CoopArgs &ca) {
     constexpr int TE = kCoopTE, TD = TE - 6;
     const EsdeArgs &a = ca.a;
     __shared__ double2 ms[kGL][TE], AC[kGL][TE], BD[kGL][TE];
@@ -255,6 +254,22 @@ esde_l96_coop_kernel(const CoopArgs ca) {
     }
 }
 
+__global__ void __launch_bounds__(kCoopNT)
+esde_l96_coop_kernel(const CoopArgs ca) { esde_l96_coop_body(ca); }
+
+// Batched evaluation (mfvgp_ecost_batch): blockIdx.z selects one of B independent states of the
+// SAME problem -- B x 300 CTAs instead of 300 at the north-star size, which is what it takes to
+// fill 148 SMs.  Always guard_later: the batched tail kernel folds the tiles.
+__global__ void __launch_bounds__(kCoopNT)
+esde_l96_coop_batch_kernel(const CoopArgs ca0, const BatchStrides bs) {
+    CoopArgs ca = ca0;
+    const int64_t z = blockIdx.z;
+    ca.a.mean += z * bs.x; ca.a.vars += z * bs.x;
+    if (ca.a.dm_out != nullptr) { ca.a.dm_out += z * bs.dm; ca.a.ds_out += z * bs.ds; }
+    ca.a.part += z * bs.part;
+    esde_l96_coop_body(ca);
+}
+
 // ---------------------------------------------------------------------------
 // DW / OU / L63: esde_small_kernel with the guard folded in (one CTA per interval owns the
 // whole interval, so no ticket is needed); flagged intervals go to refine_kernel.
@@ -292,25 +307,27 @@ struct TailArgs {
 
 constexpr int kTailThreads = 256;
 
-__global__ void __launch_bounds__(kTailThreads)
-assemble_tail_kernel(const TailArgs t) {
+__device__ __forceinline__ void assemble_tail_body(const TailArgs &t) {
     __shared__ double sh_red[3 * (kTailThreads / 32)];
     __shared__ int sh_last;
     const AssembleArgs &a = t.a;
     // small problems only: the element count fits 32 bits (mfvgp_create checks)
-    const unsigned idx = blockIdx.x * kTailThreads + threadIdx.x;
+    const unsigned idx0 = blockIdx.x * kTailThreads + threadIdx.x;
+    // one entry per thread (single evaluations: one memory round trip deep); batches whose main
+    // kernel already rounds differently launch a quarter of the CTAs and stride over the entries
+    const unsigned idx_step = (gridDim.x - (unsigned)t.guard_ctas) * kTailThreads;
     const unsigned nm = (unsigned)a.D * a.Nm, ntot = nm + (unsigned)a.D * a.Ns;
     const bool guard_cta = blockIdx.x >= gridDim.x - (unsigned)t.guard_ctas;
     double acc[3] = {0.0, 0.0, 0.0};
     pdl_launch_dependents();
-    if (idx >= ntot) pdl_wait();
+    if (idx0 >= ntot) pdl_wait();
     if (guard_cta) {
         const int nwarps = t.guard_ctas * (kTailThreads / 32);
         const int w = (int)(blockIdx.x - (gridDim.x - (unsigned)t.guard_ctas)) * (kTailThreads / 32)
                       + (int)(threadIdx.x >> 5);
         for (int n = t.g.n_begin + w; n < t.g.n_end; n += nwarps)
             guard_interval(t.g, n, (int)(threadIdx.x & 31));
-    } else if (idx < ntot) {
+    } else for (unsigned idx = idx0; idx < ntot; idx += idx_step) {
         const bool is_mean = idx < nm;
         const unsigned r = is_mean ? idx : idx - nm;
         const unsigned W = is_mean ? a.Nm : a.Ns;
@@ -378,6 +395,28 @@ assemble_tail_kernel(const TailArgs t) {
         __threadfence();
         final_body<kTailThreads>(t.f);
     }
+}
+
+__global__ void __launch_bounds__(kTailThreads)
+assemble_tail_kernel(const TailArgs t) { assemble_tail_body(t); }
+
+// batched: blockIdx.y selects the state; every per-evaluation buffer is rebased, the problem
+// data (prior, observations, tables) is shared.  status / ticket / flag counters: one per entry.
+__global__ void __launch_bounds__(kTailThreads)
+assemble_tail_batch_kernel(const TailArgs t0, const BatchStrides bs, const int nl) {
+    TailArgs t = t0;
+    const int64_t z = blockIdx.y;
+    t.a.x += z * bs.x;
+    if (t.a.dm != nullptr) { t.a.dm += z * bs.dm; t.a.ds += z * bs.ds; }
+    if (t.a.grad != nullptr) t.a.grad += z * bs.x;
+    t.a.apart += z * bs.apart; t.f.apart += z * bs.apart;
+    t.ticket += z;
+    t.f.esde_n += z * bs.esde_n; t.g.esde_n += z * bs.esde_n;
+    t.f.flags += z * (int64_t)nl; t.g.flags += z * (int64_t)nl;
+    t.f.out += z * bs.out;
+    t.f.status += z; t.f.refine_status += 2 * z; t.f.nflagged += 2 * z; t.g.nflagged += 2 * z;
+    t.g.part += z * bs.part;
+    assemble_tail_body(t);
 }
 
 }  // namespace mfvgp

@@ -78,6 +78,12 @@ struct mfvgp_handle {
     int refine_grid = 1, refine_group = 1;      // CTAs per flagged item (refine.cuh GroupCtx)
     double *refine_gpart = nullptr;
     unsigned *refine_gbar = nullptr;
+    // batched evaluation (mfvgp_ecost_batch): per-entry workspaces for batch_cap entries
+    int batch_cap = 0;
+    double *b_dm = nullptr, *b_ds = nullptr, *b_part = nullptr, *b_apart = nullptr,
+           *b_esde_n = nullptr;
+    int32_t *b_flags = nullptr, *b_rstat = nullptr;
+    unsigned *b_ticket = nullptr;
     // host-API staging
     double *x_dev = nullptr, *grad_dev = nullptr;
     double *pin = nullptr;   // pinned: out[4] + status
@@ -353,7 +359,8 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->refine_ws, h->refine_info, h->refine_status, h->edge_send, h->edge_recv,
                     h->gather, h->xchg_send, h->xchg_gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
                     h->y_dense, h->rinv_row, h->head_flag, h->refine_gpart,
-                    h->refine_gbar};
+                    h->refine_gbar, h->b_dm, h->b_ds, h->b_part, h->b_apart, h->b_esde_n,
+                    h->b_flags, h->b_rstat, h->b_ticket};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
@@ -872,6 +879,122 @@ static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double 
         if (rc) return rc;
     }
     return launch_final(h, h->apart, h->D, out_d, status_d, st, want_grad ? grad_d : nullptr);
+}
+
+// ---- batched evaluation ---------------------------------------------------------------------
+// B independent states of the SAME problem in two launches (Lorenz 96, cooperative small-problem
+// path): what scipy.optimize.check_grad behind find_minimum(check_gradients=True)
+// (free_energy.py:805, :858) asks for -- len(x) + 1 evaluations -- and what fills the GPU at the
+// north-star size, where ONE evaluation is 51 cells per SM.  Fixed rule + guard only: an entry
+// whose guard flags an interval comes back with MFVGP_ST_REFINED and must be re-evaluated with
+// mfvgp_ecost (adaptive stage); the Python wrapper does that.
+extern "C" int mfvgp_ecost_batch(mfvgp_handle *h, int B, const double *x_d, int want_grad,
+                                 double *out_d, double *grad_d, int32_t *status_d,
+                                 void *cuda_stream) {
+    ARG(h && x_d && out_d && status_d, "mfvgp_ecost_batch: NULL argument");
+    ARG(B >= 1 && B <= 65535, "mfvgp_ecost_batch: 1 <= B <= 65535");
+    ARG(!want_grad || grad_d, "mfvgp_ecost_batch: gradient buffer is NULL");
+    if (!h->have_sde || !h->have_obs || !h->have_prior) {
+        g_err = "mfvgp_ecost_batch: set_sde/set_prior/set_obs not called";
+        return MFVGP_ERR_STATE;
+    }
+    ARG(h->system == MFVGP_SYS_L96 && h->coop && h->world == 1,
+        "mfvgp_ecost_batch: Lorenz 96 on the cooperative small-problem path, one GPU");
+    CK(use_device(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int D = h->D, L = h->L, nl = h->n_end - h->n_begin, nb = h->tail_grid;
+    const int per_cta = kTailThreads / 32;
+    int guard_ctas = (nl + per_cta - 1) / per_cta;
+    if (guard_ctas > 64) guard_ctas = 64;
+    // which main kernel: the cooperative one (two lanes per cell, 26 dimensions per CTA) is built
+    // for the latency of ONE evaluation; once the batch alone fills the GPU the one-thread-per-
+    // cell split kernel does the same work in a third of the time.  MFVGP_BATCH_KERNEL=coop|split
+    bool split = (int64_t)B * D * nl >= 148 * 2048;
+    {
+        const char *e = getenv("MFVGP_BATCH_KERNEL");
+        if (e && e[0] == 'c') split = false;
+        if (e && e[0] == 's') split = true;
+    }
+    // tile width with the fewest padded threads (D=500: 9 x 64 = 576 against 5 x 128 = 640)
+    int te = ((D + 121) / 122) * 128 <= ((D + 57) / 58) * 64 ? 128 : 64;
+    {
+        const char *e = getenv("MFVGP_BATCH_TE");
+        if (e && atoi(e) == 64) te = 64;
+        if (e && atoi(e) == 128) te = 128;
+    }
+    const int ntiles = split ? (D + te - 7) / (te - 6) : h->ntiles;
+    const int max_tiles = (D + 32 - 7) / (32 - 6) > h->ntiles ? (D + 32 - 7) / (32 - 6) : h->ntiles;
+    BatchStrides bs;
+    bs.x = (int64_t)D * (h->Nm + h->Ns);
+    bs.dm = (int64_t)L * D * 4; bs.ds = (int64_t)L * D * 3;
+    bs.part = (int64_t)nl * max_tiles * kPartStride;
+    bs.apart = (int64_t)nb * 4; bs.esde_n = L; bs.out = 8;
+    if (B > h->batch_cap) {
+        void *old[] = {h->b_dm, h->b_ds, h->b_part, h->b_apart, h->b_esde_n, h->b_flags,
+                       h->b_rstat, h->b_ticket};
+        CK(cudaStreamSynchronize(st));
+        for (void *p : old)
+            if (p) cudaFree(p);
+        h->batch_cap = 0;
+        h->b_dm = h->b_ds = h->b_part = h->b_apart = h->b_esde_n = nullptr;
+        h->b_flags = h->b_rstat = nullptr; h->b_ticket = nullptr;
+        if (dev_alloc(&h->b_dm, (size_t)B * bs.dm) || dev_alloc(&h->b_ds, (size_t)B * bs.ds) ||
+            dev_alloc(&h->b_part, (size_t)B * bs.part) || dev_alloc(&h->b_apart, (size_t)B * bs.apart) ||
+            dev_alloc(&h->b_esde_n, (size_t)B * bs.esde_n))
+            return MFVGP_ERR_CUDA;
+        CK(cudaMalloc((void **)&h->b_flags, (size_t)B * L * sizeof(int32_t)));
+        CK(cudaMalloc((void **)&h->b_rstat, (size_t)B * 2 * sizeof(int32_t)));
+        CK(cudaMalloc((void **)&h->b_ticket, (size_t)B * sizeof(unsigned)));
+        CK(cudaMemsetAsync(h->b_flags, 0, (size_t)B * L * sizeof(int32_t), st));
+        CK(cudaMemsetAsync(h->b_rstat, 0, (size_t)B * 2 * sizeof(int32_t), st));
+        CK(cudaMemsetAsync(h->b_ticket, 0, (size_t)B * sizeof(unsigned), st));
+        h->batch_cap = B;
+    }
+    CoopArgs c;
+    c.a.mean = x_d; c.a.vars = x_d + (int64_t)D * h->Nm; c.a.ldm = h->Nm; c.a.lds = h->Ns;
+    c.a.obs_times = h->obs_times; c.a.sigma = h->sigma; c.a.theta = h->theta;
+    c.a.dm_out = want_grad ? h->b_dm : nullptr; c.a.ds_out = want_grad ? h->b_ds : nullptr;
+    c.a.part = h->b_part;
+    c.a.D = D; c.a.n_begin = h->n_begin; c.a.n_end = h->n_end; c.a.ntiles = ntiles;
+    c.a.log_vars = 1;
+    c.g.part = h->b_part; c.g.obs_times = h->obs_times; c.g.esde_n = h->b_esde_n;
+    c.g.flags = h->b_flags; c.g.n_begin = h->n_begin; c.g.n_end = h->n_end;
+    c.g.ntiles = ntiles; c.g.nflagged = h->b_rstat + 1;
+    c.tickets = h->tickets; c.theta = h->theta_host[0]; c.guard_later = 1;
+    if (!split) {
+        CK(launch_pdl(esde_l96_coop_batch_kernel, dim3(ntiles, nl, B), kCoopNT, st, c, bs));
+    } else if (te == 128) {
+        esde_l96_split_batch_kernel<128><<<dim3(nl * ntiles, B), 128, 0, st>>>(c.a, bs);
+    } else {
+        esde_l96_split_batch_kernel<64><<<dim3(nl * ntiles, B), 64, 0, st>>>(c.a, bs);
+    }
+    CK(cudaGetLastError());
+    h->launches++;
+    TailArgs t;
+    AssembleArgs &a = t.a;
+    a.x = x_d; a.dm = c.a.dm_out; a.ds = c.a.ds_out;
+    a.mu0 = h->mu0; a.tau0 = h->tau0; a.obs_values = h->obs_values; a.obs_noise = h->obs_noise;
+    a.obs_idx = h->obs_idx; a.grad = want_grad ? grad_d : nullptr; a.apart = h->b_apart;
+    a.D = D; a.M = h->M; a.d = h->d; a.Nm = h->Nm; a.Ns = h->Ns;
+    a.n_begin = h->n_begin; a.n_end = h->n_end; a.L = L; a.with_e0 = 1;
+    t.y_dense = h->y_dense; t.rinv_row = h->rinv_row;
+    t.f.esde_n = h->b_esde_n; t.f.flags = h->b_flags; t.f.apart = h->b_apart;
+    t.f.out = out_d; t.f.status = status_d; t.f.refine_status = h->b_rstat;
+    t.f.nflagged = h->b_rstat + 1;
+    t.f.gbar = h->refine_gbar; t.f.ngbar = 0; t.f.info = nullptr;
+    // entry CTAs: one entry per thread beside the cooperative kernel (rows stay bit-identical
+    // to single evaluations), four per thread beside the split kernel (CTA count, not bytes,
+    // is what bounds this kernel across a large batch)
+    const int nbe = split ? (nb + 3) / 4 : nb;
+    t.f.record9 = 0; t.f.n_begin = h->n_begin; t.f.n_end = h->n_end; t.f.D = nbe;
+    t.f.with_e0 = 1; t.f.eobs_const = h->eobs_const;
+    t.ticket = h->b_ticket;
+    t.g = c.g;
+    t.guard_ctas = guard_ctas;
+    CK(launch_pdl(assemble_tail_batch_kernel, dim3(nbe + guard_ctas, B), kTailThreads, st, t, bs, L));
+    h->launches++;
+    CK(cudaGetLastError());
+    return MFVGP_OK;
 }
 
 static int ensure_host_staging(mfvgp_handle *h) {

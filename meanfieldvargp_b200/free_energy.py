@@ -353,6 +353,86 @@ class FreeEnergy(object):
             return float(out[0])
         return float(out[0]), buf[:n]
 
+    # ---- batched evaluation (no counterpart call in the reference; see check_gradients) ----------
+    def supports_batch(self):
+        """True where mfvgp_ecost_batch applies: Lorenz 96 on the small-problem path, one GPU."""
+        return (self.system == "L96" and getattr(self, "world", 1) == 1
+                and self.describe().get("path") == "coop")
+
+    def E_cost_batch(self, X, output_gradients=True, chunk=1024):
+        """
+        ``E_cost`` of B independent states ``X [B, len(x)]`` of this problem in two launches per
+        chunk: ``(F [B], grad [B, len(x)])`` or ``F [B]``.  CUDA ``torch.float64`` tensor in ->
+        tensors out (numpy in -> numpy out).  Rows on which scipy's ``quad_vec`` would bisect
+        further (guard flagged, MFVGP_ST_REFINED) are re-evaluated one by one with the adaptive
+        stage, so every row equals what ``E_cost`` returns for it.  What
+        ``find_minimum(check_gradients=True)`` uses for its len(x) + 1 evaluations.
+        """
+        import torch
+        self._sync_params()
+        n = self.num_mp + self.num_sp
+        if not self.supports_batch():
+            raise NotImplementedError("E_cost_batch: Lorenz 96 small-problem path on one GPU only")
+        numpy_in = not _is_tensor(X)
+        Xd = torch.as_tensor(_f64(X), device="cuda") if numpy_in else X
+        if Xd.dim() != 2 or Xd.shape[1] != n or Xd.dtype != torch.float64:
+            raise ValueError(f"E_cost_batch: X must be float64 [B, {n}]")
+        Xd = Xd.contiguous()
+        B = Xd.shape[0]
+        want = 1 if output_gradients else 0
+        out = torch.empty((B, 8), dtype=torch.float64, device=Xd.device)
+        grad = torch.empty((B, n), dtype=torch.float64, device=Xd.device) if want else None
+        status = torch.empty(B, dtype=torch.int32, device=Xd.device)
+        stream = torch.cuda.current_stream(Xd.device).cuda_stream
+        for b0 in range(0, B, chunk):
+            nb = min(chunk, B - b0)
+            _lib.check(self._lib.mfvgp_ecost_batch(
+                self._h, nb, Xd[b0].data_ptr(), want, out[b0].data_ptr(),
+                grad[b0].data_ptr() if want else None, status[b0].data_ptr(), stream),
+                "mfvgp_ecost_batch")
+        st = status.cpu().numpy()
+        F = out[:, 0].clone()
+        for b in np.nonzero(st & _lib.ST_REFINED)[0]:          # adaptive stage, one by one
+            if want:
+                fb, gb = self.E_cost(Xd[int(b)])
+                grad[int(b)] = gb
+            else:
+                fb = self.E_cost(Xd[int(b)], output_gradients=False)
+            F[int(b)] = fb
+            torch.cuda.synchronize()
+            st[b] = int(self.last_out[4:5].view(torch.int32)[0].item()) | (st[b] & ~_lib.ST_REFINED)
+        bad = np.nonzero(st & 39)[0]
+        if bad.size:
+            self._raise_on_status(int(st[bad[0]]), E0=float(out[bad[0], 1]),
+                                  Esde=float(out[bad[0], 2]), Eobs=float(out[bad[0], 3]))
+        if numpy_in:
+            F = F.cpu().numpy()
+            return (F, grad.cpu().numpy()) if output_gradients else F
+        return (F, grad) if output_gradients else F
+
+    def check_grad_batched(self, x, chunk=512):
+        """
+        ``scipy.optimize.check_grad(E_cost, grad, x)`` (free_energy.py:805, :858) -- the 2-norm of
+        the analytic gradient minus forward differences with scipy's step sqrt(eps) -- with the
+        len(x) perturbed states evaluated in batches on the device instead of one call each.
+        """
+        import torch
+        x = np.asarray(x, dtype=float).ravel()
+        n = x.size
+        eps = float(np.sqrt(np.finfo(float).eps))
+        xd = torch.as_tensor(x, device="cuda")
+        _, g = self.E_cost(xd)
+        fd = torch.empty(n, dtype=torch.float64, device="cuda")
+        for i0 in range(0, n, chunk):
+            m = min(chunk, n - i0)
+            X = xd.repeat(m + 1, 1)       # last row: x itself, through the same kernels as the rest
+            idx = torch.arange(m, device="cuda")
+            X[idx, i0 + idx] = X[idx, i0 + idx] + eps
+            h = X[idx, i0 + idx] - xd[i0:i0 + m]          # the step actually taken (scipy does the same)
+            F = self.E_cost_batch(X, output_gradients=False, chunk=m + 1)
+            fd[i0:i0 + m] = (F[:m] - F[m]) / h
+        return float(torch.sqrt(torch.sum((g - fd) ** 2)).item())
+
     # ---- find_minimum, free_energy.py:753-862 --------------------------------
     def find_minimum(self, x0, max_iter=100, x_tol=1.0e-5, f_tol=1.0e-5,
                      check_gradients=False, verbose=False):
@@ -361,8 +441,11 @@ class FreeEnergy(object):
         def _grad_check(tag, xin):
             from scipy.optimize import check_grad
             print(f"Grad-Check |{tag}| minimization ...")
-            err = check_grad(lambda v: self.E_cost(v, output_gradients=False),
-                             lambda v: self.E_cost(v)[1], np.array(xin, dtype=float))
+            if self.supports_batch():
+                err = self.check_grad_batched(np.array(xin, dtype=float))
+            else:
+                err = check_grad(lambda v: self.E_cost(v, output_gradients=False),
+                                 lambda v: self.E_cost(v)[1], np.array(xin, dtype=float))
             print(f" > Error = {err:.3E}")
             print("------------------------------------\n")
 
