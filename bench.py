@@ -327,6 +327,18 @@ def run_batched(torch, fe, g, fp64_peak_tf, hbm_gbs, steps=20, warmup=3):
         if best is None or rec["value"] > best[1]["value"]:
             best = (B, rec)
         del X, F, G
+    # the call in the reference's API that needs a batch: scipy.optimize.check_grad behind
+    # find_minimum(check_gradients=True) -- len(x) + 1 evaluations (free_energy.py:805)
+    fe.check_grad_batched(g["x0"])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    err = fe.check_grad_batched(g["x0"])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["check_grad"] = {"evaluations": int(n + 1), "wall_ms": dt * 1e3, "evals_per_s": (n + 1) / dt,
+                         "error_norm": err,
+                         "note": "FreeEnergy.check_grad_batched(x0): forward differences of all "
+                                 "len(x) coordinates, F only, 512 states per launch pair"}
     out["value"] = best[1]["value"]
     out["B"] = best[0]
     out["note"] = ("whole step (main + tail kernel, status read-back, host wrapper) against the FP64 "
