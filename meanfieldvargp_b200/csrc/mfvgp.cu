@@ -983,9 +983,14 @@ extern "C" int mfvgp_ecost_batch(mfvgp_handle *h, int B, const double *x_d, int 
     t.f.nflagged = h->b_rstat + 1;
     t.f.gbar = h->refine_gbar; t.f.ngbar = 0; t.f.info = nullptr;
     // entry CTAs: one entry per thread beside the cooperative kernel (rows stay bit-identical
-    // to single evaluations), four per thread beside the split kernel (CTA count, not bytes,
-    // is what bounds this kernel across a large batch)
-    const int nbe = split ? (nb + 3) / 4 : nb;
+    // to single evaluations), eight per thread beside the split kernel (CTA count, not bytes,
+    // is what bounds this kernel across a large batch; MFVGP_BATCH_TAIL_EPT)
+    int ept = 8;
+    {
+        const char *e = getenv("MFVGP_BATCH_TAIL_EPT");
+        if (e && atoi(e) >= 1 && atoi(e) <= 64) ept = atoi(e);
+    }
+    const int nbe = split ? (nb + ept - 1) / ept : nb;
     t.f.record9 = 0; t.f.n_begin = h->n_begin; t.f.n_end = h->n_end; t.f.D = nbe;
     t.f.with_e0 = 1; t.f.eobs_const = h->eobs_const;
     t.ticket = h->b_ticket;

@@ -137,3 +137,30 @@ def test_guard_in_tail_kernel_equals_guard_in_main_kernel(name, monkeypatch):
         F, grad = fe.E_cost(np.array(x0, dtype=float))
         out[v] = (F, grad.copy())
     assert out["0"][0] == out["1"][0] and np.array_equal(out["0"][1], out["1"][1])
+
+
+def test_scg_fallback_cluster_shape_agrees():
+    """8 CTAs x 1024 threads (devices without 16-CTA clusters) against the default 16 x 512: the
+    choice is cached per process, so the fallback runs in a subprocess"""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    from helpers import synthetic_l96
+    code = (
+        "import sys, json, contextlib, io; sys.path.insert(0, 'tests'); sys.path.insert(0, '.')\n"
+        "from helpers import make_free_energy, synthetic_l96\n"
+        "g = synthetic_l96(40, 20, seed=5); fe = make_free_energy(g)\n"
+        "with contextlib.redirect_stdout(io.StringIO()):\n"
+        "    x, fx, st = fe.find_minimum(g['x0'].copy(), max_iter=60)\n"
+        "print(json.dumps([int(st['nit']), int(st['func_eval']), float(fx)]))\n")
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True,
+                         env=dict(os.environ, MFVGP_SCG_CLUSTER16="0"), timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    nit, nev, fx8 = json.loads(out.stdout.strip().splitlines()[-1])
+    g = synthetic_l96(40, 20, seed=5)
+    x, fx, st = make_free_energy(g).find_minimum(g["x0"].copy(), max_iter=60)
+    assert (nit, nev) == (st["nit"], st["func_eval"])
+    assert abs(fx8 - fx) <= 1.0e-10 * abs(fx)
