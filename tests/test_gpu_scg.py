@@ -164,3 +164,26 @@ def test_scg_fallback_cluster_shape_agrees():
     x, fx, st = make_free_energy(g).find_minimum(g["x0"].copy(), max_iter=60)
     assert (nit, nev) == (st["nit"], st["func_eval"])
     assert abs(fx8 - fx) <= 1.0e-10 * abs(fx)
+
+
+def test_scg_variants_agree_on_random_small_problems(monkeypatch):
+    """tools/scg_soak.py in small: random Lorenz-96 problems, pipelining off / default / forced
+    bit-identical under both reductions, and the same branch counts across the reductions"""
+    from helpers import synthetic_l96
+    rng = np.random.default_rng(2026)
+    for _ in range(8):
+        D, M = int(rng.integers(4, 70)), int(rng.integers(3, 14))
+        g = synthetic_l96(D, M, seed=int(rng.integers(1 << 30)), partial=bool(rng.integers(2)))
+        iters = int(rng.integers(10, 60))
+        out = {}
+        for cl in ("0", "1"):
+            for pipe in ("0", "1", "2"):
+                monkeypatch.setenv("MFVGP_SCG_PIPELINE", pipe)
+                monkeypatch.setenv("MFVGP_SCG_CLUSTER", cl)
+                x, fx, st = make_free_energy(g).find_minimum(g["x0"].copy(), max_iter=iters)
+                out[cl, pipe] = (x, fx, int(st["nit"]), int(st["func_eval"]))
+        for cl in ("0", "1"):
+            for pipe in ("1", "2"):
+                a, b = out[cl, "0"], out[cl, pipe]
+                assert np.array_equal(a[0], b[0]) and a[1:] == b[1:], (D, M, cl, pipe)
+        assert out["0", "0"][2:] == out["1", "0"][2:], (D, M)
