@@ -198,8 +198,8 @@ int mfvgp_reconstruct_host(int device, int D, int M, int num, const double *Tx_h
  * Batched evaluation: B independent states x_d [B][n] of the SAME problem in two launches
  * (out_d [B][8]: F, E0, Esde, Eobs; grad_d [B][n]; status_d [B]).  Serves the n + 1 evaluations
  * scipy.optimize.check_grad makes behind find_minimum(check_gradients=True)
- * (src/var_bayes/free_energy.py:805, :858) and multi-start runs.  Lorenz 96 on the cooperative
- * small-problem path, one GPU.  Fixed rule + guard only: an entry whose status has
+ * (src/var_bayes/free_energy.py:805, :858) and multi-start runs.  Small-problem path (DW, OU,
+ * L63, Lorenz 96 up to 37 888 cells), one GPU.  Fixed rule + guard only: an entry whose status has
  * MFVGP_ST_REFINED set holds the fixed-rule value of a state on which quad_vec would bisect
  * further -- re-evaluate it with mfvgp_ecost.  Workspaces grow to the largest B seen.
  */

@@ -286,6 +286,27 @@ esde_small_inkernel(const CoopArgs ca) {
     if (tid < 32) guard_interval(ca.g, n, tid);
 }
 
+// batched (mfvgp_ecost_batch): blockIdx.y selects the state; the guard runs in the kernel as
+// above, on that state's partials, flags and flag counter
+template <int SYS>
+__global__ void __launch_bounds__(64)
+esde_small_batch_kernel(const CoopArgs ca0, const BatchStrides bs, const int nl) {
+    CoopArgs ca = ca0;
+    const int64_t z = blockIdx.y;
+    ca.a.mean += z * bs.x; ca.a.vars += z * bs.x;
+    if (ca.a.dm_out != nullptr) { ca.a.dm_out += z * bs.dm; ca.a.ds_out += z * bs.ds; }
+    ca.a.part += z * bs.part;
+    ca.g.part += z * bs.part; ca.g.esde_n += z * bs.esde_n; ca.g.flags += z * (int64_t)nl;
+    ca.g.nflagged += 2 * z;
+    const EsdeArgs &a = ca.a;
+    const int n = a.n_begin + blockIdx.x, tid = threadIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
+    esde_small_body<SYS>(a);
+    __syncthreads();
+    if (tid < 32) guard_interval(ca.g, n, tid);
+}
+
 // ---------------------------------------------------------------------------
 // E_cost tail for small problems (single GPU): gradient assembly
 // (free_energy.py:711-743), E_kl0 / E_obs terms (:309-310, :594-612, :733-738) and

@@ -882,8 +882,8 @@ static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double 
 }
 
 // ---- batched evaluation ---------------------------------------------------------------------
-// B independent states of the SAME problem in two launches (Lorenz 96, cooperative small-problem
-// path): what scipy.optimize.check_grad behind find_minimum(check_gradients=True)
+// B independent states of the SAME problem in two launches (small-problem path: DW, OU, L63,
+// Lorenz 96 up to 37 888 cells): what scipy.optimize.check_grad behind find_minimum(check_gradients=True)
 // (free_energy.py:805, :858) asks for -- len(x) + 1 evaluations -- and what fills the GPU at the
 // north-star size, where ONE evaluation is 51 cells per SM.  Fixed rule + guard only: an entry
 // whose guard flags an interval comes back with MFVGP_ST_REFINED and must be re-evaluated with
@@ -898,19 +898,21 @@ extern "C" int mfvgp_ecost_batch(mfvgp_handle *h, int B, const double *x_d, int 
         g_err = "mfvgp_ecost_batch: set_sde/set_prior/set_obs not called";
         return MFVGP_ERR_STATE;
     }
-    ARG(h->system == MFVGP_SYS_L96 && h->coop && h->world == 1,
-        "mfvgp_ecost_batch: Lorenz 96 on the cooperative small-problem path, one GPU");
+    ARG(h->coop && h->world == 1,
+        "mfvgp_ecost_batch: small-problem path (cooperative kernels), one GPU");
+    const bool l96 = h->system == MFVGP_SYS_L96;
     CK(use_device(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int D = h->D, L = h->L, nl = h->n_end - h->n_begin, nb = h->tail_grid;
     const int per_cta = kTailThreads / 32;
     int guard_ctas = (nl + per_cta - 1) / per_cta;
     if (guard_ctas > 64) guard_ctas = 64;
+    if (!l96) guard_ctas = 0;          // DW / OU / L63: the guard runs inside the main kernel
     // which main kernel: the cooperative one (two lanes per cell, 26 dimensions per CTA) is built
     // for the latency of ONE evaluation; once the batch alone fills the GPU the one-thread-per-
     // cell split kernel does the same work in a third of the time.  MFVGP_BATCH_KERNEL=coop|split
-    bool split = (int64_t)B * D * nl >= 148 * 2048;
-    {
+    bool split = l96 && (int64_t)B * D * nl >= 148 * 2048;
+    if (l96) {
         const char *e = getenv("MFVGP_BATCH_KERNEL");
         if (e && e[0] == 'c') split = false;
         if (e && e[0] == 's') split = true;
@@ -961,7 +963,14 @@ extern "C" int mfvgp_ecost_batch(mfvgp_handle *h, int B, const double *x_d, int 
     c.g.flags = h->b_flags; c.g.n_begin = h->n_begin; c.g.n_end = h->n_end;
     c.g.ntiles = ntiles; c.g.nflagged = h->b_rstat + 1;
     c.tickets = h->tickets; c.theta = h->theta_host[0]; c.guard_later = 1;
-    if (!split) {
+    c.a.log_vars = 1;
+    if (h->system == MFVGP_SYS_DW) {
+        CK(launch_pdl(esde_small_batch_kernel<0>, dim3(nl, B), 64, st, c, bs, L));
+    } else if (h->system == MFVGP_SYS_OU) {
+        CK(launch_pdl(esde_small_batch_kernel<1>, dim3(nl, B), 64, st, c, bs, L));
+    } else if (h->system == MFVGP_SYS_L63) {
+        CK(launch_pdl(esde_small_batch_kernel<2>, dim3(nl, B), 64, st, c, bs, L));
+    } else if (!split) {
         CK(launch_pdl(esde_l96_coop_batch_kernel, dim3(ntiles, nl, B), kCoopNT, st, c, bs));
     } else if (te == 128) {
         esde_l96_split_batch_kernel<128><<<dim3(nl * ntiles, B), 128, 0, st>>>(c.a, bs);

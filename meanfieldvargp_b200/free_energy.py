@@ -355,9 +355,11 @@ class FreeEnergy(object):
 
     # ---- batched evaluation (no counterpart call in the reference; see check_gradients) ----------
     def supports_batch(self):
-        """True where mfvgp_ecost_batch applies: Lorenz 96 on the small-problem path, one GPU."""
-        return (self.system == "L96" and getattr(self, "world", 1) == 1
-                and self.describe().get("path") == "coop")
+        """True where mfvgp_ecost_batch applies: the small-problem kernels (DW, OU, L63, Lorenz 96
+        up to 37 888 cells; MFVGP_COOP=0 switches them off) on one GPU."""
+        import os
+        return (getattr(self, "world", 1) == 1 and os.environ.get("MFVGP_COOP", "1")[:1] != "0"
+                and self.describe().get("path") in ("coop", "small"))
 
     def E_cost_batch(self, X, output_gradients=True, chunk=1024):
         """
@@ -372,7 +374,7 @@ class FreeEnergy(object):
         self._sync_params()
         n = self.num_mp + self.num_sp
         if not self.supports_batch():
-            raise NotImplementedError("E_cost_batch: Lorenz 96 small-problem path on one GPU only")
+            raise NotImplementedError("E_cost_batch: small-problem path on one GPU only")
         numpy_in = not _is_tensor(X)
         Xd = torch.as_tensor(_f64(X), device="cuda") if numpy_in else X
         if Xd.dim() != 2 or Xd.shape[1] != n or Xd.dtype != torch.float64:

@@ -82,12 +82,36 @@ def test_batched_gradient_check_equals_scipy_check_grad(kernel, capsys, monkeypa
     assert out.count("Grad-Check |") == 2 and out.count(" > Error = ") == 2
 
 
-def test_batch_is_refused_where_it_does_not_apply():
-    g = load_golden("eval", "DW")
+@pytest.mark.parametrize("case", ["DW", "OU", "L63", "DW_refine"])
+def test_batch_of_the_small_systems(case):
+    """DW / OU / L63: the batch runs the single evaluation's own kernels (guard inside), so rows are
+    bit-identical; DW flags intervals often, those rows go through the adaptive stage"""
+    g = load_golden("eval", case)
     fe = make_free_energy(g)
-    assert not fe.supports_batch()
-    with pytest.raises(NotImplementedError):
-        fe.E_cost_batch(np.asarray(g["x0"], dtype=float)[None, :])
+    assert fe.supports_batch()
+    X = _states(g, 40, seed=7, scale=0.02)
+    F, G = fe.E_cost_batch(X, chunk=16)
+    for b in range(X.shape[0]):
+        f1, g1 = fe.E_cost(X[b])
+        assert f1 == F[b] and np.array_equal(g1, G[b]), b
+    assert abs(F[0] - float(g["F"])) <= 1.0e-10 * abs(float(g["F"]))
+    assert rel_err(G[0], g["grad"]) <= 1.0e-10
+
+
+def test_small_system_gradient_check_goes_through_the_batch(capsys):
+    """example_DW / example_OU / example_L63 call find_minimum(check_gradients=True)"""
+    from scipy.optimize import check_grad
+    g = load_golden("scg", "DW")
+    fe = make_free_energy(g)
+    x = np.asarray(g["x0"], dtype=float)
+    ref = check_grad(lambda v: fe.E_cost(v, output_gradients=False), lambda v: fe.E_cost(v)[1], x)
+    got = fe.check_grad_batched(x, chunk=50)
+    assert abs(got - ref) <= 1.0e-6 * ref
+
+
+def test_batch_is_refused_where_it_does_not_apply():
     big = synthetic_l96(256, 200, seed=1)                   # 51 000 cells: walk path
     fb = make_free_energy(big)
     assert fb.describe()["path"] == "walk" and not fb.supports_batch()
+    with pytest.raises(NotImplementedError):
+        fb.E_cost_batch(np.asarray(big["x0"], dtype=float)[None, :])
