@@ -212,6 +212,9 @@ struct WalkArgs {
     int D, M, d, Nm, Ns, L;
     int n_begin, n_end;          // intervals of this shard
     int ntiles, nruns, TN;       // dim tiles, runs, intervals per run
+    int nshort, TNs;             // the first nshort runs are short (TNs intervals): they are taken
+                                 // LAST (runs go from the last one backwards), so the kernel's
+                                 // ragged end is half a short run instead of half a long one
     int with_e0;
 };
 
@@ -267,8 +270,9 @@ esde_l96_walk_kernel(const WalkArgs a) {
     __syncthreads();
     const int lid = (int)sm.cta_id;
     const int tile = lid % a.ntiles, run = a.nruns - 1 - lid / a.ntiles;
-    const int n0 = a.n_begin + run * a.TN;
-    const int tnv = min(a.TN, a.n_end - n0);            // intervals in this run
+    const int n0 = a.n_begin + (run < a.nshort ? run * a.TNs
+                                               : a.nshort * a.TNs + (run - a.nshort) * a.TN);
+    const int tnv = run < a.nshort ? a.TNs : min(a.TN, a.n_end - n0);   // intervals in this run
     const int d0 = tile * TD, D = a.D;
     int j = (d0 - 3 + e) % D;
     if (j < 0) j += D;

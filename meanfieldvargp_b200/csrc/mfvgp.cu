@@ -60,6 +60,7 @@ struct mfvgp_handle {
     // walk kernel (l96_walk.cuh; fused = 2): dim tile fte, ftn consecutive intervals per run,
     // grid = fntn runs x fntiles tiles.  fused = 0: split / coop kernels with a workspace
     int fte = 64, ftn = 1, fntiles = 1, fntn = 1, fused = 0;
+    int fnshort = 0, ftns = 1;   // walk kernel: short runs at the start of the time axis (taken last)
     double *fedge_m = nullptr, *fedge_s = nullptr, *fapart = nullptr;
     bool have_sde = false, have_prior = false, have_obs = false;
     double eobs_const = 0.0;
@@ -253,6 +254,28 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         }
         h->fntiles = (D + h->fte - 7) / (h->fte - 6);
         h->fntn = (nl + h->ftn - 1) / h->ftn;
+        if (h->fused == 2) {
+            // Runs are taken from the last one backwards by CTAs in the order they start, so the
+            // runs at the START of the time axis are processed last.  Making those short (about
+            // two waves of CTAs in runs of TN/4) shrinks the ragged end of the kernel from half a
+            // long run to half a short one.  Measured at D=8192: 463.0 -> 460.2 us (L=512),
+            // 3383.6 -> 3361.5 us (L=4096), i.e. 0.6 % -- the main kernel's time is a + b L with
+            // a = 47 us, and only a small part of a is that end.  MFVGP_WALK_SHORT=0 switches it
+            // off, "S,TNs" sets it.
+            const int resident = 148 * (512 / h->fte);
+            int tns = h->ftn / 4 < 2 ? 2 : h->ftn / 4;
+            int ns = (2 * resident + h->fntiles - 1) / h->fntiles;
+            if (const char *e = getenv("MFVGP_WALK_SHORT")) {
+                int a = 0, b = 0;
+                if (sscanf(e, "%d,%d", &a, &b) == 2) { ns = a; tns = b; }
+                else if (e[0] == '0') ns = 0;
+            }
+            if (tns >= h->ftn || tns < 1) ns = 0;
+            while (ns > 0 && (int64_t)ns * tns > nl / 2) ns /= 2;      // at most half of the intervals
+            h->fnshort = ns; h->ftns = tns;
+            const int rest = nl - ns * tns;
+            h->fntn = ns + (rest + h->ftn - 1) / h->ftn;
+        }
     }
     double tab[kNodes * kTabStride];
     build_fixed_table(tab);
@@ -618,6 +641,7 @@ static int launch_walk(mfvgp_handle *h, const double *x, double *grad, cudaStrea
     w.D = h->D; w.M = h->M; w.d = h->d; w.Nm = h->Nm; w.Ns = h->Ns; w.L = h->L;
     w.n_begin = h->n_begin; w.n_end = h->n_end;
     w.ntiles = h->fntiles; w.nruns = h->fntn; w.TN = h->ftn;
+    w.nshort = h->fnshort; w.TNs = h->ftns;
     w.with_e0 = h->n_begin == 0;
     int rc;
     if (h->fte == 32) rc = launch_walk_kernel<32>(w, grid, st);
