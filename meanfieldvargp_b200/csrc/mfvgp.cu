@@ -259,9 +259,9 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
             // runs at the START of the time axis are processed last.  Making those short (about
             // two waves of CTAs in runs of TN/4) shrinks the ragged end of the kernel from half a
             // long run to half a short one.  Measured at D=8192: 463.0 -> 460.2 us (L=512),
-            // 3383.6 -> 3361.5 us (L=4096), i.e. 0.6 % -- the main kernel's time is a + b L with
-            // a = 47 us, and only a small part of a is that end.  MFVGP_WALK_SHORT=0 switches it
-            // off, "S,TNs" sets it.
+            // 3383.6 -> 3361.5 us (L=4096), i.e. 0.6 %: what separates 0.91 us per interval at
+            // L=32 from 0.81 at L=4096 is the per-run prologue, not this end.
+            // MFVGP_WALK_SHORT=0 switches it off, "S,TNs" sets it.
             const int resident = 148 * (512 / h->fte);
             int tns = h->ftn / 4 < 2 ? 2 : h->ftn / 4;
             int ns = (2 * resident + h->fntiles - 1) / h->fntiles;
