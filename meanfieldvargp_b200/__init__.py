@@ -6,8 +6,8 @@ include/mfvgp.h.
 """
 from ._lib import MfvgpError, load as load_library          # noqa: F401
 from .free_energy import FreeEnergy                          # noqa: F401
-from .posterior import (pack, reconstruct, support_indices,  # noqa: F401
-                        time_knots, unpack)
+from .posterior import (initial_path, initial_state, pack,   # noqa: F401
+                        reconstruct, support_indices, time_knots, unpack)
 from .trajectory import (collect_obs, simulate_dw, simulate_l63,   # noqa: F401
                          simulate_l96, simulate_ou)
 from .systems import (DoubleWell, Lorenz63, Lorenz96,        # noqa: F401
@@ -15,5 +15,5 @@ from .systems import (DoubleWell, Lorenz63, Lorenz96,        # noqa: F401
 
 __all__ = ["FreeEnergy", "DoubleWell", "OrnsteinUhlenbeck", "Lorenz63", "Lorenz96",
            "StochasticProcess", "MfvgpError", "load_library", "reconstruct",
-           "support_indices", "pack", "unpack", "time_knots", "simulate_l96", "simulate_dw", "simulate_ou",
+           "support_indices", "pack", "unpack", "time_knots", "initial_path", "initial_state", "simulate_l96", "simulate_dw", "simulate_ou",
            "simulate_l63", "collect_obs"]

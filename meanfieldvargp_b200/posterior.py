@@ -7,7 +7,9 @@ side of the free-energy path in the reference's notebooks (SURVEY.md 8(f) ranks 
 ``symbolics.get_local_polynomials`` (src/numerical/symbolics.py:102-149) once per
 (time sample, dimension), by one CUDA kernel (csrc/posterior.cuh).  ``support_indices``,
 ``pack`` and ``unpack`` are the host-side bookkeeping of cells 17/19 and of
-free_energy.py:678-684.  No CPU fallback: ``reconstruct`` needs the library and a GPU.
+free_energy.py:678-684; ``initial_path`` / ``initial_state`` are cells 14 and 19 (the start
+of the optimisation; scipy on the host, as in the notebook).  No CPU fallback: ``reconstruct``
+needs the library and a GPU.
 """
 import ctypes
 
@@ -102,3 +104,56 @@ def unpack(x, dim_D, num_M):
     if x.size != nm + ns:
         raise ValueError(f"unpack: x has {x.size} entries, expected {nm + ns}")
     return x[:nm].reshape(dim_D, 3 * num_M + 4), np.exp(x[nm:]).reshape(dim_D, 2 * num_M + 3)
+
+
+def initial_path(tk, obs_idk, obs_val, h_mask=None, sample_path=None, window=51, polyorder=3):
+    """
+    The notebooks' initial sample path ``x0(t)`` [D, len(tk)] (example_500D.ipynb cell 14,
+    :356-400): observed dimensions get the cubic B-spline through ``[obs[0], *obs, obs[-1]]`` at
+    ``[t0, *tk[obs_idk], tf]`` (``scipy.interpolate.splrep(k=3)`` / ``splev``), unobserved ones the
+    Savitzky-Golay smoothing of ``sample_path[:, i]`` (``savgol_filter(.., 51, 3)``).
+
+    :param obs_val: [M, d] noisy observations (d = number of observed dimensions)
+    :param h_mask: [D] booleans (default: all observed)
+    :param sample_path: [len(tk), D], needed only when some dimension is unobserved
+    """
+    from scipy.interpolate import splev, splrep
+    from scipy.signal import savgol_filter
+    tk = np.asarray(tk, dtype=float)
+    obs_val = np.asarray(obs_val, dtype=float)
+    if obs_val.ndim == 1:
+        obs_val = obs_val[:, None]
+    D = len(h_mask) if h_mask is not None else obs_val.shape[1]
+    mask = [True] * D if h_mask is None else list(h_mask)
+    spl_timex = np.array([tk[0], *tk[np.asarray(obs_idk, dtype=int)], tk[-1]])
+    spl_value = np.array([obs_val[0], *obs_val, obs_val[-1]])
+    x0, j = [], 0
+    for i in range(D):
+        if mask[i]:
+            yy = splev(tk, splrep(spl_timex, spl_value[:, j], k=3))
+            j += 1
+        else:
+            if sample_path is None:
+                raise ValueError("initial_path: sample_path is needed for unobserved dimensions")
+            yy = savgol_filter(np.asarray(sample_path)[:, i], window, polyorder)
+        x0.append(yy)
+    return np.array(x0)
+
+
+def initial_state(x0_path, obs_idk, rng=None, var_base=4.0, var_spread=2.0):
+    """
+    ``x`` for ``find_minimum`` from an initial path (example_500D.ipynb cells 17 and 19,
+    :402-428): means = the path at the mean support indices, variances
+    ``var_base + var_spread * U[0,1)`` at the variance support indices, in log space.
+
+    :param rng: ``numpy.random.Generator`` (the notebook draws from the unseeded global
+                ``np.random.rand``; pass a generator for a reproducible start)
+    :return: ``(x, mp_idk, sp_idk)``
+    """
+    x0_path = np.atleast_2d(np.asarray(x0_path, dtype=float))
+    mp_idk, sp_idk = support_indices(obs_idk, x0_path.shape[1])
+    rng = np.random.default_rng() if rng is None else rng
+    mp = x0_path[:, mp_idk]
+    sp = var_base * np.ones((x0_path.shape[0], len(sp_idk)))
+    sp += var_spread * rng.random(sp.shape)
+    return pack(mp, sp), mp_idk, sp_idk            # pack puts the variances in log space

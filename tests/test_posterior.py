@@ -119,3 +119,39 @@ def test_reconstruct_after_find_minimum_interpolates_support_points():
     assert rel_err(mt[:, ::50][:, :-1], mp[:, 0:-3:3]) <= 1e-12
     assert rel_err(st[:, ::50][:, :-1], sp[:, 0:-2:2]) <= 1e-12
     assert np.all(np.diff(tt) > 0)
+
+
+def test_initial_path_and_state_follow_the_notebook_cells():
+    """example_500D.ipynb cells 14, 17, 19 written out, against mf.initial_path / initial_state"""
+    from scipy.interpolate import splev, splrep
+    from scipy.signal import savgol_filter
+    import meanfieldvargp_b200 as mf
+    rng = np.random.default_rng(3)
+    D, dt, t0, tf = 6, 0.01, 0.0, 3.0
+    tk = np.arange(t0, tf + dt, dt)
+    path = np.cumsum(rng.standard_normal((tk.size, D)), axis=0) * 0.1
+    h_mask = [True, False, True, True, False, True]
+    obs_idk = np.array([50, 100, 150, 200, 250])
+    obs_val = path[obs_idk][:, h_mask] + 0.1 * rng.standard_normal((obs_idk.size, sum(h_mask)))
+    # cell 14
+    spl_timex = np.array([t0, *(obs_idk * dt), tf])
+    spl_value = np.array([obs_val[0], *obs_val, obs_val[-1]])
+    want, j = [], 0
+    for i in range(D):
+        if h_mask[i]:
+            want.append(splev(tk, splrep(spl_timex, spl_value[:, j], k=3)))
+            j += 1
+        else:
+            want.append(savgol_filter(path[:, i], 51, 3))
+    want = np.array(want)
+    got = mf.initial_path(tk, obs_idk, obs_val, h_mask, path)
+    assert got.shape == (D, tk.size) and np.allclose(got, want, rtol=0, atol=1e-12)
+    # cells 17 + 19
+    x, mp_idk, sp_idk = mf.initial_state(got, obs_idk, rng=np.random.default_rng(9))
+    M = obs_idk.size
+    assert len(mp_idk) == 3 * M + 4 and len(sp_idk) == 2 * M + 3
+    r = np.random.default_rng(9)
+    sp = np.log(4.0 * np.ones((D, len(sp_idk))) + 2.0 * r.random((D, len(sp_idk))))
+    assert np.array_equal(x, np.concatenate((want[:, mp_idk].flatten(), sp.flatten())))
+    with pytest.raises(ValueError, match="sample_path"):
+        mf.initial_path(tk, obs_idk, obs_val, h_mask)
