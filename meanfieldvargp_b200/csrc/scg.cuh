@@ -128,18 +128,28 @@ __device__ __forceinline__ void fold_partials(const double *part, int nblk, doub
 }
 
 // scaled_cg.py:228-239 from the folded d.(g+ - g): theta, delta, beta and the step alpha
+struct ChainIn { double sigma, mu, kappa, beta; };      // what the step needs beside the dot product
+__device__ __forceinline__ ChainIn load_chain_in(const FoldArgs &fa) {
+    const double *c = fa.ctrl;
+    ChainIn ci;
+    ci.sigma = __ldcg(c + 0); ci.mu = __ldcg(c + 5); ci.kappa = __ldcg(c + 6);
+    ci.beta = fa.spec ? __ldcg(c + 12) : fa.beta_in;   // 12: written by the previous chain's decision
+    return ci;
+}
+__device__ __forceinline__ double chain_alpha_from(double dot, const ChainIn &ci, double &theta,
+                                                   double &delta, double &beta) {
+    theta = dot / ci.sigma;
+    beta = ci.beta;
+    delta = __dadd_rn(theta, __dmul_rn(beta, ci.kappa));
+    if (delta <= 0.0) {
+        delta = __dmul_rn(beta, ci.kappa);
+        beta = __dsub_rn(beta, theta / ci.kappa);
+    }
+    return -(ci.mu / delta);
+}
 __device__ __forceinline__ double chain_alpha(double dot, const FoldArgs &fa, double &theta,
                                               double &delta, double &beta) {
-    const double *c = fa.ctrl;
-    const double sigma = __ldcg(c + 0), mu = __ldcg(c + 5), kappa = __ldcg(c + 6);
-    theta = dot / sigma;
-    beta = fa.spec ? __ldcg(c + 12) : fa.beta_in;      // 12: written by the previous chain's decision
-    delta = __dadd_rn(theta, __dmul_rn(beta, kappa));
-    if (delta <= 0.0) {
-        delta = __dmul_rn(beta, kappa);
-        beta = __dsub_rn(beta, theta / kappa);
-    }
-    return -(mu / delta);
+    return chain_alpha_from(dot, load_chain_in(fa), theta, delta, beta);
 }
 
 // The accept / continue decision at the end of a chain (scaled_cg.py:253-369, the host's
@@ -503,28 +513,46 @@ scg_cl_theta_kernel(const double *d, const double *gp, const double *g, const Cl
     double dreg[kClPerThread], xreg[kClPerThread];
     scg_pdl_enter();
     if (chain_is_void(fa)) return;
+    const bool lead = cl_rank() == 0 && threadIdx.x == 0;
+    const bool step = cv.x != nullptr;           // chain (mode 2): the alpha step follows
+    // the scalars of the direction kernel and the status of the evaluation just finished are
+    // final: fetch them with the vectors, not after the reduction
+    ChainIn ci = {1.0, 0.0, 1.0, 0.0};
+    int32_t st_eval = 0;
+    if (step) {
+        ci = load_chain_in(fa);
+        if (lead) st_eval = __ldcg(fa.status);
+    }
     const int T = (int)cl_size() * NT, t0 = (int)cl_rank() * NT + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < kClPerThread; ++k) {
         const int i = t0 + k * T;
         dreg[k] = xreg[k] = 0.0;
         if (i < cv.n) {
-            if (cv.x != nullptr) xreg[k] = cv.x[i];
+            if (step) xreg[k] = cv.x[i];
             dreg[k] = d[i];
             v[0] = fma(dreg[k], gp[i] - g[i], v[0]);
         }
     }
     double r[kRedSlots];
     cl_reduce<NT, 1, false>(v, r);
-    if (cl_rank() == 0 && threadIdx.x == 0) fold_finish(r, fa);
-    if (cv.x != nullptr) {                       // alpha step (scaled_cg.py:232-247)
-        double theta, delta, beta;
-        const double alpha = chain_alpha(r[0], fa, theta, delta, beta);
+    if (!step) {
+        if (lead) fold_finish(r, fa);
+        return;
+    }
+    double theta, delta, beta;                   // scaled_cg.py:228-247
+    const double alpha = chain_alpha_from(r[0], ci, theta, delta, beta);
+    if (lead) {                                  // fold_finish, mode 2, with the values at hand
+        double *c = fa.ctrl;
 #pragma unroll
-        for (int k = 0; k < kClPerThread; ++k) {
-            const int i = t0 + k * T;
-            if (i < cv.n) cv.xt[i] = xreg[k] + alpha * dreg[k];
-        }
+        for (int i = 0; i < kRedSlots; ++i) fa.scal[i] = r[i];
+        c[1] = alpha; c[2] = theta; c[3] = delta; c[4] = beta;
+        c[8] = (double)st_eval;
+    }
+#pragma unroll
+    for (int k = 0; k < kClPerThread; ++k) {
+        const int i = t0 + k * T;
+        if (i < cv.n) cv.xt[i] = xreg[k] + alpha * dreg[k];
     }
 }
 
