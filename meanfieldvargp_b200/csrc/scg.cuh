@@ -156,17 +156,25 @@ __device__ __forceinline__ double chain_alpha(double dot, const FoldArgs &fa, do
 // operations).  stats_decide_calc only reads: 1 if the trial point is accepted and the run
 // carries on, with f_old, gamma and beta for the next chain in nxt[0..2].  stats_decide_commit
 // leaves them in ctrl[9], [11], [12] and sets / clears the void flag ctrl[10].
-__device__ __forceinline__ double stats_decide_calc(const double (&r)[kRedSlots],
-                                                    const FoldArgs &fa, double (&nxt)[3]) {
+struct DecideIn { double f_new, alpha, mu, flags, beta, f_old; int stt; };
+__device__ __forceinline__ DecideIn load_decide_in(const FoldArgs &fa) {
+    const double *c = fa.ctrl;
+    DecideIn in;
+    in.f_new = __ldcg(fa.scal + 4);
+    in.stt = (int)__ldcg(fa.status) | (int)__ldcg(c + 8);
+    in.alpha = __ldcg(c + 1); in.mu = __ldcg(c + 5); in.flags = __ldcg(c + 7);
+    in.beta = __ldcg(c + 4);
+    in.f_old = fa.spec ? __ldcg(c + 9) : fa.f_old_in;
+    return in;
+}
+__device__ __forceinline__ double stats_decide_from(const double (&r)[kRedSlots],
+                                                    const FoldArgs &fa, const DecideIn &in,
+                                                    double (&nxt)[3]) {
     nxt[0] = nxt[1] = nxt[2] = 0.0;
     if (!fa.decide) return 0.0;
-    const double *c = fa.ctrl;
-    const double f_new = __ldcg(fa.scal + 4);
-    const int stt = (int)__ldcg(fa.status) | (int)__ldcg(c + 8);
-    const double alpha = __ldcg(c + 1), mu = __ldcg(c + 5), flags = __ldcg(c + 7);
-    double beta = __ldcg(c + 4);
-    const double f_old = fa.spec ? __ldcg(c + 9) : fa.f_old_in;
-    if (flags != 0.0 || (stt & 7) != 0 || (stt & fa.refined_mask) != 0) return 0.0;
+    const double f_new = in.f_new, f_old = in.f_old, alpha = in.alpha, mu = in.mu;
+    double beta = in.beta;
+    if (in.flags != 0.0 || (in.stt & 7) != 0 || (in.stt & fa.refined_mask) != 0) return 0.0;
     const double Delta = __ddiv_rn(__dmul_rn(2.0, __dsub_rn(f_new, f_old)),
                                    __dmul_rn(alpha, mu));                       // :253
     const bool stop = (__dmul_rn(fabs(alpha), r[3]) <= fa.x_tol &&
@@ -179,6 +187,11 @@ __device__ __forceinline__ double stats_decide_calc(const double (&r)[kRedSlots]
     nxt[1] = fmax(__ddiv_rn(r[2], mu), 0.0);                                      // :367
     nxt[2] = beta;
     return 1.0;
+}
+__device__ __forceinline__ double stats_decide_calc(const double (&r)[kRedSlots],
+                                                    const FoldArgs &fa, double (&nxt)[3]) {
+    if (!fa.decide) { nxt[0] = nxt[1] = nxt[2] = 0.0; return 0.0; }
+    return stats_decide_from(r, fa, load_decide_in(fa), nxt);
 }
 __device__ __forceinline__ void stats_decide_commit(double carry_on, const double (&nxt)[3],
                                                     const FoldArgs &fa) {
@@ -640,13 +653,17 @@ scg_cl_stats_direction_kernel(const double *g_now, const double *g_new, double *
     }
     double r[kRedSlots];
     TQ();
+    // thread 0 of every CTA fetches what the decision needs now: the latency hides under the
+    // reduction instead of following it
+    DecideIn din = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0};
+    if (threadIdx.x == 0 && fa3.decide) din = load_decide_in(fa3);
     cl_reduce<NT, 3, true>(v, r, 0);
     TQ();
     // every CTA takes the decision from the same numbers (no broadcast across the cluster);
     // the lead commits it only after the second reduction's barrier, when all have read ctrl
     double nxt[3];
     if (threadIdx.x == 0) {
-        const double carry = stats_decide_calc(r, fa3, nxt);
+        const double carry = stats_decide_from(r, fa3, din, nxt);
         sh_dec[0] = carry;
         sh_dec[1] = nxt[1];
         if (lead) {
