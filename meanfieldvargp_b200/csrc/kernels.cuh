@@ -759,6 +759,14 @@ __device__ __forceinline__ void final_body(const FinalArgs &a) {
     __shared__ double sh_red[4 * (NT / 32)];
     __shared__ int sh_flag;
     if (threadIdx.x == 0) sh_flag = 0;
+    // thread 0 needs two more words at the very end; they are final by now (refine_kernel ran
+    // before this launch, the guard's count before this CTA saw the last ticket): fetch them
+    // under the loads below instead of after the block sum
+    int32_t rs_pre = 0, nf_pre = 0;
+    if (threadIdx.x == 0) {
+        rs_pre = __ldcg(a.refine_status);
+        if (a.nflagged != nullptr) nf_pre = __ldcg(a.nflagged);
+    }
     __syncthreads();
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     int anyflag = 0;
@@ -794,10 +802,10 @@ __device__ __forceinline__ void final_body(const FinalArgs &a) {
         if (!isfinite(E0)) st |= 2;
         if (!isfinite(Eobs)) st |= 4;
         if (sh_flag) st |= 8;
-        st |= a.refine_status[0];
+        st |= rs_pre;
         a.refine_status[0] = 0;
         if (a.nflagged != nullptr) {
-            if (a.nflagged[0] != 0)
+            if (nf_pre != 0)
                 for (int i = 0; i < a.ngbar; ++i) a.gbar[i] = 0u;
             a.nflagged[0] = 0;
         }
