@@ -26,6 +26,18 @@ def rel_err(a, b):
     return float(np.abs(a - b).max()) / den
 
 
+def worst_elem_err(a, b, floor=1.0e-3):
+    """
+    Worst element-wise relative error: max_i |a_i - b_i| / max(|b_i|, floor * max|b|).
+    rel_err above is a max-norm and never looks at small entries on their own; this does, down
+    to entries `floor` times the largest (below that an entry is the rounding residue of
+    cancelling terms of the size of the largest one, so 1e-16 / floor is what FP64 can give).
+    """
+    a, b = np.asarray(a, dtype=float).ravel(), np.asarray(b, dtype=float).ravel()
+    den = np.maximum(np.abs(b), floor * max(float(np.abs(b).max()), 1e-300))
+    return float((np.abs(a - b) / den).max())
+
+
 def make_sde(g):
     """Our parameter holder for a golden case."""
     import meanfieldvargp_b200 as mf

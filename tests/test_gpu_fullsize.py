@@ -1,6 +1,7 @@
 """
-Full-size checks (BASELINE.json configs[4]: Lorenz 96, D=8192, long horizon) through
-size-independent properties -- the oracle cannot run at this size:
+Full-size checks (BASELINE.json configs[4]: Lorenz 96, D=8192, long horizon): the default
+(walk) kernel against the neighbour-sparse oracle at D=8192 for short horizons (M = 9, 33: the
+oracle takes seconds there), and at the long horizon through size-independent properties:
 
 * the walk kernel (default) and the split kernel + assemble_kernel, two independent
   implementations of the same quadrature, agree to rounding;
@@ -12,7 +13,7 @@ size-independent properties -- the oracle cannot run at this size
 import numpy as np
 import pytest
 
-from helpers import make_free_energy, synthetic_l96
+from helpers import make_free_energy, make_oracle, rel_err, synthetic_l96, worst_elem_err
 
 pytestmark = pytest.mark.gpu
 
@@ -99,3 +100,37 @@ def test_safe_log_clamps_at_full_size(problem):
     assert d * np.log(2.0) > clamp                                # prod(R) overflows
     Eobs = 0.5 * (quad + M * (d * np.log(2.0 * np.pi) + clamp))
     assert abs(fe.last_terms["Eobs"] - Eobs) <= 1e-12 * abs(Eobs)
+
+
+# ---- the walk kernel against the oracle at D=8192 (68 dim tiles, wrap-around halo) --------------
+@pytest.mark.parametrize("M_", [9, 33])
+def test_walk_kernel_equals_oracle_at_D8192(M_):
+    """
+    lorenz_96.py:221-236 (circular neighbours) over 68 tiles of 122 rows, free_energy.py:651-751.
+    Two bands of rows get a steep variance mid-point so that scipy's quad_vec bisects further on
+    those intervals (the oracle calls the real quad_vec): the guard must flag them and
+    refine_kernel must reproduce the refined integrals.  Tolerance 1e-10 (north_star) on F, on the
+    gradient in the max-norm and on its worst single element.
+    """
+    g = synthetic_l96(D, M_, seed=8192 + M_)
+    Nm, Ns = 3 * M_ + 4, 2 * M_ + 3
+    x = g["x0"].copy()
+    sp = x[D * Nm:].reshape(D, Ns)
+    sp[100:103, 5] = np.log(0.3)                  # interval 2: the dS integrand refines
+    sp[4000:4002, 9] = np.log(0.12)               # interval 4: deeper
+    oracle = make_oracle(g, adaptive=True)
+    Fo, go = oracle.E_cost(x)
+    neval = np.array(oracle.neval)
+    assert (neval[:, 2] > 63).sum() >= 2          # the reference's quadrature did refine
+    fe = make_free_energy(g)
+    assert fe.describe()["path"] == "walk" and int(fe.describe()["ntiles"]) == 68
+    F, grad = fe.E_cost(x)
+    assert fe.last_status & 8                     # MFVGP_ST_REFINED
+    info = fe.refine_info()
+    assert np.array_equal(21 + 42 * np.maximum(info[:, 0], 1), neval[:, 0])
+    assert np.array_equal(21 + 42 * np.maximum(info[:, 1], 1), neval[:, 2])
+    assert abs(F - Fo) <= 1e-10 * abs(Fo), (F, Fo)
+    assert rel_err(grad, go) <= 1e-10, rel_err(grad, go)
+    assert worst_elem_err(grad, go) <= 1e-10, worst_elem_err(grad, go)
+    # never-integrated columns (free_energy.py:711-712) are exact zeros in both
+    assert np.array_equal(grad == 0.0, go == 0.0)
