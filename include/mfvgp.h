@@ -147,6 +147,25 @@ int mfvgp_eobs_host(mfvgp_handle *h, const double *mean_obs_h /*[d][M]*/,
                     double *dEobs_ds_h /*[d][M]*/, int32_t *status_h);
 
 /*
+ * Gradients of the free energy with respect to the drift parameters theta and the diffusion
+ * coefficients Sigma.  The reference has the hooks and no
+ * implementation: the sde_theta / sde_sigma setters "used only if we optimize the drift /
+ * diffusion parameters" (free_energy.py:241-279) and the closing note of E_cost (:745-748).
+ * Only E_sde depends on them (E_kl0 :281-336 and E_obs :567-649 do not):
+ *   dtheta [ntheta] = dEsde/dtheta_k = 1/2 sum_n sum_i 1/Sigma_i int_n dE_i/dtheta_k dt
+ *   dsigma [D]      = dEsde/dSigma_i = 1/2 sum_n [-1/Sigma_i^2 int_n E_i dt
+ *                                                  + 1/Sigma_i int_n dE_i/dSigma_i dt]
+ * with the integrands E_i of energy_functions/ *.sym and the fixed 42-node Gauss-Kronrod rule
+ * that quad_vec (free_energy.py:405-417) returns when it converges after its first bisection.
+ * x as in mfvgp_ecost.  status bit MFVGP_ST_ESDE_NONFINITE: a non-finite result.
+ * On a sharded handle (mfvgp_comm_init) the call is collective and every rank receives the sums.
+ */
+int mfvgp_eparam(mfvgp_handle *h, const double *x_d, double *dtheta_d /*[ntheta]*/,
+                 double *dsigma_d /*[D]*/, int32_t *status_d, void *cuda_stream);
+int mfvgp_eparam_host(mfvgp_handle *h, const double *x_h, double *dtheta_h /*[ntheta]*/,
+                      double *dsigma_h /*[D]*/, int32_t *status_h);
+
+/*
  * SCG.minimize(x0) over E_cost (scaled_cg.py:107-386 as driven by
  * FreeEnergy.find_minimum, free_energy.py:815-830).  Iterates, gradients and
  * the line-search dot products stay on the device; x_d is updated in place.
@@ -169,10 +188,12 @@ int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x_tol,
  * interval block [n_begin, n_end).  Afterwards mfvgp_ecost / mfvgp_scg are
  * collective calls: x_d / grad_d keep the full reference layout, each rank
  * reads and writes only its own columns (plus the one column it shares with
- * the next rank), the shared column's gradient is exchanged with
- * ncclSend/ncclRecv over NVLink, and the scalars (F, E0, Esde, Eobs, status,
- * SCG dot products) are all-gathered and folded in rank order, so every rank
- * takes identical SCG branches.  NCCL is bound at run time (dlopen).
+ * the next rank).  Per evaluation ONE ncclAllGather carries each rank's scalar
+ * record (F, E0, Esde, Eobs, the six status bits) and its two shared gradient
+ * columns; records are folded in rank order, so every rank holds identical
+ * scalars and takes identical SCG branches (MFVGP_XCHG=split selects
+ * ncclSend/ncclRecv of the columns + an all-gather of the record instead).
+ * NCCL is bound at run time (dlopen).
  */
 int mfvgp_comm_unique_id(void *id128_out /*128 bytes*/);
 int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void *id128);

@@ -38,6 +38,8 @@ SIGNATURES = {
     "mfvgp_host_free": (None, [c_void_p]),
     "mfvgp_ekl0_host": (c_int, [c_void_p, _P, _P, c_int, POINTER(c_double), _P, _P, POINTER(c_int32)]),
     "mfvgp_eobs_host": (c_int, [c_void_p, _P, _P, c_int, POINTER(c_double), _P, _P, POINTER(c_int32)]),
+    "mfvgp_eparam": (c_int, [c_void_p, _P, _P, _P, _P, c_void_p]),
+    "mfvgp_eparam_host": (c_int, [c_void_p, _P, _P, _P, POINTER(c_int32)]),
     "mfvgp_scg": (c_int, [c_void_p, _P, c_int, c_double, c_double, _P, _P, _P, c_void_p]),
     "mfvgp_scg_host": (c_int, [c_void_p, _P, c_int, c_double, c_double, _P, _P, _P]),
     "mfvgp_comm_unique_id": (c_int, [_P]),

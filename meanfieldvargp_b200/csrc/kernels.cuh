@@ -33,6 +33,8 @@ __constant__ double c_gkx_main[kNodesPerPanel];     // Kronrod abscissae (descen
 __constant__ double c_vxB[kNodes], c_vxD[kNodes], c_m1poly[4];   // tables.h build_moment_table
 
 constexpr int kPartStride = 12;  // doubles per (interval, dim-tile) partial
+constexpr int kStatusBits = 6;   // MFVGP_ST_* bits carried through the multi-GPU record
+constexpr int kRecordLen = 4 + kStatusBits;   // F, E0, Esde, Eobs + one 0/1 slot per status bit
 // partial slots (raw sums; scaled by h = dt/4 in guard_reduce_kernel)
 //  0: sum_i sum_r v_r E_i / Sigma_i         (weighted energy)
 //  1: sum_i (sum_r v_r E_i)^2               (|I_E|^2 for quad_vec's tol)
@@ -746,7 +748,7 @@ struct FinalArgs {
     int ngbar;
     int32_t *info;            // [L][2] bisection counts: zeroed here when nothing was flagged and
                               //        refine_kernel may not have been launched (or nullptr)
-    int record9;              // out has 9 slots (multi-GPU record)
+    int record9;              // out is the multi-GPU record: 4 energies + kStatusBits flag slots
     int n_begin, n_end, D;    // D = number of apart rows (state dims, or CTAs of the walk / tail kernel)
     int with_e0;
     double eobs_const;        // M (d log 2pi + safe_log(prod R)), 0 on non-owning shards
@@ -809,7 +811,7 @@ __device__ __forceinline__ void final_body(const FinalArgs &a) {
                 for (int i = 0; i < a.ngbar; ++i) a.gbar[i] = 0u;
             a.nflagged[0] = 0;
         }
-        // record[0..3] = F, E0, Esde, Eobs; record[4..8] = status bits as 0/1 so
+        // record[0..3] = F, E0, Esde, Eobs; record[4..9] = the six status bits as 0/1 so
         // that shards can be combined by summation (combine_record_kernel)
         a.out[0] = E0 + Esde + Eobs;
         a.out[1] = E0;
@@ -817,7 +819,7 @@ __device__ __forceinline__ void final_body(const FinalArgs &a) {
         a.out[3] = Eobs;
         if (a.record9) {
 #pragma unroll
-            for (int b = 0; b < 5; ++b) a.out[4 + b] = (st >> b) & 1 ? 1.0 : 0.0;
+            for (int b = 0; b < kStatusBits; ++b) a.out[4 + b] = (st >> b) & 1 ? 1.0 : 0.0;
         }
         a.status[0] = st;
     }
@@ -909,18 +911,18 @@ __global__ void __launch_bounds__(256)
 combine_all_kernel(const XchgArgs a) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = 16 + 4 * (int64_t)a.D;
-    if (blockIdx.x == 0 && threadIdx.x < 9) {
+    if (blockIdx.x == 0 && threadIdx.x < kRecordLen) {
         const int i = threadIdx.x;
         double v = a.gathered[i];
         for (int r = 1; r < a.world; ++r) v += a.gathered[r * stride + i];
         if (i < 4) a.out[i] = v;
-        // status bits travel as 0/1 in slots 4..8 (final_kernel record9)
-        __shared__ double sh_bits[9];
+        // status bits travel as 0/1 in slots 4..9 (final_kernel record9)
+        __shared__ double sh_bits[kRecordLen];
         sh_bits[i] = v;
         __syncwarp();
         if (i == 0) {
             int32_t st = 0;
-            for (int b = 0; b < 5; ++b)
+            for (int b = 0; b < kStatusBits; ++b)
                 if (sh_bits[4 + b] > 0.0) st |= 1 << b;
             a.status[0] = st;
         }
@@ -954,7 +956,7 @@ __global__ void combine_record_kernel(const double *gathered, int world, int n, 
         __syncthreads();
         if (i == 0) {
             int32_t st = 0;
-            for (int b = 0; b < 5; ++b)
+            for (int b = 0; b < kStatusBits; ++b)
                 if (out[4 + b] > 0.0) st |= 1 << b;
             status[0] = st;
         }
@@ -1021,6 +1023,9 @@ eobs_final_kernel(const double *rowsum, int d, double eobs_const, double *out, i
         status[0] = isfinite(Eobs) ? 0 : 4;
     }
 }
+
+// test hook (MFVGP_INJECT_STATUS): ORs bits into the status word the next final_kernel consumes
+__global__ void or_status_kernel(int32_t *status, int32_t bits) { atomicOr(status, bits); }
 
 // ---------------------------------------------------------------------------
 // FP64 FMA throughput micro-benchmark: the roofline denominator for the Esde

@@ -19,6 +19,7 @@
 #include "posterior.cuh"
 #include "trajectory.cuh"
 #include "scg.cuh"
+#include "eparam.cuh"
 
 using namespace mfvgp;
 
@@ -104,6 +105,8 @@ struct mfvgp_handle {
     double *rec_ws = nullptr;                            // [16] local record before combine
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    double *eparam_ws = nullptr;  // mfvgp_eparam: [nl][D] + [nl * ntiles][kMaxTheta] + out + gather
+    int inject_status = 0;        // MFVGP_INJECT_STATUS="bits[@rank]" (tests): OR-ed into every evaluation
     // optional per-launch timing of the dominant (Esde) kernel, for bench.py
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -366,6 +369,9 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     CK(cudaMemset(h->esde_n, 0, L * sizeof(double)));
     CK(cudaMallocHost((void **)&h->pin, 16 * sizeof(double)));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // the memsets above ran on the legacy stream; evaluations run on non-blocking streams,
+    // which are not ordered after it
+    CK(cudaDeviceSynchronize());
     guard.h = nullptr;
     *out = h;
     return MFVGP_OK;
@@ -383,7 +389,7 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->gather, h->xchg_send, h->xchg_gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
                     h->y_dense, h->rinv_row, h->head_flag, h->refine_gpart,
                     h->refine_gbar, h->b_dm, h->b_ds, h->b_part, h->b_apart, h->b_esde_n,
-                    h->b_flags, h->b_rstat, h->b_ticket};
+                    h->b_flags, h->b_rstat, h->b_ticket, h->eparam_ws};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
@@ -402,8 +408,10 @@ extern "C" int mfvgp_set_sde(mfvgp_handle *h, const double *sigma_h, const doubl
     for (int i = 0; i < h->D; ++i)   // stochastic_process.py:112-115
         ARG(sigma_h[i] > 0.0, "SDE noise vector is not positive");
     CK(use_device(h->device));
+    CK(cudaDeviceSynchronize());     // evaluations in flight (any stream) still read the old values
     CK(cudaMemcpy(h->sigma, sigma_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->theta, theta_h, ntheta * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());     // pageable uploads may return before their DMA has landed
     h->ntheta = ntheta;
     for (int i = 0; i < ntheta && i < 8; ++i) h->theta_host[i] = theta_h[i];
     h->have_sde = true;
@@ -413,8 +421,10 @@ extern "C" int mfvgp_set_sde(mfvgp_handle *h, const double *sigma_h, const doubl
 extern "C" int mfvgp_set_prior(mfvgp_handle *h, const double *mu0_h, const double *tau0_h) {
     ARG(h && mu0_h && tau0_h, "mfvgp_set_prior: NULL argument");
     CK(use_device(h->device));
+    CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h->mu0, mu0_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->tau0, tau0_h, h->D * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());
     h->have_prior = true;
     return MFVGP_OK;
 }
@@ -434,6 +444,7 @@ extern "C" int mfvgp_set_obs(mfvgp_handle *h, const double *obs_times_h,
     const double clamped = fmax(fmin(prod, 1.0e300), 1.0e-300);
     h->eobs_const = h->M * (h->d * 1.8378770664093453 + log(clamped));
     CK(use_device(h->device));
+    CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h->obs_times, obs_times_h, h->M * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->obs_values, obs_values_h, (size_t)h->M * h->d * sizeof(double),
                   cudaMemcpyHostToDevice));
@@ -450,6 +461,7 @@ extern "C" int mfvgp_set_obs(mfvgp_handle *h, const double *obs_times_h,
         CK(cudaMemcpy(h->y_dense, yd.data(), yd.size() * sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(h->rinv_row, ri.data(), ri.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    CK(cudaDeviceSynchronize());
     h->have_obs = true;
     return MFVGP_OK;
 }
@@ -706,6 +718,10 @@ static int launch_final(mfvgp_handle *h, const double *apart, int napart, double
     f.n_begin = h->n_begin; f.n_end = h->n_end; f.D = napart;
     f.with_e0 = h->n_begin == 0;
     f.eobs_const = h->n_begin == 0 ? h->eobs_const : 0.0;
+    if (h->inject_status) {              // tests: a status bit raised on this rank only
+        or_status_kernel<<<1, 1, 0, st>>>(h->refine_status, h->inject_status);
+        CK(cudaGetLastError());
+    }
     if (napart > 2048) final_kernel_wide<<<1, 1024, 0, st>>>(f);
     else final_kernel<<<1, 256, 0, st>>>(f);
     h->launches++;
@@ -729,7 +745,7 @@ static int launch_final(mfvgp_handle *h, const double *apart, int napart, double
     }
     if (multi) {
         // scalar free energy: every rank ends up with the same F, E0, Esde, Eobs
-        int rc = combine_over_ranks(h, h->rec_ws, 9, 9, h->rec_ws, status, st);
+        int rc = combine_over_ranks(h, h->rec_ws, kRecordLen, kRecordLen, h->rec_ws, status, st);
         if (rc) return rc;
         CK(cudaMemcpyAsync(out, h->rec_ws, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
@@ -785,6 +801,11 @@ extern "C" int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void 
     memcpy(&id, id128, sizeof(id));
     NCK(nccl().CommInitRank(&h->comm, world, id, rank));
     h->rank = rank; h->world = world;
+    if (const char *e = getenv("MFVGP_INJECT_STATUS")) {
+        int bits = 0, at = -1;
+        const int nf = sscanf(e, "%d@%d", &bits, &at);
+        if (nf >= 1 && (nf == 1 || at == rank)) h->inject_status = bits;
+    }
     {
         const char *e = getenv("MFVGP_XCHG");
         h->one_collective = !(e && std::string(e) == "split");
@@ -1341,6 +1362,83 @@ extern "C" int mfvgp_fp64_peak(int device, double *tflops_out) {
     cudaEventDestroy(e1);
     cudaFree(buf);
     *tflops_out = best;
+    return MFVGP_OK;
+}
+
+// ---- gradients with respect to theta and Sigma (eparam.cuh) ------------
+extern "C" int mfvgp_eparam(mfvgp_handle *h, const double *x_d, double *dtheta_d,
+                            double *dsigma_d, int32_t *status_d, void *cuda_stream) {
+    ARG(h && x_d && dtheta_d && dsigma_d && status_d, "mfvgp_eparam: NULL argument");
+    if (!h->have_sde || !h->have_obs) {
+        g_err = "mfvgp_eparam: set_sde/set_obs not called";
+        return MFVGP_ERR_STATE;
+    }
+    CK(use_device(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int nl = h->n_end - h->n_begin, D = h->D, nth = h->ntheta;
+    const bool l96 = h->system == MFVGP_SYS_L96;
+    // the dim tiling of the one-thread-per-cell kernels
+    const int te = !l96 ? 0 : (D <= 26 ? 32 : ((int64_t)D * nl <= 148 * 256 ? 64 : 128));
+    const int ntiles = l96 ? (D + te - 7) / (te - 6) : 1;
+    const size_t n_sig = (size_t)nl * D, n_th = (size_t)nl * ntiles * kMaxTheta, n_out = nth + D;
+    if (!h->eparam_ws &&
+        dev_alloc(&h->eparam_ws, n_sig + n_th + n_out * (1 + (size_t)h->world)))
+        return MFVGP_ERR_CUDA;
+    EparamArgs a;
+    a.x = x_d; a.obs_times = h->obs_times; a.sigma = h->sigma; a.theta = h->theta;
+    a.part_sig = h->eparam_ws; a.part_th = h->eparam_ws + n_sig;
+    a.D = D; a.Nm = h->Nm; a.Ns = h->Ns; a.n_begin = h->n_begin; a.n_end = h->n_end;
+    a.ntiles = ntiles;
+    double *out = h->eparam_ws + n_sig + n_th, *gathered = out + n_out;
+    CK(cudaMemsetAsync(status_d, 0, sizeof(int32_t), st));
+    switch (h->system) {
+        case MFVGP_SYS_DW: eparam_small_kernel<0><<<nl, 64, 0, st>>>(a); break;
+        case MFVGP_SYS_OU: eparam_small_kernel<1><<<nl, 64, 0, st>>>(a); break;
+        case MFVGP_SYS_L63: eparam_small_kernel<2><<<nl, 64, 0, st>>>(a); break;
+        default: {
+            const unsigned grid = (unsigned)nl * ntiles;
+            if (te == 32) eparam_l96_kernel<32><<<grid, 32, 0, st>>>(a);
+            else if (te == 64) eparam_l96_kernel<64><<<grid, 64, 0, st>>>(a);
+            else eparam_l96_kernel<128><<<grid, 128, 0, st>>>(a);
+        }
+    }
+    CK(cudaGetLastError());
+    eparam_reduce_kernel<<<(D + 255) / 256 + 1, 256, 0, st>>>(a.part_th, nl * ntiles, nth, a.part_sig,
+                                                            nl, D, out, status_d);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    if (h->world > 1) {
+        // every rank integrated its own intervals: all-gather, fold in rank order
+        NCK(nccl().AllGather(out, gathered, n_out, kNcclFloat64, h->comm, st));
+        eparam_combine_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(gathered, h->world,
+                                                                         (int)n_out, out, status_d);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    CK(cudaMemcpyAsync(dtheta_d, out, nth * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(dsigma_d, out + nth, D * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_eparam_host(mfvgp_handle *h, const double *x_h, double *dtheta_h,
+                                 double *dsigma_h, int32_t *status_h) {
+    ARG(h && x_h && dtheta_h && dsigma_h && status_h, "mfvgp_eparam_host: NULL argument");
+    CK(use_device(h->device));
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const size_t nx = (size_t)h->D * (h->Nm + h->Ns);
+    CK(cudaMemcpyAsync(h->x_dev, x_h, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // results land behind the staged gradient buffer: [dtheta | dsigma]
+    double *res = h->grad_dev;
+    rc = mfvgp_eparam(h, h->x_dev, res, res + h->ntheta, h->status_ws, h->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dtheta_h, res, h->ntheta * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(dsigma_h, res + h->ntheta, h->D * sizeof(double), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaMemcpyAsync(h->pin + 8, h->status_ws, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(status_h, h->pin + 8, sizeof(int32_t));
     return MFVGP_OK;
 }
 

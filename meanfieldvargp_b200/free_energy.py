@@ -9,7 +9,9 @@ Same constructor, same method names, argument meaning, return shapes and
 exceptions as the reference.  ``n_jobs`` is accepted and ignored (the joblib
 fan-out of free_energy.py:500-508 is one kernel launch here).  numpy in ->
 numpy out (copies inside the call); CUDA ``torch.float64`` tensors in ->
-tensors out (zero copy, caller's current stream).
+tensors out (zero copy, caller's current stream, no synchronisation: the
+reference's ``RuntimeError`` for non-finite energies is then raised by
+``FreeEnergy.check_last()``, not by the call itself).
 
 There is no CPU fallback: without the built library or a CUDA device every
 compute call raises ``MfvgpError``.
@@ -235,6 +237,26 @@ class FreeEnergy(object):
         if status & _lib.ST_EOBS:                                 # :615-618
             raise RuntimeError(f" {name}: Eobs is not a finite number: {Eobs}")
 
+    def check_last(self):
+        """
+        Deferred error check of the CUDA-tensor path.  ``E_cost(tensor)`` returns device
+        tensors without synchronising, so it cannot raise the reference's ``RuntimeError`` for a
+        non-finite E0 / Esde / Eobs (free_energy.py:313-316, 547-550, 615-618) at call time as
+        the numpy path does; this reads the status word of the last tensor evaluation (one
+        synchronising 40-byte copy), raises exactly what the numpy path would have raised, and
+        returns the status bits otherwise.
+        """
+        out = getattr(self, "last_out", None)
+        if out is None:
+            return 0
+        host = out.detach().cpu()
+        status = int(host[4:5].view(dtype=host.dtype).numpy().view(np.int32)[0])
+        self.last_status = status
+        if status & 39:
+            self._raise_on_status(status, E0=float(host[1]), Esde=float(host[2]),
+                                  Eobs=float(host[3]))
+        return status
+
     # ---- E_kl0, free_energy.py:281-336 ---------------------------------------
     def E_kl0(self, m0, s0, output_gradients=True):
         self._sync_params()
@@ -353,6 +375,43 @@ class FreeEnergy(object):
             return float(out[0])
         return float(out[0]), buf[:n]
 
+    # ---- hyper-parameter gradients: the hooks at free_energy.py:241-279, :745-748 ---------------
+    def grad_params(self, x):
+        """
+        Gradients of ``E_cost`` with respect to the drift parameters and the diffusion
+        coefficients at state ``x``: ``(dF_dtheta [len(theta)], dF_dsigma [D])``.  The
+        reference keeps the ``sde_theta`` / ``sde_sigma`` setters "to be used only if we
+        optimize the drift / diffusion parameters" (free_energy.py:241-279) and implements no
+        gradient for them (:745-748); ``E_kl0`` and ``E_obs`` do not depend on either, so these
+        are the derivatives of ``E_sde`` (csrc/eparam.cuh states the formulas).  numpy in ->
+        numpy out, CUDA tensor in -> tensors out.
+        """
+        self._sync_params()
+        n = self.num_mp + self.num_sp
+        nth = self.theta.size
+        if _is_tensor(x):
+            import torch
+            xd = x.contiguous().reshape(-1)
+            if xd.numel() != n:
+                raise ValueError(f"grad_params: x has {xd.numel()} entries, expected {n}")
+            res = torch.empty(nth + self.dim_D + 1, dtype=torch.float64, device=xd.device)
+            stream = torch.cuda.current_stream(xd.device).cuda_stream
+            p = res.data_ptr()
+            _lib.check(self._lib.mfvgp_eparam(self._h, xd.data_ptr(), p, p + 8 * nth,
+                                              p + 8 * (nth + self.dim_D), stream), "mfvgp_eparam")
+            return res[:nth], res[nth:nth + self.dim_D]
+        xh = _f64(x).ravel()
+        if xh.size != n:
+            raise ValueError(f"grad_params: x has {xh.size} entries, expected {n}")
+        dth, dsg = np.empty(nth), np.empty(self.dim_D)
+        status = ctypes.c_int32()
+        _lib.check(self._lib.mfvgp_eparam_host(self._h, _ptr(xh), _ptr(dth), _ptr(dsg),
+                                               ctypes.byref(status)), "mfvgp_eparam_host")
+        if status.value & _lib.ST_ESDE:
+            raise RuntimeError(f" {self.__class__.__name__}: the gradient with respect to the "
+                               f"drift / diffusion parameters is not finite.")
+        return dth, dsg
+
     # ---- batched evaluation (no counterpart call in the reference; see check_gradients) ----------
     def supports_batch(self):
         """True where mfvgp_ecost_batch applies: the small-problem kernels (DW, OU, L63, Lorenz 96
@@ -424,6 +483,7 @@ class FreeEnergy(object):
         eps = float(np.sqrt(np.finfo(float).eps))
         xd = torch.as_tensor(x, device="cuda")
         _, g = self.E_cost(xd)
+        self.check_last()
         fd = torch.empty(n, dtype=torch.float64, device="cuda")
         for i0 in range(0, n, chunk):
             m = min(chunk, n - i0)

@@ -477,18 +477,27 @@ class FreeEnergyOracle(object):
         return Ecost, np.concatenate((Ecost_dm.ravel(), Ecost_ds.ravel()), axis=0)
 
     # free_energy.py:753-862 (without the prints)
-    def find_minimum(self, x0, max_iter=100, x_tol=1.0e-5, f_tol=1.0e-5):
+    def find_minimum(self, x0, max_iter=100, x_tol=1.0e-5, f_tol=1.0e-5, events=None):
         max_iter = max(int(max_iter), 10)
         x_tol = max(float(x_tol), 1.0e-20)
         f_tol = max(float(f_tol), 1.0e-20)
-        x, fx, stats = scg_minimize(self.E_cost, x0, max_iter, x_tol, f_tol)
+        x, fx, stats = scg_minimize(self.E_cost, x0, max_iter, x_tol, f_tol, events=events)
         return x, fx, stats
 
 
 # --------------------------------------------------------------------------
 # Scaled conjugate gradient, scaled_cg.py:107-386 (line numbers inline).
 # --------------------------------------------------------------------------
-def scg_minimize(func, x0, max_it=500, x_tol=1.0e-6, f_tol=1.0e-8):
+def scg_minimize(func, x0, max_it=500, x_tol=1.0e-6, f_tol=1.0e-8, events=None):
+    """
+    ``events`` (dict, optional) receives how often each rare branch was taken: "reject"
+    (:254-279), "delta<=0" (:233-236), "mu>=0" (:194-197), "restart" (:361-364).  The reference
+    keeps no such counters; goldens carry them from this restatement once its trajectory has
+    been checked against the reference's (oracle/ref_harness/make_golden.py).
+    """
+    ev = events if events is not None else {}
+    for k in ("reject", "delta<=0", "mu>=0", "restart"):
+        ev[k] = 0
     stats = {"nit": max_it, "fx": np.zeros(max_it), "dfx": np.zeros(max_it),
              "func_eval": 0}
     x = np.asarray(x0, dtype=float).flatten()
@@ -509,6 +518,7 @@ def scg_minimize(func, x0, max_it=500, x_tol=1.0e-6, f_tol=1.0e-8):
         if success:
             mu = d.dot(grad_new)
             if mu >= 0.0:
+                ev["mu>=0"] += 1
                 d = -grad_new
                 mu = d.dot(grad_new)
             kappa = d.dot(d)
@@ -521,6 +531,7 @@ def scg_minimize(func, x0, max_it=500, x_tol=1.0e-6, f_tol=1.0e-8):
             theta = d.dot(g_plus - grad_new) / sigma            # :228
         delta = theta + beta * kappa
         if delta <= 0.0:
+            ev["delta<=0"] += 1
             delta = beta * kappa
             beta = beta - theta / kappa
         alpha = -(mu / delta)
@@ -535,6 +546,7 @@ def scg_minimize(func, x0, max_it=500, x_tol=1.0e-6, f_tol=1.0e-8):
             f_now = f_new
             x = x_new.copy()
         else:
+            ev["reject"] += 1
             success = False
             f_now = f_old
             g_now = grad_old.copy()
@@ -558,6 +570,7 @@ def scg_minimize(func, x0, max_it=500, x_tol=1.0e-6, f_tol=1.0e-8):
         if Delta > 0.75:
             beta = max(0.5 * beta, beta_min)
         if count_success == dim_x:
+            ev["restart"] += 1
             d = -grad_new
             count_success = 0
         elif success:

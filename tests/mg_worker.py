@@ -32,12 +32,47 @@ def active_columns(fe, D, M):
     return idx
 
 
+def inject_status(rank, world, local):
+    """MFVGP_INJECT_STATUS=32@1: rank 1 alone raises MFVGP_ST_SYNC_TIMEOUT in every evaluation
+    (what the walk kernel does when a mailbox wait gives up); every rank must see the bit in
+    the combined status word -- E_cost with and without gradient, and the SCG loop."""
+    from meanfieldvargp_b200 import MfvgpError
+    assert os.environ["MFVGP_INJECT_STATUS"] == "32@1"
+    for path in ("", "walk"):
+        g = synthetic_l96(67, 9, seed=5)
+        if path:
+            os.environ["MFVGP_PATH"] = path
+        sh = ShardedFreeEnergy(g, rank, world, device=local)
+        os.environ.pop("MFVGP_PATH", None)
+        x = torch.tensor(g["x0"], dtype=torch.float64, device="cuda")
+        for want in (True, False):
+            sh.E_cost(x, output_gradients=want)
+            try:
+                sh.local.check_last()
+                raise AssertionError("status bit 32 was dropped on rank %d" % rank)
+            except MfvgpError as ex:
+                assert "MFVGP_ST_SYNC_TIMEOUT" in str(ex)
+            assert sh.local.last_status & 32
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                sh.local.find_minimum(x, max_iter=10)
+            raise AssertionError("SCG dropped status bit 32 on rank %d" % rank)
+        except MfvgpError as ex:
+            assert "MFVGP_ST_SYNC_TIMEOUT" in str(ex)
+        dist.barrier()
+    if rank == 0:
+        print("MG_INJECT_OK", world)
+    dist.destroy_process_group()
+
+
 def main():
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if os.environ.get("MG_MODE") == "inject":
+        return inject_status(rank, world, local)
     # sharded path: default kernels (small problems: coop kernel + assemble + edge exchange)
     # and the walk kernel (what the D=8192 long-horizon problem runs)
     for D, M, path in ((67, 9, ""), (130, 13, ""), (67, 9, "walk"), (130, 41, "walk")):

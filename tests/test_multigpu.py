@@ -78,3 +78,16 @@ def test_sharded_matches_single_gpu():
     res = _torchrun(world, [str(ROOT / "tests" / "mg_worker.py")], timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert f"MG_OK {world}" in res.stdout
+
+
+@pytest.mark.gpu
+def test_status_bits_survive_the_rank_combine():
+    """a status bit raised on ONE rank (here MFVGP_ST_SYNC_TIMEOUT, injected on rank 1) reaches
+    the status word of every rank"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    res = _torchrun(2, [str(ROOT / "tests" / "mg_worker.py")],
+                    env_extra={"MG_MODE": "inject", "MFVGP_INJECT_STATUS": "32@1"}, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "MG_INJECT_OK 2" in res.stdout

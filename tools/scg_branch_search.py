@@ -18,73 +18,11 @@ from helpers import load_golden, make_oracle  # noqa: E402
 
 
 def scg_branches(func, x0, max_it, x_tol=1e-5, f_tol=1e-5):
-    """scaled_cg.py:107-386 restated with branch counters (same arithmetic as the oracle's)."""
-    ev = {"reject": 0, "delta<=0": 0, "mu>=0": 0, "restart": 0, "nit": max_it, "evals": 0}
-    x = np.asarray(x0, dtype=float).flatten()
-    n = x.size
-    f_now, gn = func(x)
-    gn = np.array(gn)
-    go = gn.copy()
-    ev["evals"] += 1
-    f_old = f_now
-    d = -gn
-    success, cs = True, 0
-    beta, kappa, theta, mu = 1.0, 0.0, 0.0, 0.0
-    for j in range(max_it):
-        if success:
-            mu = d.dot(gn)
-            if mu >= 0.0:
-                ev["mu>=0"] += 1
-                d = -gn
-                mu = d.dot(gn)
-            kappa = d.dot(d)
-            if kappa < np.finfo(float).eps:
-                ev["nit"] = j + 1
-                return ev
-            sigma = 1e-3 / np.sqrt(kappa)
-            _, gp = func(x + sigma * d)
-            ev["evals"] += 1
-            theta = d.dot(gp - gn) / sigma
-        delta = theta + beta * kappa
-        if delta <= 0.0:
-            ev["delta<=0"] += 1
-            delta = beta * kappa
-            beta = beta - theta / kappa
-        alpha = -(mu / delta)
-        xn = x + alpha * d
-        f_new, g_now = func(xn)
-        g_now = np.array(g_now)
-        ev["evals"] += 1
-        Delta = 2.0 * (f_new - f_old) / (alpha * mu)
-        if Delta >= 0.0:
-            success = True
-            cs += 1
-            x = xn
-        else:
-            success = False
-            ev["reject"] += 1
-        if success:
-            if np.abs(alpha * d).max() <= x_tol and abs(f_new - f_old) <= f_tol:
-                ev["nit"] = j + 1
-                return ev
-            f_old = f_new
-            go = gn.copy()
-            gn = g_now
-            ev["evals"] += 1
-            if np.isclose(gn.dot(gn), 0.0):
-                ev["nit"] = j + 1
-                return ev
-        if Delta < 0.25:
-            beta = min(4.0 * beta, 1e100)
-        if Delta > 0.75:
-            beta = max(0.5 * beta, 1e-15)
-        if cs == n:
-            ev["restart"] += 1
-            d = -gn
-            cs = 0
-        elif success:
-            gamma = max(gn.dot(go - gn) / mu, 0.0)
-            d = gamma * d - gn
+    """branch counters of the oracle's SCG restatement (oracle/mfvgp_oracle.py scg_minimize)"""
+    from oracle.mfvgp_oracle import scg_minimize
+    ev = {}
+    _, _, st = scg_minimize(func, x0, max_it, x_tol, f_tol, events=ev)
+    ev["nit"], ev["evals"] = int(st["nit"]), int(st["func_eval"])
     return ev
 
 
