@@ -157,7 +157,10 @@ int mfvgp_eobs_host(mfvgp_handle *h, const double *mean_obs_h /*[d][M]*/,
  *                                                  + 1/Sigma_i int_n dE_i/dSigma_i dt]
  * with the integrands E_i of energy_functions/ *.sym and the fixed 42-node Gauss-Kronrod rule
  * that quad_vec (free_energy.py:405-417) returns when it converges after its first bisection.
- * x as in mfvgp_ecost.  status bit MFVGP_ST_ESDE_NONFINITE: a non-finite result.
+ * Where that rule is not converged (quad_vec would bisect further) a composite GK21 rule on 16
+ * panels is used and MFVGP_ST_REFINED raised: the values then agree with quad_vec of the same
+ * integrand to quad_vec's accuracy.  MFVGP_ST_ESDE_NONFINITE: a non-finite result.
+ * x as in mfvgp_ecost.
  * On a sharded handle (mfvgp_comm_init) the call is collective and every rank receives the sums.
  */
 int mfvgp_eparam(mfvgp_handle *h, const double *x_d, double *dtheta_d /*[ntheta]*/,

@@ -18,19 +18,31 @@
 // Quadrature: the fixed rule that is quad_vec's answer whenever it converges after its first
 // bisection (tables.h): the rational terms on scipy's 2 x 21 Kronrod nodes, polynomial terms
 // by any exact rule (7-point Gauss-Legendre for Lorenz 96, the 42 nodes for DW / OU / L63).
+// Where that rule is NOT converged -- quad_vec would bisect further there, and no reference
+// integrand exists whose bisection order could be mirrored -- the rational terms are integrated
+// by a composite GK21 rule on kFinePanels panels instead (exact to rounding for these
+// integrands) and MFVGP_ST_REFINED is raised: the result then agrees with a quad_vec of the
+// same integrand to quad_vec's own accuracy, not bit for bit.
 // These are called once per outer (hyper-parameter) step, not per SCG iteration, so they are
 // separate kernels: the E_cost kernels carry none of this.
 #pragma once
 
 #include "kernels.cuh"
+#include "refine.cuh"
 
 namespace mfvgp {
+
+constexpr int kFinePanels = 16;
+// the fixed rule counts as converged while scipy's error heuristic (200 |K - G|)^1.5 stays
+// below ~1e-9 of the integral of |f|:  200 |K - G| <= 1e-6 sum v |f|
+constexpr double kParamGuard = 1.0e-6 / 200.0;
 
 struct EparamArgs {
     const double *x;           // [D*Nm + D*Ns]: means, then LOG-variances (free_energy.py:678-684)
     const double *obs_times, *sigma, *theta;
     double *part_th;           // [(n_end-n_begin) * rows_th][kMaxTheta] partial sums of dEsde/dtheta
     double *part_sig;          // [(n_end-n_begin)][D]: dEsde/dSigma_i of interval n
+    int32_t *status;           // MFVGP_ST_REFINED is OR-ed in when a finer rule had to be used
     int D, Nm, Ns, n_begin, n_end, ntiles;
 };
 
@@ -68,8 +80,24 @@ __device__ __forceinline__ void drift_dtheta(const double *m, const double *dm, 
     }
 }
 
-// DW / OU / L63: one CTA per interval, one thread per node of the 42-node rule, node values
-// summed in scipy's order (panel 1 then panel 2, r = 0..20) by one thread per quantity.
+// cubic / quadratic Lagrange bases on knots k/3, k/2 at local coordinate tau, d/dtau beside
+__device__ __forceinline__ void lagrange_bases(double t, double *B3, double *D3, double *B2,
+                                               double *D2) {
+    const double a = t, b = t - 1.0 / 3.0, c = t - 2.0 / 3.0, d = t - 1.0;
+    B3[0] = -4.5 * b * c * d;  D3[0] = -4.5 * (c * d + b * d + b * c);
+    B3[1] = 13.5 * a * c * d;  D3[1] = 13.5 * (c * d + a * d + a * c);
+    B3[2] = -13.5 * a * b * d; D3[2] = -13.5 * (b * d + a * d + a * b);
+    B3[3] = 4.5 * a * b * c;   D3[3] = 4.5 * (b * c + a * c + a * b);
+    const double e = t - 0.5;
+    B2[0] = 2.0 * e * d;   D2[0] = 2.0 * (d + e);
+    B2[1] = -4.0 * a * d;  D2[1] = -4.0 * (d + a);
+    B2[2] = 2.0 * a * e;   D2[2] = 2.0 * (e + a);
+}
+
+// DW / OU / L63: one CTA per interval.  A composite GK21 rule on P panels is evaluated 42
+// nodes (two panels) at a time, one thread per node, node values summed in scipy's order by
+// one thread per quantity: P = 2 is the fixed rule; the embedded Gauss-10 sums of that pass
+// decide whether the P = kFinePanels rule replaces it.
 template <int SYS>
 __global__ void __launch_bounds__(64)
 eparam_small_kernel(const EparamArgs a) {
@@ -77,53 +105,84 @@ eparam_small_kernel(const EparamArgs a) {
     constexpr int D = Dr::D, NTH = Dr::NTHETA;
     constexpr int NV = NTH + 2 * D;                     // dtheta_k | E_i | dE_i/dSigma_i
     __shared__ double vals[NV][kNodes];
+    __shared__ double res[2][NV];                       // integrals over [0,1]: fixed, fine
+    __shared__ int sh_fine;
     const int n = a.n_begin + blockIdx.x, q = threadIdx.x;
     const double dt = fabs(a.obs_times[n + 1] - a.obs_times[n]);
     const double inv_dt = 1.0 / dt;
     const double *lvars = a.x + (int64_t)a.D * a.Nm;
-    if (q < kNodes) {
-        const double *T = c_tab + q * kTabStride;
-        double m[D], dm[D], s[D], ds[D], Sig[D], inv_sig[D], th[NTH];
+    double P[D][4], S[D][3], Sig[D], inv_sig[D], th[NTH];
 #pragma unroll
-        for (int i = 0; i < NTH; ++i) th[i] = a.theta[i];
+    for (int i = 0; i < NTH; ++i) th[i] = a.theta[i];
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const double *mp = a.x + (int64_t)j * a.Nm + 3 * (int64_t)n;
-            const double *sp = lvars + (int64_t)j * a.Ns + 2 * (int64_t)n;
-            const double S0 = exp(sp[0]), S1 = exp(sp[1]), S2 = exp(sp[2]);
-            m[j] = mp[0] * T[T_B3] + mp[1] * T[T_B3 + 1] + mp[2] * T[T_B3 + 2] + mp[3] * T[T_B3 + 3];
-            dm[j] = (mp[0] * T[T_DB3] + mp[1] * T[T_DB3 + 1] + mp[2] * T[T_DB3 + 2]
-                     + mp[3] * T[T_DB3 + 3]) * inv_dt;
-            s[j] = S0 * T[T_B2] + S1 * T[T_B2 + 1] + S2 * T[T_B2 + 2];
-            ds[j] = (S0 * T[T_DB2] + S1 * T[T_DB2 + 1] + S2 * T[T_DB2 + 2]) * inv_dt;
-            Sig[j] = a.sigma[j];
-            inv_sig[j] = 1.0 / Sig[j];
-        }
-        double E[D], Em[D][D], Edm[D], Es[D][D], Eds[D], dth[NTH];
-        Dr::nodal(m, dm, s, ds, Sig, th, E, Em, Edm, Es, Eds);
-        drift_dtheta<SYS>(m, dm, s, ds, Sig, th, inv_sig, dth);
+    for (int j = 0; j < D; ++j) {
+        const double *mp = a.x + (int64_t)j * a.Nm + 3 * (int64_t)n;
+        const double *sp = lvars + (int64_t)j * a.Ns + 2 * (int64_t)n;
 #pragma unroll
-        for (int k = 0; k < NTH; ++k) vals[k][q] = dth[k];
+        for (int k = 0; k < 4; ++k) P[j][k] = mp[k];
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-            vals[NTH + i][q] = E[i];
-            vals[NTH + D + i][q] = -Eds[i];              // dE_i/dSigma_i
-        }
+        for (int k = 0; k < 3; ++k) S[j][k] = exp(sp[k]);
+        Sig[j] = a.sigma[j];
+        inv_sig[j] = 1.0 / Sig[j];
     }
-    __syncthreads();
-    if (q < NV) {
-        double K = 0.0;
-        for (int r = 0; r < kNodes; ++r) K = fma(c_tab[r * kTabStride + T_V], vals[q][r], K);
-        vals[q][0] = 0.25 * dt * K;                      // integral over the interval
+    if (q == 0) sh_fine = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int np = pass == 0 ? 2 : kFinePanels;
+        const double hw = 0.5 / np;                     // panel half width in tau
+        double acc = 0.0, accG = 0.0, accA = 0.0;       // thread q < NV: Kronrod, Gauss, |f| sums
+        for (int p0 = 0; p0 < np; p0 += 2) {
+            __syncthreads();
+            if (q < kNodes) {
+                const int p = p0 + q / kNodesPerPanel, r = q % kNodesPerPanel;
+                const double tau = fma(hw, c_gk_x[r], (2 * p + 1) * hw);
+                double B3[4], D3[4], B2[3], D2[3];
+                lagrange_bases(tau, B3, D3, B2, D2);
+                double m[D], dm[D], sv[D], ds[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    m[j] = P[j][0] * B3[0] + P[j][1] * B3[1] + P[j][2] * B3[2] + P[j][3] * B3[3];
+                    dm[j] = (P[j][0] * D3[0] + P[j][1] * D3[1] + P[j][2] * D3[2] + P[j][3] * D3[3])
+                            * inv_dt;
+                    sv[j] = S[j][0] * B2[0] + S[j][1] * B2[1] + S[j][2] * B2[2];
+                    ds[j] = (S[j][0] * D2[0] + S[j][1] * D2[1] + S[j][2] * D2[2]) * inv_dt;
+                }
+                double E[D], Em[D][D], Edm[D], Es[D][D], Eds[D], dth[NTH];
+                Dr::nodal(m, dm, sv, ds, Sig, th, E, Em, Edm, Es, Eds);
+                drift_dtheta<SYS>(m, dm, sv, ds, Sig, th, inv_sig, dth);
+#pragma unroll
+                for (int k = 0; k < NTH; ++k) vals[k][q] = dth[k];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    vals[NTH + i][q] = E[i];
+                    vals[NTH + D + i][q] = -Eds[i];          // dE_i/dSigma_i
+                }
+            }
+            __syncthreads();
+            if (q < NV)
+                for (int r = 0; r < kNodes; ++r) {
+                    const int rr = r % kNodesPerPanel;
+                    const double f = vals[q][r];
+                    acc = fma(c_gk_v[rr], f, acc);
+                    accA = fma(c_gk_v[rr], fabs(f), accA);
+                    if (rr & 1) accG = fma(c_gk_w[rr >> 1], f, accG);
+                }
+        }
+        if (q < NV) {
+            res[pass][q] = hw * acc;
+            if (pass == 0 && !(fabs(acc - accG) <= kParamGuard * accA)) atomicOr(&sh_fine, 1);
+        }
+        __syncthreads();
+        if (!sh_fine) break;                            // the fixed rule is converged (CTA-uniform)
     }
-    __syncthreads();
+    const int use = sh_fine ? 1 : 0;
+    if (q == 0 && use) atomicOr(a.status, 8);           // MFVGP_ST_REFINED
     if (q < NTH)
-        a.part_th[(int64_t)blockIdx.x * kMaxTheta + q] = 0.5 * vals[q][0];
+        a.part_th[(int64_t)blockIdx.x * kMaxTheta + q] = 0.5 * dt * res[use][q];
     else if (q < NTH + D) {
         const int i = q - NTH;
-        const double is = 1.0 / a.sigma[i];
+        const double is = inv_sig[i];
         a.part_sig[(int64_t)blockIdx.x * a.D + i] =
-            0.5 * is * (vals[NTH + D + i][0] - is * vals[NTH + i][0]);
+            0.5 * is * dt * (res[use][NTH + D + i] - is * res[use][NTH + i]);
     }
 }
 
@@ -180,18 +239,40 @@ eparam_l96_kernel(const EparamArgs a) {
         // rational part: sum_42 v q^2/s and sum_42 v q/s (tau-polynomials of s and q)
         const double a0 = S0, a1 = -3.0 * S0 + 4.0 * S1 - S2, a2 = 2.0 * (S0 - 2.0 * S1 + S2);
         const double b0 = a1 * inv_dt - Sig, b1 = 2.0 * a2 * inv_dt;
-        double aE = 0.0, aL = 0.0;
+        // RE = int_0^1 q^2/s dtau, RL = int_0^1 q/s dtau: fixed rule (2 panels), and the
+        // composite rule on kFinePanels panels where its Kronrod - Gauss estimate is too large
+        double RE = 0.0, RL = 0.0;
+        bool fine = false;
 #pragma unroll 1
-        for (int r = 0; r < kNodes; ++r) {
-            const double tau = c_rat[r * kTabStride + R_TAU], v = c_rat[r * kTabStride + R_V];
-            const double s = fma(fma(a2, tau, a1), tau, a0), qq = fma(b1, tau, b0);
-            const double qi = qq / s;
-            aE = fma(v, qq * qi, aE);
-            aL = fma(v, qi, aL);
+        for (int pass = 0; pass < 2; ++pass) {
+            const int np = pass == 0 ? 2 : kFinePanels;
+            const double hw = 0.5 / np;
+            double kE = 0.0, kL = 0.0, gE = 0.0, gL = 0.0, aL = 0.0;
+#pragma unroll 1
+            for (int p = 0; p < np; ++p)
+#pragma unroll 1
+                for (int r = 0; r < kNodesPerPanel; ++r) {
+                    const double tau = fma(hw, c_gk_x[r], (2 * p + 1) * hw), v = c_gk_v[r];
+                    const double s = fma(fma(a2, tau, a1), tau, a0), qq = fma(b1, tau, b0);
+                    const double qi = qq / s;
+                    kE = fma(v, qq * qi, kE);
+                    kL = fma(v, qi, kL);
+                    aL = fma(v, fabs(qi), aL);
+                    if (r & 1) {
+                        gE = fma(c_gk_w[r >> 1], qq * qi, gE);
+                        gL = fma(c_gk_w[r >> 1], qi, gL);
+                    }
+                }
+            RE = hw * kE;
+            RL = hw * kL;
+            if (pass == 0)
+                fine = !(fabs(kE - gE) <= kParamGuard * fabs(kE) && fabs(kL - gL) <= kParamGuard * aL);
+            if (!fine) break;
         }
+        if (fine) atomicOr(a.status, 8);                 // MFVGP_ST_REFINED
         const double own_poly = dt * (S0 + 4.0 * S1 + S2) * (1.0 / 6.0) + (S2 - S0) - Sig * dt;
-        const double I_E = fma(dt, accE, fma(0.0625 * dt, aE, own_poly));    // int_n E_i dt
-        const double I_dS = -fma(0.125 * dt, aL, dt);                        // int_n dE_i/dSigma_i dt
+        const double I_E = fma(dt, accE, fma(0.25 * dt, RE, own_poly));      // int_n E_i dt
+        const double I_dS = -fma(0.5 * dt, RL, dt);                          // int_n dE_i/dSigma_i dt
         a.part_sig[(int64_t)nl * D + j] = 0.5 * inv_sig * (I_dS - inv_sig * I_E);
         dth = inv_sig * dt * accR;                       // 1/2 (1/Sigma_i) int 2 R_i dt
     }

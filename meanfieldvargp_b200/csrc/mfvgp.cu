@@ -1386,7 +1386,7 @@ extern "C" int mfvgp_eparam(mfvgp_handle *h, const double *x_d, double *dtheta_d
         return MFVGP_ERR_CUDA;
     EparamArgs a;
     a.x = x_d; a.obs_times = h->obs_times; a.sigma = h->sigma; a.theta = h->theta;
-    a.part_sig = h->eparam_ws; a.part_th = h->eparam_ws + n_sig;
+    a.part_sig = h->eparam_ws; a.part_th = h->eparam_ws + n_sig; a.status = status_d;
     a.D = D; a.Nm = h->Nm; a.Ns = h->Ns; a.n_begin = h->n_begin; a.n_end = h->n_end;
     a.ntiles = ntiles;
     double *out = h->eparam_ws + n_sig + n_th, *gathered = out + n_out;

@@ -407,6 +407,7 @@ class FreeEnergy(object):
         status = ctypes.c_int32()
         _lib.check(self._lib.mfvgp_eparam_host(self._h, _ptr(xh), _ptr(dth), _ptr(dsg),
                                                ctypes.byref(status)), "mfvgp_eparam_host")
+        self.last_status = status.value
         if status.value & _lib.ST_ESDE:
             raise RuntimeError(f" {self.__class__.__name__}: the gradient with respect to the "
                                f"drift / diffusion parameters is not finite.")

@@ -100,6 +100,64 @@ def scg_case(setup, max_iter, name=None):
     print(f"scg_{name}: fx={fx:.12g} nit={stats['nit']} evals={stats['func_eval']} ({wall:.1f}s)")
 
 
+# -- SCG starts that take the rare branches of scaled_cg.py ---------------------------------
+def _truncate(setup, M):
+    """the setup cut down to its first M observation times (x0 columns with it)"""
+    sde = setup["sde"]
+    D = int(np.atleast_1d(sde.sigma).size)
+    M0 = len(setup["obs_times"])
+    mp = setup["x0"][:D * (3 * M0 + 4)].reshape(D, 3 * M0 + 4)[:, :3 * M + 4]
+    sp = setup["x0"][D * (3 * M0 + 4):].reshape(D, 2 * M0 + 3)[:, :2 * M + 3]
+    s = dict(setup)
+    s["obs_times"] = np.asarray(setup["obs_times"])[:M]
+    s["obs_values"] = np.asarray(setup["obs_values"])[:M]
+    s["x0"] = np.concatenate((mp.ravel(), sp.ravel()))
+    return s
+
+
+def scg_branch_case(setup, M, seed, amps_m, amps_s, max_iter, name):
+    """
+    SCG from a perturbed start (x0 + am N(0,1) on the means, + as N(0,1) on the log-variances;
+    am, as drawn from amps_m, amps_s by default_rng(seed) first: the recipe of
+    tools/scg_branch_search.py, which found these starts).  The reference's SCG.minimize runs
+    unmodified and keeps no branch counters, so the counters stored beside its statistics come
+    from the oracle's restatement (oracle/mfvgp_oracle.py scg_minimize), after checking here
+    that the restatement follows the reference's run: same nit, func_eval and fx / dfx history.
+    """
+    from oracle import mfvgp_oracle as O
+    harness.install()
+    s = _truncate(setup, M)
+    sde = s["sde"]
+    D = int(np.atleast_1d(sde.sigma).size)
+    nm = D * (3 * M + 4)
+    r = np.random.default_rng(seed)
+    am, asg = float(r.choice(amps_m)), float(r.choice(amps_s))
+    x0 = s["x0"].copy()
+    x0[:nm] += am * r.standard_normal(nm)
+    x0[nm:] += asg * r.standard_normal(x0.size - nm)
+    s["x0"] = x0
+    fe = setups.free_energy_of(s, n_jobs=1)
+    t0 = time.perf_counter()
+    x, fx, stats = fe.find_minimum(x0.copy(), max_iter=max_iter)
+    wall = time.perf_counter() - t0
+    out = _inputs(s)
+    o = O.FreeEnergyOracle(out["system"], out["sigma"], out["theta"], out["mu0"], out["tau0"],
+                           out["obs_times"], out["obs_values"], out["obs_noise"],
+                           None if out["obs_mask"].size == 0 else list(out["obs_mask"]))
+    ev = {}
+    xo, fxo, so = o.find_minimum(x0.copy(), max_iter=max_iter, events=ev)
+    nit = int(stats["nit"])
+    assert so["nit"] == nit and so["func_eval"] == int(stats["func_eval"]), (so["nit"], nit)
+    assert np.abs(so["fx"][:nit] - stats["fx"][:nit]).max() <= 1e-9 * np.abs(stats["fx"][:nit]).max()
+    assert np.abs(so["dfx"][:nit] - stats["dfx"][:nit]).max() <= 1e-7 * np.abs(stats["dfx"][:nit]).max()
+    out.update(max_iter=max_iter, x_opt=x, fx_opt=float(fx), nit=nit, fx_hist=stats["fx"],
+               dfx_hist=stats["dfx"], func_eval=int(stats["func_eval"]), ref_wall_s=wall,
+               n_reject=ev["reject"], n_delta_le0=ev["delta<=0"], n_mu_ge0=ev["mu>=0"],
+               n_restart=ev["restart"], start_seed=seed, start_am=am, start_as=asg)
+    np.savez_compressed(GOLDEN_DIR / f"scg_{name}.npz", **out)
+    print(f"scg_{name}: fx={fx:.12g} nit={nit} evals={stats['func_eval']} branches={ev} ({wall:.1f}s)")
+
+
 # -- special inputs -----------------------------------------------------------
 def _with_x(setup, x, name):
     s = dict(setup)
@@ -158,6 +216,19 @@ CASES = {
     "scg_OU": lambda: scg_case(setups.make_ou(), 25),
     "scg_L63": lambda: scg_case(setups.make_l63(tf=5.0), 15, name="L63_T5"),
     "scg_L96_8": lambda: scg_case(setups.make_l96(D=8, tf=2.0), 15),
+    # rejected trial points (scaled_cg.py:254-279), mu >= 0 (:194-197), delta <= 0 (:233-236),
+    # restart after dim_x successes (:361-364), convergence exit (:306-318)
+    "scg_branch_DW3": lambda: scg_branch_case(
+        setups.make_dw(), 3, 672241289, [0.2, 0.5, 1.0, 1.5, 3.0], [0.0, 0.3, 0.6, 1.0, 1.5], 80,
+        "branch_DW3"),
+    "scg_branch_DW4": lambda: scg_branch_case(
+        setups.make_dw(), 4, 819696831, [0.2, 0.5, 1.0, 2.0, 3.0], [0.0, 0.2, 0.4, 0.6], 60,
+        "branch_DW4"),
+    "scg_branch_OU2": lambda: scg_branch_case(
+        setups.make_ou(), 2, 630436052, [0.0, 0.5, 1.5], [0.0, 0.5, 1.0, 2.0], 60, "branch_OU2"),
+    "scg_branch_L96_8": lambda: scg_branch_case(
+        setups.make_l96(D=8, tf=2.0), 2, 335045, [0.2, 0.5, 1.0, 2.0], [0.6, 0.8, 1.0, 1.2], 40,
+        "branch_L96_8"),
 }
 
 if __name__ == "__main__":

@@ -190,6 +190,11 @@ def _refine_dw():
     return refine_dw()
 
 
+def _refine_l96():
+    from .make_golden import refine_l96
+    return refine_l96()
+
+
 CASES = {
     "DW": lambda: param_case(setups.make_dw()),
     "OU": lambda: param_case(setups.make_ou()),
@@ -198,6 +203,7 @@ CASES = {
     "L96_40": lambda: param_case(setups.make_l96(D=40, tf=5.0), n_jobs=8),
     "L96_67p": lambda: param_case(setups.make_l96(D=67, tf=1.5, partial=True), n_jobs=8),
     "DW_refine": lambda: param_case(_refine_dw()),
+    "L96_6_refine": lambda: param_case(_refine_l96()),
 }
 
 if __name__ == "__main__":

@@ -9,6 +9,9 @@ EVAL_CASES = ["DW", "OU", "L63", "L96_4", "L96_8", "L96_40", "L96_67p", "L96_500
               "L96_5_irregular"]
 REFINE_CASES = ["DW_refine", "L96_6_refine"]
 SCG_CASES = ["DW", "OU", "L63_T5", "L96_8"]
+# reference runs that take the rare branches of scaled_cg.py: rejected trial points (:254-279),
+# mu >= 0 (:194-197), restart after dim_x successes (:361-364)
+SCG_BRANCH_CASES = ["branch_DW3", "branch_DW4"]
 
 
 def load_golden(kind, name):

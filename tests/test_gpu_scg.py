@@ -9,7 +9,8 @@ history matching to 1e-8 relative and the final iterate to 1e-6.
 import numpy as np
 import pytest
 
-from helpers import SCG_CASES, load_golden, make_free_energy, make_oracle, rel_err
+from helpers import (SCG_BRANCH_CASES, SCG_CASES, load_golden, make_free_energy, make_oracle,
+                     rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -28,6 +29,71 @@ def test_scg_matches_reference_trajectory(name, capsys):
     assert rel_err(stats["dfx"][:nit], g["dfx_hist"][:nit]) <= 1.0e-5
     assert abs(fx - float(g["fx_opt"])) <= 1.0e-8 * abs(float(g["fx_opt"]))
     assert rel_err(x, g["x_opt"]) <= 1.0e-6
+
+
+VARIANTS = [{}, {"MFVGP_SCG_PIPELINE": "0"}, {"MFVGP_SCG_PIPELINE": "2"},
+            {"MFVGP_SCG_CLUSTER": "0"}, {"MFVGP_SCG_FUSED": "0"},
+            {"MFVGP_SCG_PIPELINE": "2", "MFVGP_SCG_CLUSTER": "0"}]
+
+
+@pytest.mark.parametrize("name", SCG_BRANCH_CASES)
+@pytest.mark.parametrize("variant", range(len(VARIANTS)))
+def test_scg_rare_branches_match_reference(name, variant, monkeypatch):
+    """
+    Runs of the UNMODIFIED reference that reject trial points (scaled_cg.py:254-279: g_now <-
+    grad_old, dfx = sum|grad_old|), find mu >= 0 and reset the direction (:194-197) and restart
+    after dim_x successes (:361-364): same nit, func_eval and fx / dfx history on the device, in
+    every variant of the control loop -- chains enqueued ahead (and voided by a rejection),
+    step by step, cluster and grid reductions, host-read records (MFVGP_SCG_FUSED=0).
+    """
+    for k, v in VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+    g = load_golden("scg", name)
+    assert int(g["n_reject"]) >= 4 and int(g["n_mu_ge0"]) >= 1 and int(g["n_restart"]) >= 2
+    fe = make_free_energy(g)
+    x, fx, stats = fe.find_minimum(g["x0"].copy(), max_iter=int(g["max_iter"]))
+    nit = int(g["nit"])
+    assert stats["nit"] == nit and stats["func_eval"] == int(g["func_eval"])
+    assert rel_err(stats["fx"][:nit], g["fx_hist"][:nit]) <= 1.0e-8
+    assert rel_err(stats["dfx"][:nit], g["dfx_hist"][:nit]) <= 1.0e-6
+    # the accept / reject pattern itself: fx repeats exactly where a trial point was rejected
+    assert np.array_equal(np.diff(stats["fx"][:nit]) == 0.0, np.diff(g["fx_hist"][:nit]) == 0.0)
+    assert abs(fx - float(g["fx_opt"])) <= 1.0e-8 * abs(float(g["fx_opt"]))
+    assert rel_err(x, g["x_opt"]) <= 1.0e-6
+
+
+WILD = {"OU2": ("OU", 2, 290291082), "L96_8": ("L96_8", 2, 672604860)}
+
+
+@pytest.mark.parametrize("case", sorted(WILD))
+def test_scg_wild_start_raises_like_the_reference(case):
+    """
+    Starts with scattered log-variances (x0 + as N(0,1), as ~ 1): the interpolated variance dips
+    to zero inside an interval, and the UNMODIFIED reference stops its SCG run with
+    ``RuntimeError: ... is not a finite number`` (free_energy.py:313-316, 547-550) -- recorded
+    while searching for starts that take SCG's delta <= 0 branch (tools/scg_branch_search.py;
+    that branch, scaled_cg.py:233-236, showed up on such starts only, so no reference golden
+    pins it: it is covered by the host code reading line by line like :232-236 and by the
+    CUDA variants agreeing with each other, test_scg_switches_agree).  The device run must end
+    the same way: the reference's exception, not a silent result.
+    """
+    name, M_, seed = WILD[case]
+    g0 = load_golden("scg", name)
+    D_ = int(np.atleast_1d(g0["sigma"]).size)
+    M0 = int(g0["obs_times"].size)
+    mp = g0["x0"][:D_ * (3 * M0 + 4)].reshape(D_, 3 * M0 + 4)[:, :3 * M_ + 4]
+    sp = g0["x0"][D_ * (3 * M0 + 4):].reshape(D_, 2 * M0 + 3)[:, :2 * M_ + 3]
+    g = dict(g0)
+    g["obs_times"], g["obs_values"] = g0["obs_times"][:M_], g0["obs_values"][:M_]
+    r = np.random.default_rng(seed)
+    am, asg = float(r.choice([0.2, 0.5, 1.0, 2.0])), float(r.choice([0.6, 0.8, 1.0, 1.2]))
+    nm = D_ * (3 * M_ + 4)
+    x0 = np.concatenate((mp.ravel(), sp.ravel()))
+    x0[:nm] += am * r.standard_normal(nm)
+    x0[nm:] += asg * r.standard_normal(x0.size - nm)
+    fe = make_free_energy(g)
+    with pytest.raises(RuntimeError, match="is not a finite number"):
+        fe.find_minimum(x0.copy(), max_iter=40)
 
 
 def test_scg_tensor_in_place_and_floor():

@@ -7,7 +7,8 @@ against the reference itself, live.
 import numpy as np
 import pytest
 
-from helpers import (EVAL_CASES, REFINE_CASES, SCG_CASES, load_golden, make_oracle, rel_err)
+from helpers import (EVAL_CASES, REFINE_CASES, SCG_BRANCH_CASES, SCG_CASES, load_golden,
+                     make_oracle, rel_err)
 
 RTOL = 1.0e-12
 
@@ -64,11 +65,20 @@ def test_gradient_columns_never_integrated_are_obs_only():
         assert np.all(gm[:, c] == 0.0)
 
 
-@pytest.mark.parametrize("name", ["OU"])
+@pytest.mark.parametrize("name", ["OU"] + SCG_BRANCH_CASES)
 def test_oracle_scg_matches_reference_trajectory(name):
     g = load_golden("scg", name)
     o = make_oracle(g, adaptive=True)
-    x, fx, stats = o.find_minimum(g["x0"].copy(), max_iter=int(g["max_iter"]))
+    ev = {}
+    x, fx, stats = o.find_minimum(g["x0"].copy(), max_iter=int(g["max_iter"]), events=ev)
+    if name in SCG_BRANCH_CASES:
+        # the reference's run rejected trial points, reset a non-descent direction and
+        # restarted after dim_x successes -- and the restatement takes every one of them
+        assert int(g["func_eval"]) < 3 * int(g["nit"]) + 1
+        assert (ev["reject"], ev["mu>=0"], ev["restart"]) == (
+            int(g["n_reject"]), int(g["n_mu_ge0"]), int(g["n_restart"]))
+        assert ev["reject"] >= 4 and ev["mu>=0"] >= 1 and ev["restart"] >= 2
+        assert rel_err(stats["dfx"][:stats["nit"]], g["dfx_hist"][:stats["nit"]]) <= 1.0e-7
     assert stats["nit"] == int(g["nit"]) and stats["func_eval"] == int(g["func_eval"])
     nit = stats["nit"]
     assert rel_err(stats["fx"][:nit], g["fx_hist"][:nit]) <= 1.0e-9
