@@ -20,6 +20,8 @@
 #include "trajectory.cuh"
 #include "scg.cuh"
 #include "eparam.cuh"
+#include "peer.cuh"
+#include "walk_tail.cuh"
 
 using namespace mfvgp;
 
@@ -103,6 +105,18 @@ struct mfvgp_handle {
     double *gather = nullptr;                            // [world][16]
     double *xchg_send = nullptr, *xchg_gather = nullptr; // one-collective exchange: [16 + 4D], [world][..]
     double *rec_ws = nullptr;                            // [16] local record before combine
+    // peer-memory exchange (peer.cuh): this rank's mailbox and the peers' as mapped here
+    double *mbox = nullptr;
+    double *peer_box[kPeerMaxWorld] = {};
+    bool peer_ok = false;
+    int64_t peer_slot = 0;
+    long long xchg_epoch = 0;
+    unsigned *peer_ticket = nullptr;
+    int peer_nchunk = 1;
+    // walk path tail (walk_tail.cuh)
+    double *tail_part = nullptr;
+    int32_t *tail_late = nullptr;
+    bool walk_tail = true;        // MFVGP_WALK_TAIL=0: guard / final / exchange as separate launches
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     double *eparam_ws = nullptr;  // mfvgp_eparam: [nl][D] + [nl * ntiles][kMaxTheta] + out + gather
@@ -153,9 +167,10 @@ extern "C" int mfvgp_describe(const mfvgp_handle *h, char *buf, int buflen) {
     }
     const int n = snprintf(buf, (size_t)buflen,
                            "system=%s path=%s kernel=%s te=%d tn=%d ntiles=%d nruns=%d D=%d M=%d "
-                           "intervals=%d..%d world=%d",
+                           "intervals=%d..%d world=%d xchg=%s",
                            sys[h->system], path, kern, te, tn, nt, nr, h->D, h->M, h->n_begin,
-                           h->n_end, h->world);
+                           h->n_end, h->world,
+                           h->world == 1 ? "none" : (h->peer_ok ? "peer" : (h->one_collective ? "nccl" : "split")));
     return n < buflen ? n : buflen - 1;
 }
 
@@ -365,6 +380,13 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     CK(cudaMalloc((void **)&h->flags, L * sizeof(int32_t)));
 
     CK(cudaMalloc((void **)&h->status_ws, sizeof(int32_t)));
+    if (dev_alloc(&h->tail_part, (size_t)((nl + 7) / 8) * 4)) return MFVGP_ERR_CUDA;
+    CK(cudaMalloc((void **)&h->tail_late, sizeof(int32_t)));
+    CK(cudaMemset(h->tail_late, 0, sizeof(int32_t)));
+    {
+        const char *e = getenv("MFVGP_WALK_TAIL");
+        h->walk_tail = !(e && e[0] == '0');
+    }
     CK(cudaMemset(h->flags, 0, L * sizeof(int32_t)));
     CK(cudaMemset(h->esde_n, 0, L * sizeof(double)));
     CK(cudaMallocHost((void **)&h->pin, 16 * sizeof(double)));
@@ -389,9 +411,13 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->gather, h->xchg_send, h->xchg_gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
                     h->y_dense, h->rinv_row, h->head_flag, h->refine_gpart,
                     h->refine_gbar, h->b_dm, h->b_ds, h->b_part, h->b_apart, h->b_esde_n,
-                    h->b_flags, h->b_rstat, h->b_ticket, h->eparam_ws};
+                    h->b_flags, h->b_rstat, h->b_ticket, h->eparam_ws, h->tail_part, h->tail_late};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (int r = 0; r < h->world && r < kPeerMaxWorld; ++r)
+        if (h->peer_ok && r != h->rank && h->peer_box[r]) cudaIpcCloseMemHandle(h->peer_box[r]);
+    if (h->mbox) cudaFree(h->mbox);
+    if (h->peer_ticket) cudaFree(h->peer_ticket);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->scg_hostrec) cudaFreeHost(h->scg_hostrec);
@@ -666,6 +692,7 @@ static int launch_walk(mfvgp_handle *h, const double *x, double *grad, cudaStrea
         CK(cudaEventRecord(ev1, st));
         h->timing_events.emplace_back(ev0, ev1);
     }
+    if (h->walk_tail && (h->world == 1 || h->peer_ok)) return MFVGP_OK;   // launch_walk_tail follows
     // refined dS integrals come back as (refined - fixed) in ds_ws and are applied below
     rc = launch_guard_refine(h, x, h->Nm, lvar, h->Ns, 1, grad ? h->ds_ws : nullptr,
                              h->fntiles, 1, st);
@@ -691,9 +718,28 @@ static int launch_walk(mfvgp_handle *h, const double *x, double *grad, cudaStrea
         }                                                                     \
     } while (0)
 
+// one exchange over peer memory (peer.cuh): every rank's record to every rank, the shared
+// gradient columns to the neighbours; folded in rank order on arrival
+static int peer_exchange(mfvgp_handle *h, const double *rec, int n_rec, int n_sum, double *out,
+                         int32_t *status_out, double *grad, cudaStream_t st) {
+    PeerArgs a;
+    for (int r = 0; r < kPeerMaxWorld; ++r) a.box[r] = r < h->world ? h->peer_box[r] : nullptr;
+    a.slot_doubles = h->peer_slot; a.epoch = ++h->xchg_epoch; a.ticket = h->peer_ticket;
+    a.status = h->refine_status; a.rec = rec; a.out = out; a.status_out = status_out;
+    a.grad = grad; a.n_rec = n_rec; a.n_sum = n_sum;
+    a.D = h->D; a.Nm = h->Nm; a.Ns = h->Ns; a.n_begin = h->n_begin; a.n_end = h->n_end;
+    a.rank = h->rank; a.world = h->world;
+    const unsigned grid = grad ? (unsigned)((h->D + 255) / 256) : 1u;
+    CK(launch_pdl(peer_publish_kernel, dim3(grid), 256, st, a));
+    CK(launch_pdl(peer_combine_kernel, dim3(grid), 256, st, a));
+    h->launches += 2;
+    return MFVGP_OK;
+}
+
 // all-gather `n` doubles from every rank and fold them in rank order
 static int combine_over_ranks(mfvgp_handle *h, const double *local, int n, int nsum,
                               double *out, int32_t *status, cudaStream_t st) {
+    if (h->peer_ok) return peer_exchange(h, local, n, nsum, out, status, nullptr, st);
     NCK(nccl().AllGather(local, h->gather, n, kNcclFloat64, h->comm, st));
     combine_record_kernel<<<1, 32, 0, st>>>(h->gather, h->world, n, nsum, out, status);
     h->launches++;
@@ -726,6 +772,12 @@ static int launch_final(mfvgp_handle *h, const double *apart, int napart, double
     else final_kernel<<<1, 256, 0, st>>>(f);
     h->launches++;
     CK(cudaGetLastError());
+    if (multi && grad != nullptr && h->peer_ok) {
+        int rc = peer_exchange(h, h->rec_ws, kRecordLen, kRecordLen, h->rec_ws, status, grad, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out, h->rec_ws, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        return MFVGP_OK;
+    }
     if (multi && grad != nullptr && h->one_collective) {
         XchgArgs x;
         x.grad = grad; x.rec = h->rec_ws; x.send = h->xchg_send; x.gathered = h->xchg_gather;
@@ -781,6 +833,64 @@ static int exchange_edges(mfvgp_handle *h, double *grad, cudaStream_t st) {
     return MFVGP_OK;
 }
 
+// walk path: everything behind the main kernel (walk_tail.cuh) -- guard + scalar sums + record
+// and shared columns to the peers in one kernel, the adaptive path's kernels (no-ops unless an
+// interval is flagged), and on sharded handles the kernel that waits for the peers and folds
+static int launch_walk_tail(mfvgp_handle *h, const double *x, double *grad, double *out,
+                            int32_t *status, cudaStream_t st) {
+    const int nl = h->n_end - h->n_begin;
+    const bool multi = h->world > 1;
+    const double *lvar = x + (int64_t)h->D * h->Nm;
+    double *gs = grad ? grad + (int64_t)h->D * h->Nm : nullptr;
+    if (h->inject_status) {              // tests: a status bit raised on this rank only
+        or_status_kernel<<<1, 1, 0, st>>>(h->refine_status, h->inject_status);
+        CK(cudaGetLastError());
+    }
+    WalkLateArgs la;
+    WalkTailArgs &t = la.t;
+    t.g.part = h->part; t.g.obs_times = h->obs_times; t.g.esde_n = h->esde_n; t.g.flags = h->flags;
+    t.g.n_begin = h->n_begin; t.g.n_end = h->n_end; t.g.ntiles = h->fntiles;
+    t.g.nflagged = h->refine_status + 1;
+    t.apart = h->fapart; t.napart = h->fntn * h->fntiles;
+    t.tpart = h->tail_part; t.ticket = h->tickets + h->L + 3; t.late = h->tail_late;
+    t.out = multi ? h->rec_ws : out; t.status = status; t.refine_status = h->refine_status;
+    t.gbar = h->refine_gbar; t.ngbar = h->refine_grid / h->refine_group;
+    t.with_e0 = h->n_begin == 0;
+    t.eobs_const = h->n_begin == 0 ? h->eobs_const : 0.0;
+    t.guard_ctas = (nl + 7) / 8;
+    t.nchunk = h->peer_nchunk;
+    PeerArgs &p = t.p;
+    for (int r = 0; r < kPeerMaxWorld; ++r) p.box[r] = r < h->world ? h->peer_box[r] : nullptr;
+    p.slot_doubles = h->peer_slot; p.epoch = multi ? ++h->xchg_epoch : 0; p.ticket = nullptr;
+    p.status = h->refine_status; p.rec = h->rec_ws; p.out = h->rec_ws; p.status_out = status;
+    p.grad = multi ? grad : nullptr; p.n_rec = kPeerRec; p.n_sum = kPeerRec;
+    p.D = h->D; p.Nm = h->Nm; p.Ns = h->Ns; p.n_begin = h->n_begin; p.n_end = h->n_end;
+    p.rank = h->rank; p.world = h->world;
+    const int edge_ctas = (multi && grad) ? h->peer_nchunk : 0;
+    CK(launch_pdl(walk_tail_kernel, dim3(t.guard_ctas + edge_ctas), 256, st, t));
+    h->launches++;
+    // adaptive path: refined dS integrals come back as (refined - fixed) in ds_ws
+    int rc = launch_refine(h, x, h->Nm, lvar, h->Ns, 1, grad ? h->ds_ws : nullptr, 1, st);
+    if (rc) return rc;
+    if (grad != nullptr) {
+        ApplyRefineArgs ar;
+        ar.flags = h->flags; ar.nflagged = h->refine_status + 1; ar.delta = h->ds_ws; ar.x = x;
+        ar.gs = gs;
+        ar.D = h->D; ar.Nm = h->Nm; ar.Ns = h->Ns; ar.n_begin = h->n_begin; ar.n_end = h->n_end;
+        CK(launch_pdl(apply_refine_kernel, dim3(nl + 1), 256, st, ar));
+        h->launches++;
+    }
+    la.esde_n = h->esde_n; la.flags = h->flags;
+    CK(launch_pdl(walk_late_kernel, dim3(1 + edge_ctas), 256, st, la));
+    h->launches++;
+    if (multi) {
+        CK(launch_pdl(walk_combine_kernel, dim3(grad ? h->peer_nchunk : 1), 256, st, p,
+                      h->peer_nchunk, out));
+        h->launches++;
+    }
+    return MFVGP_OK;
+}
+
 extern "C" int mfvgp_comm_unique_id(void *id128_out) {
     ARG(id128_out != nullptr, "mfvgp_comm_unique_id: NULL argument");
     if (!nccl().load()) { g_err = "NCCL (libnccl.so.2) could not be loaded"; return MFVGP_ERR_CUDA; }
@@ -809,6 +919,74 @@ extern "C" int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void 
     {
         const char *e = getenv("MFVGP_XCHG");
         h->one_collective = !(e && std::string(e) == "split");
+    }
+    {
+        // peer mailboxes (peer.cuh): allocate, exchange the IPC handles through the communicator,
+        // map every peer's.  MFVGP_XCHG=nccl|split keeps the collectives; so does any failure
+        // here (e.g. ranks that cannot map each other's memory), reported by mfvgp_describe.
+        const char *e = getenv("MFVGP_XCHG");
+        const bool want = world <= kPeerMaxWorld && !(e && (std::string(e) == "nccl" || std::string(e) == "split"));
+        if (want) {
+            h->peer_nchunk = (h->D + 255) / 256;
+            h->peer_slot = ((int64_t)world * kPeerRec + 4 * (int64_t)h->D + world + 2
+                            + 2 * (int64_t)h->peer_nchunk + 1) / 2 * 2;
+            const size_t bytes = 2 * (size_t)h->peer_slot * sizeof(double);
+            CK(cudaMalloc((void **)&h->mbox, bytes));
+            CK(cudaMemset(h->mbox, 0, bytes));
+            CK(cudaMalloc((void **)&h->peer_ticket, sizeof(unsigned)));
+            CK(cudaMemset(h->peer_ticket, 0, sizeof(unsigned)));
+            cudaIpcMemHandle_t mine;
+            std::vector<cudaIpcMemHandle_t> all(world);
+            bool ok = cudaIpcGetMemHandle(&mine, h->mbox) == cudaSuccess;
+            if (!ok) cudaGetLastError();
+            // 64 handle bytes + 1 "ok" word per rank, gathered as doubles
+            static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+            double *hs = nullptr, *hr = nullptr;
+            if (dev_alloc(&hs, 9) || dev_alloc(&hr, 9 * (size_t)world)) return MFVGP_ERR_CUDA;
+            double pack[9];
+            memcpy(pack, &mine, 64);
+            pack[8] = ok ? 1.0 : 0.0;
+            CK(cudaMemcpy(hs, pack, sizeof(pack), cudaMemcpyHostToDevice));
+            CK(cudaDeviceSynchronize());
+            NCK(nccl().AllGather(hs, hr, 9, kNcclFloat64, h->comm, nullptr));
+            CK(cudaDeviceSynchronize());
+            std::vector<double> got(9 * (size_t)world);
+            CK(cudaMemcpy(got.data(), hr, got.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            cudaFree(hs);
+            cudaFree(hr);
+            for (int r = 0; r < world; ++r) ok = ok && got[9 * r + 8] == 1.0;
+            for (int r = 0; r < world && ok; ++r) {
+                if (r == rank) { h->peer_box[r] = h->mbox; continue; }
+                cudaIpcMemHandle_t hd;
+                memcpy(&hd, &got[9 * r], 64);
+                void *ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = false;
+                    break;
+                }
+                h->peer_box[r] = static_cast<double *>(ptr);
+            }
+            // every rank must take the same path: agree on the outcome
+            double *fs = nullptr, *fr = nullptr;
+            if (dev_alloc(&fs, 1) || dev_alloc(&fr, (size_t)world)) return MFVGP_ERR_CUDA;
+            const double mineok = ok ? 1.0 : 0.0;
+            CK(cudaMemcpy(fs, &mineok, sizeof(double), cudaMemcpyHostToDevice));
+            CK(cudaDeviceSynchronize());
+            NCK(nccl().AllGather(fs, fr, 1, kNcclFloat64, h->comm, nullptr));
+            CK(cudaDeviceSynchronize());
+            std::vector<double> oks(world);
+            CK(cudaMemcpy(oks.data(), fr, world * sizeof(double), cudaMemcpyDeviceToHost));
+            cudaFree(fs);
+            cudaFree(fr);
+            bool all_ok = true;
+            for (int r = 0; r < world; ++r) all_ok = all_ok && oks[r] == 1.0;
+            if (!all_ok) {
+                for (int r = 0; r < world; ++r)
+                    if (r != rank && h->peer_box[r]) { cudaIpcCloseMemHandle(h->peer_box[r]); h->peer_box[r] = nullptr; }
+            }
+            h->peer_ok = all_ok;
+        }
     }
     if (dev_alloc(&h->edge_send, 4 * (size_t)h->D) || dev_alloc(&h->edge_recv, 4 * (size_t)h->D) ||
         dev_alloc(&h->gather, 16 * (size_t)world) ||
@@ -868,7 +1046,9 @@ static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double 
     if (h->fused) {
         rc = launch_walk(h, x_d, want_grad ? grad_d : nullptr, st);
         if (rc) return rc;
-        if (h->world > 1 && want_grad && !h->one_collective) {
+        if (h->walk_tail && (h->world == 1 || h->peer_ok))
+            return launch_walk_tail(h, x_d, want_grad ? grad_d : nullptr, out_d, status_d, st);
+        if (h->world > 1 && want_grad && !h->one_collective && !h->peer_ok) {
             rc = exchange_edges(h, grad_d, st);
             if (rc) return rc;
         }
@@ -919,7 +1099,7 @@ static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double 
     assemble_kernel<<<h->D, 256, 0, st>>>(a);
     h->launches++;
     CK(cudaGetLastError());
-    if (h->world > 1 && want_grad && !h->one_collective) {
+    if (h->world > 1 && want_grad && !h->one_collective && !h->peer_ok) {
         rc = exchange_edges(h, grad_d, st);
         if (rc) return rc;
     }

@@ -578,6 +578,8 @@ struct ApplyRefineArgs {
 
 __global__ void __launch_bounds__(256)
 apply_refine_kernel(const ApplyRefineArgs a) {
+    pdl_wait();                      // refine_kernel's deltas (no-ops after a plain launch)
+    pdl_launch_dependents();
     if (a.nflagged != nullptr && a.nflagged[0] == 0) return;
     const int n = a.n_begin + blockIdx.x;             // n_end itself: last shared column only
     const bool f_own = n < a.n_end && (a.flags[n] & 2);

@@ -62,7 +62,7 @@ def test_scg_rare_branches_match_reference(name, variant, monkeypatch):
     assert rel_err(x, g["x_opt"]) <= 1.0e-6
 
 
-WILD = {"OU2": ("OU", 2, 290291082), "L96_8": ("L96_8", 2, 672604860)}
+WILD = {"OU2": ("OU", 2, 290291082)}
 
 
 @pytest.mark.parametrize("case", sorted(WILD))
