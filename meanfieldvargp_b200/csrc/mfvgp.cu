@@ -1709,8 +1709,29 @@ struct ScgRun {
         }
         return fa;
     }
+    bool peer_rec = false;       // sharded over peer memory: folds publish to the host record too
     int fold() {
         if (fused) return MFVGP_OK;
+        if (peer_rec) {
+            // fold + send in one kernel, then the rank-ordered fold, which also writes the
+            // host-mapped record: no memcpy, no stream synchronisation per read
+            PeerArgs a;
+            for (int r = 0; r < kPeerMaxWorld; ++r) a.box[r] = r < h->world ? h->peer_box[r] : nullptr;
+            a.slot_doubles = h->peer_slot; a.epoch = ++h->xchg_epoch; a.ticket = h->peer_ticket;
+            a.status = h->refine_status; a.rec = h->scg_scal; a.out = h->scg_scal;
+            a.status_out = nullptr; a.grad = nullptr; a.n_rec = 4; a.n_sum = 3;
+            a.D = h->D; a.Nm = h->Nm; a.Ns = h->Ns; a.n_begin = h->n_begin; a.n_end = h->n_end;
+            a.rank = h->rank; a.world = h->world;
+            a.fold_part = h->scg_part; a.fold_nblk = h->scg_nblk;
+            last_epoch = ++h->scg_epoch;
+            a.host_rec = h->scg_hostrec_dev + 32 * (last_epoch & 1);
+            a.host_epoch = last_epoch;
+            a.ecost_out = h->scg_scal + 4; a.ecost_status = h->status_ws;
+            CK(launch_pdl(scg_peer_fold_publish_kernel, dim3(1), kRedBlock, st, a));
+            CK(launch_pdl(peer_combine_kernel, dim3(1), 256, st, a));
+            h->launches += 2;
+            return MFVGP_OK;
+        }
         scg_fold_kernel<<<1, kRedBlock, 0, st>>>(h->scg_part, h->scg_nblk, h->scg_scal);
         h->launches++;
         CK(cudaGetLastError());
@@ -1746,7 +1767,7 @@ struct ScgRun {
     }
     // reads scal[0..3] (fold output), scal[4..7] (E_cost output) and the status
     int read(double *s8) {
-        if (fused) {
+        if (fused || peer_rec) {
             // the last reduction kernel publishes the record and then the epoch
             const double *rec;
             int rc = wait_record(last_epoch, &rec);
@@ -1943,6 +1964,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     {
         const char *e = getenv("MFVGP_SCG_FUSED");
         R.fused = h->world == 1 && !(e && e[0] == '0');
+        R.peer_rec = h->world > 1 && h->peer_ok && !(e && e[0] == '0');
         const char *c = getenv("MFVGP_SCG_CLUSTER");
         if (R.fused && n <= kClMaxElems && !(c && c[0] == '0')) {
             const bool wide = scg_cluster16_ok(h->device);

@@ -42,6 +42,14 @@ struct PeerArgs {
     double *grad;                     // gradient of x (edges), or nullptr: records only
     int n_rec, n_sum;                 // record length; slots < n_sum are summed, the rest max'ed
     int D, Nm, Ns, n_begin, n_end, rank, world;
+    // SCG folds: the folded sums also go to the host-mapped record the control loop spins on
+    // (scg.cuh FoldArgs: [0..3] sums, [4..7] F, E0, Esde, Eobs of the last E_cost, [8] its status)
+    double *host_rec = nullptr;       // [32] host-mapped, or nullptr
+    long long host_epoch = 0;
+    const double *ecost_out = nullptr;
+    const int32_t *ecost_status = nullptr;
+    const double *fold_part = nullptr;   // scg_peer_fold_publish_kernel: [fold_nblk][4] partials
+    int fold_nblk = 0;
 };
 
 __device__ __forceinline__ double *peer_rec(double *box, const PeerArgs &a, int r) {
@@ -153,6 +161,13 @@ peer_combine_kernel(const PeerArgs a) {
         a.out[i] = v;
         sh_rec[i] = v;
         __syncwarp();
+        if (i == 0 && a.host_rec != nullptr) {
+            for (int k = 0; k < a.n_rec && k < 4; ++k) a.host_rec[k] = sh_rec[k];
+            for (int k = 0; k < 4; ++k) a.host_rec[4 + k] = a.ecost_out[k];
+            a.host_rec[8] = (double)(a.ecost_status[0] | (sh_ok ? 0 : 32));
+            __threadfence_system();
+            *reinterpret_cast<volatile long long *>(a.host_rec + 24) = a.host_epoch;
+        }
         if (i == 0 && a.status_out != nullptr) {
             int32_t st = sh_ok ? 0 : 32;
             for (int b = 0; b < kStatusBits; ++b)

@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "peer.cuh"
+
 namespace mfvgp {
 
 constexpr int kRedBlock = 256;
@@ -720,6 +722,26 @@ scg_cl_stats_direction_kernel(const double *g_now, const double *g_new, double *
 #endif
     }
 #undef TQ
+}
+
+// Sharded runs: second stage and exchange in one -- folds this rank's per-block partials in
+// fixed order and sends the four sums to every rank's mailbox (peer.cuh); peer_combine_kernel
+// follows, folds the ranks' sums in rank order and publishes them to the host record.
+__global__ void __launch_bounds__(kRedBlock)
+scg_peer_fold_publish_kernel(const PeerArgs a) {
+    __shared__ double sh[kRedSlots][kRedBlock / 32];
+    scg_pdl_enter();
+    double r[kRedSlots];
+    fold_partials(a.fold_part, a.fold_nblk, r, sh);
+    if (threadIdx.x == 0) {
+        for (int p = 0; p < a.world; ++p) {
+            double *dst = peer_rec(a.box[p], a, a.rank);
+#pragma unroll
+            for (int i = 0; i < kRedSlots; ++i) dst[i] = r[i];
+        }
+        __threadfence_system();
+        for (int p = 0; p < a.world; ++p) st_release_sys(peer_flag(a.box[p], a, a.rank), a.epoch);
+    }
 }
 
 // Second stage: one block folds the per-block partials in a fixed order.

@@ -25,7 +25,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ev.sort(key=lambda e: e.time_range.end)          # PDL successors become resident early: order by END
 rows = [(e.name.split("(")[0].split("::")[-1][:34], e.time_range.start, e.time_range.end - e.time_range.start) for e in ev]
-walks = [i for i, r in enumerate(rows) if "walk" in r[0]]
+walks = [i for i, r in enumerate(rows) if "esde_l96_walk" in r[0]]
 lines = []
 if len(walks) >= 6:
     i0, i1 = walks[4], walks[5]
