@@ -2240,9 +2240,13 @@ extern "C" int mfvgp_reconstruct(int D, int M, int num, const double *Tx_d,
     a.tt = tt_d; a.mt = mt_d; a.st = st_d;
     a.P = ((int64_t)M + 1) * num + 1;
     a.D = D; a.M = M; a.num = num;
-    const int64_t nbx = (a.P + 255) / 256;
     ARG(a.P < 4294967296LL, "mfvgp_reconstruct: too many samples (P must fit 32 bits)");
-    reconstruct_kernel<<<dim3((unsigned)nbx, (unsigned)((D + kReconRows - 1) / kReconRows)), 256, 0, st>>>(a);
+    const int64_t nbx = (a.P + 255) / 256;
+    // 64 rows per CTA once that still leaves several CTAs per SM, fewer for small problems
+    int groups = kReconGroups;
+    while (groups > 1 && nbx * ((D + kReconRows * groups - 1) / (kReconRows * groups)) < 8 * 148) groups /= 2;
+    const int rows_per_cta = kReconRows * groups;
+    reconstruct_kernel<<<dim3((unsigned)nbx, (unsigned)((D + rows_per_cta - 1) / rows_per_cta)), 256, 0, st>>>(a, groups);
     CK(cudaGetLastError());
     if (vexp) CK(cudaFreeAsync(vexp, st));
     return MFVGP_OK;
@@ -2260,10 +2264,12 @@ extern "C" int mfvgp_reconstruct_host(int device, int D, int M, int num, const d
     CK(use_device(device));
     const int64_t Nm = 3 * (int64_t)M + 4, Ns = 2 * (int64_t)M + 3, P = ((int64_t)M + 1) * num + 1;
     double *buf = nullptr;
-    const size_t n_in = (size_t)(M + 2) + (size_t)D * (Nm + Ns), n_out = (size_t)P * (2 * (size_t)D + 1);
+    auto pad4 = [](size_t n) { return (n + 3) / 4 * 4; };      // keep every block 32-byte aligned
+    const size_t n_in = pad4((size_t)(M + 2)) + pad4((size_t)D * Nm) + pad4((size_t)D * Ns);
+    const size_t n_out = pad4((size_t)P) + 2 * pad4((size_t)D * P);
     CK(cudaMalloc((void **)&buf, (n_in + n_out) * sizeof(double)));
-    double *Tx = buf, *mp = Tx + (M + 2), *sp = mp + (size_t)D * Nm, *tt = sp + (size_t)D * Ns,
-           *mt = tt + P, *st = mt + (size_t)D * P;
+    double *Tx = buf, *mp = Tx + pad4((size_t)(M + 2)), *sp = mp + pad4((size_t)D * Nm),
+           *tt = sp + pad4((size_t)D * Ns), *mt = tt + pad4((size_t)P), *st = mt + pad4((size_t)D * P);
     int rc = MFVGP_OK;
     cudaError_t e = cudaMemcpy(Tx, Tx_h, (M + 2) * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(mp, mean_pts_h, (size_t)D * Nm * sizeof(double), cudaMemcpyHostToDevice);
