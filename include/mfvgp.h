@@ -135,8 +135,16 @@ void mfvgp_host_free(void *p);
  * FreeEnergy.E_kl0(m0, s0, output_gradients) (free_energy.py:281-336) and
  * FreeEnergy.E_obs(mean_pts[d][M], vars_pts[d][M], output_gradients)
  * (:567-649) as stand-alone calls; E_cost computes both terms itself.
- * Returned energies carry the reference's 1/2 factor (:335, :648).
+ * Returned energies carry the reference's 1/2 factor (:335, :648).  Device-pointer entries
+ * (caller's stream, no synchronisation) and host-buffer entries (copies inside).
  */
+int mfvgp_ekl0(mfvgp_handle *h, const double *m0_d /*[D]*/, const double *s0_d /*[D]*/,
+               int want_grad, double *E0_d /*[1]*/, double *dE0_dm0_d /*[D]*/,
+               double *dE0_ds0_d /*[D]*/, int32_t *status_d, void *cuda_stream);
+int mfvgp_eobs(mfvgp_handle *h, const double *mean_obs_d /*[d][M]*/,
+               const double *vars_obs_d /*[d][M]*/, int want_grad, double *Eobs_d /*[1]*/,
+               double *dEobs_dm_d /*[d][M]*/, double *dEobs_ds_d /*[d][M]*/, int32_t *status_d,
+               void *cuda_stream);
 int mfvgp_ekl0_host(mfvgp_handle *h, const double *m0_h /*[D]*/,
                     const double *s0_h /*[D]*/, int want_grad, double *E0_h,
                     double *dE0_dm0_h /*[D]*/, double *dE0_ds0_h /*[D]*/,

@@ -6,6 +6,7 @@ include/mfvgp.h.
 """
 from ._lib import MfvgpError, load as load_library          # noqa: F401
 from .free_energy import FreeEnergy                          # noqa: F401
+from .scaled_cg import SCG                                   # noqa: F401
 from .posterior import (initial_path, initial_state, pack,   # noqa: F401
                         reconstruct, support_indices, time_knots, unpack)
 from .trajectory import (collect_obs, simulate_dw, simulate_l63,   # noqa: F401
@@ -13,7 +14,7 @@ from .trajectory import (collect_obs, simulate_dw, simulate_l63,   # noqa: F401
 from .systems import (DoubleWell, Lorenz63, Lorenz96,        # noqa: F401
                       OrnsteinUhlenbeck, StochasticProcess)
 
-__all__ = ["FreeEnergy", "DoubleWell", "OrnsteinUhlenbeck", "Lorenz63", "Lorenz96",
+__all__ = ["FreeEnergy", "SCG", "DoubleWell", "OrnsteinUhlenbeck", "Lorenz63", "Lorenz96",
            "StochasticProcess", "MfvgpError", "load_library", "reconstruct",
            "support_indices", "pack", "unpack", "time_knots", "initial_path", "initial_state", "simulate_l96", "simulate_dw", "simulate_ou",
            "simulate_l63", "collect_obs"]

@@ -36,6 +36,8 @@ SIGNATURES = {
     "mfvgp_ecost_host_packed": (c_int, [c_void_p, _P, c_int, _P]),
     "mfvgp_host_alloc": (c_void_p, [c_int64]),
     "mfvgp_host_free": (None, [c_void_p]),
+    "mfvgp_ekl0": (c_int, [c_void_p, _P, _P, c_int, _P, _P, _P, _P, c_void_p]),
+    "mfvgp_eobs": (c_int, [c_void_p, _P, _P, c_int, _P, _P, _P, _P, c_void_p]),
     "mfvgp_ekl0_host": (c_int, [c_void_p, _P, _P, c_int, POINTER(c_double), _P, _P, POINTER(c_int32)]),
     "mfvgp_eobs_host": (c_int, [c_void_p, _P, _P, c_int, POINTER(c_double), _P, _P, POINTER(c_int32)]),
     "mfvgp_eparam": (c_int, [c_void_p, _P, _P, _P, _P, c_void_p]),

@@ -1413,6 +1413,40 @@ extern "C" int mfvgp_esde_host(mfvgp_handle *h, const double *mean_pts_h,
     return MFVGP_OK;
 }
 
+// E_kl0 / E_obs as stand-alone calls on DEVICE buffers (free_energy.py:281-336, 567-649)
+extern "C" int mfvgp_ekl0(mfvgp_handle *h, const double *m0_d, const double *s0_d, int want_grad,
+                          double *E0_d, double *dm0_d, double *ds0_d, int32_t *status_d,
+                          void *cuda_stream) {
+    ARG(h && m0_d && s0_d && E0_d && status_d, "mfvgp_ekl0: NULL argument");
+    ARG(!want_grad || (dm0_d && ds0_d), "mfvgp_ekl0: gradient buffers are NULL");
+    if (!h->have_prior) { g_err = "mfvgp_ekl0: set_prior not called"; return MFVGP_ERR_STATE; }
+    CK(use_device(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    ekl0_kernel<<<1, 256, 0, st>>>(m0_d, s0_d, h->mu0, h->tau0, h->D, E0_d,
+                                   want_grad ? dm0_d : nullptr, want_grad ? ds0_d : nullptr,
+                                   status_d);
+    h->launches++;
+    CK(cudaGetLastError());
+    return MFVGP_OK;
+}
+
+extern "C" int mfvgp_eobs(mfvgp_handle *h, const double *mean_obs_d, const double *vars_obs_d,
+                          int want_grad, double *Eobs_d, double *dm_d, double *ds_d,
+                          int32_t *status_d, void *cuda_stream) {
+    ARG(h && mean_obs_d && vars_obs_d && Eobs_d && status_d, "mfvgp_eobs: NULL argument");
+    ARG(!want_grad || (dm_d && ds_d), "mfvgp_eobs: gradient buffers are NULL");
+    if (!h->have_obs) { g_err = "mfvgp_eobs: set_obs not called"; return MFVGP_ERR_STATE; }
+    CK(use_device(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    eobs_rows_kernel<<<h->d, 256, 0, st>>>(mean_obs_d, vars_obs_d, h->obs_values, h->obs_noise,
+                                           h->d, h->M, h->apart, want_grad ? dm_d : nullptr,
+                                           want_grad ? ds_d : nullptr);
+    eobs_final_kernel<<<1, 256, 0, st>>>(h->apart, h->d, h->eobs_const, Eobs_d, status_d);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return MFVGP_OK;
+}
+
 // E_kl0 / E_obs as stand-alone calls on host buffers (free_energy.py:281-336, 567-649)
 extern "C" int mfvgp_ekl0_host(mfvgp_handle *h, const double *m0_h, const double *s0_h,
                                int want_grad, double *E0_h, double *dm0_h, double *ds0_h,

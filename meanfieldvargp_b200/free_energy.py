@@ -94,8 +94,12 @@ class FreeEnergy(object):
         self.num_mp = self.dim_D * (3 * self.num_M + 4)          # :168
         self.num_sp = self.dim_D * (2 * self.num_M + 3)
         self.num_L = self.num_M - 1                              # :490
-        self.ikm = [3 * i for i in range(1, self.num_M + 1)]
+        self.ikm = [3 * i for i in range(1, self.num_M + 1)]              # :171-172
         self.iks = [2 * i for i in range(1, self.num_M + 1)]
+        # mesh-grids that pick the observed rows at the observation columns (:176-177):
+        # mean_points[fe.ix_ikm], vars_points[fe.ix_iks] are what E_obs takes
+        self.ix_ikm = np.ix_(self.obs_mask, self.ikm)
+        self.ix_iks = np.ix_(self.obs_mask, self.iks)
 
         # ---- device side ------------------------------------------------
         self._lib = _lib.require_device()
@@ -260,10 +264,27 @@ class FreeEnergy(object):
     # ---- E_kl0, free_energy.py:281-336 ---------------------------------------
     def E_kl0(self, m0, s0, output_gradients=True):
         self._sync_params()
-        tensor_in = _is_tensor(m0)
-        m0h = _f64(m0.detach().cpu().numpy() if tensor_in else m0).reshape(self.dim_D)
-        s0h = _f64(s0.detach().cpu().numpy() if tensor_in else s0).reshape(self.dim_D)
         want = 1 if output_gradients else 0
+        if _is_tensor(m0):                   # tensors in -> tensors out, caller's stream
+            import torch
+            m0d = m0.contiguous().reshape(-1)
+            s0d = torch.as_tensor(s0, device=m0d.device).contiguous().reshape(-1)
+            D = self.dim_D
+            if m0d.numel() != D or s0d.numel() != D:
+                raise ValueError(f"E_kl0: m0 and s0 must have {D} entries")
+            res = torch.empty(2 + 2 * D, dtype=torch.float64, device=m0d.device)
+            p = res.data_ptr()
+            stream = torch.cuda.current_stream(m0d.device).cuda_stream
+            _lib.check(self._lib.mfvgp_ekl0(self._h, m0d.data_ptr(), s0d.data_ptr(), want, p,
+                                            p + 16 if want else None,
+                                            p + 16 + 8 * D if want else None, p + 8, stream),
+                       "mfvgp_ekl0")
+            self.last_out = None
+            if not output_gradients:
+                return res[0], None, None
+            return res[0], res[2:2 + D], res[2 + D:]
+        m0h = _f64(m0).reshape(self.dim_D)
+        s0h = _f64(s0).reshape(self.dim_D)
         E0, status = ctypes.c_double(), ctypes.c_int32()
         dm0 = np.empty(self.dim_D) if want else None
         ds0 = np.empty(self.dim_D) if want else None
@@ -280,6 +301,24 @@ class FreeEnergy(object):
     def E_obs(self, mean_pts, vars_pts, output_gradients=True):
         self._sync_params()
         d, M = self.dim_d, self.num_M
+        if _is_tensor(mean_pts):             # tensors in -> tensors out, caller's stream
+            import torch
+            mo = mean_pts.contiguous().reshape(d, M)
+            so = torch.as_tensor(vars_pts, device=mo.device).contiguous().reshape(d, M)
+            want = 1 if output_gradients else 0
+            res = torch.empty(2 + 2 * d * M, dtype=torch.float64, device=mo.device)
+            p = res.data_ptr()
+            stream = torch.cuda.current_stream(mo.device).cuda_stream
+            _lib.check(self._lib.mfvgp_eobs(self._h, mo.data_ptr(), so.data_ptr(), want, p,
+                                            p + 16 if want else None,
+                                            p + 16 + 8 * d * M if want else None, p + 8, stream),
+                       "mfvgp_eobs")
+            if not output_gradients:
+                return res[0], None, None
+            dm, ds = res[2:2 + d * M].view(d, M), res[2 + d * M:].view(d, M)
+            if d == 1:                                            # :637-642
+                return res[0], dm.squeeze(), ds.squeeze()
+            return res[0], dm, ds
         mo = _f64(mean_pts).reshape(d, M)
         so = _f64(vars_pts).reshape(d, M)
         want = 1 if output_gradients else 0
@@ -518,13 +557,32 @@ class FreeEnergy(object):
         max_iter = max(int(max_iter), 10)                          # :815-817
         x_tol = max(float(x_tol), 1.0e-20)
         f_tol = max(float(f_tol), 1.0e-20)
+        if verbose:
+            print("SCG: Optimization started ...")
+        time_t0 = perf_counter()
+        opt_x, opt_fx, stats = self._scg(x0, max_iter, x_tol, f_tol)
+        time_tf = perf_counter()
+        nit, fx_hist, dfx_hist = stats["nit"], stats["fx"], stats["dfx"]
+        if nit == max_iter:                                        # scaled_cg.py:376-385
+            print(f"SGC: Maximum number of iterations ({max_iter}) has been reached.")
+        if verbose:
+            for j in range(0, nit, 50):                           # scaled_cg.py:288-296
+                print(f"It= {j:>5}: F(x)= {fx_hist[j]:.3E} -:- "
+                      f"Sum(|Gradients|)= {dfx_hist[j]:.3E}")
+        print(f"Elapsed time [{nit}]: {(time_tf - time_t0):.2f} seconds.\n")
+        if check_gradients:
+            _grad_check("AFTER", opt_x.detach().cpu().numpy() if tensor_in else opt_x)
+        print("Done!")
+        return opt_x, opt_fx, stats
+
+    def _scg(self, x0, max_iter, x_tol, f_tol):
+        """SCG.minimize over E_cost on the device (mfvgp_scg): (x, fx, stats)."""
+        self._sync_params()
+        tensor_in = _is_tensor(x0)
         fx_hist = np.zeros(max_iter)
         dfx_hist = np.zeros(max_iter)
         result = np.zeros(4)
         n = self.num_mp + self.num_sp
-        if verbose:
-            print("SCG: Optimization started ...")
-        time_t0 = perf_counter()
         if tensor_in:
             import torch
             opt_x = x0.detach().clone().contiguous().reshape(-1)
@@ -541,18 +599,9 @@ class FreeEnergy(object):
             _lib.check(self._lib.mfvgp_scg_host(self._h, _ptr(opt_x), max_iter, x_tol, f_tol,
                                                 _ptr(fx_hist), _ptr(dfx_hist), _ptr(result)),
                        "mfvgp_scg_host")
-        time_tf = perf_counter()
         opt_fx, nit, func_eval, status = (float(result[0]), int(result[1]),
                                           int(result[2]), int(result[3]))
         self.last_status = status
         self._raise_on_status(status, E0=opt_fx, Esde=opt_fx, Eobs=opt_fx)
         stats = {"nit": nit, "fx": fx_hist, "dfx": dfx_hist, "func_eval": func_eval}
-        if verbose:
-            for j in range(0, nit, 50):                           # scaled_cg.py:288-296
-                print(f"It= {j:>5}: F(x)= {fx_hist[j]:.3E} -:- "
-                      f"Sum(|Gradients|)= {dfx_hist[j]:.3E}")
-        print(f"Elapsed time [{nit}]: {(time_tf - time_t0):.2f} seconds.\n")
-        if check_gradients:
-            _grad_check("AFTER", opt_x.detach().cpu().numpy() if tensor_in else opt_x)
-        print("Done!")
         return opt_x, opt_fx, stats

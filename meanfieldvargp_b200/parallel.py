@@ -31,25 +31,41 @@ def owned_columns(M, n0, n1):
 
 
 class ShardedFreeEnergy(object):
-    """E_cost of one problem evaluated by ``world`` ranks, intervals sharded."""
+    """
+    E_cost / find_minimum / grad_params of one problem evaluated by ``world`` ranks, the L = M-1
+    time intervals sharded in contiguous blocks (any of the four systems).  ``g``: the
+    constructor inputs as a dict (system, sigma, theta, mu0, tau0, obs_times, obs_values,
+    obs_noise, obs_mask).  A rank needs at least one interval: world <= L (SURVEY.md 8(e)'s
+    alternative for L < world, sharding the state dimensions with a 3-row halo, moves three
+    rows of every column per evaluation and is not built: such problems are far below one
+    wave of one GPU).
+    """
 
     def __init__(self, g, rank=0, world=1, device=None):
         import torch
-        from . import systems
+        from .synthetic import make_sde
         self.rank, self.world = rank, world
-        D = int(np.asarray(g["sigma"]).size)
-        sde = systems.Lorenz96(g["sigma"], float(np.atleast_1d(g["theta"])[0]), dim_D=D)
-        sde.time_window = np.array([0.0, float(g["obs_times"][-1]) + 1.0])
+        g = dict(g)
+        g.setdefault("system", "L96")
+        g["theta"] = np.atleast_1d(np.asarray(g["theta"], dtype=float))
+        g["sigma"] = np.atleast_1d(np.asarray(g["sigma"], dtype=float))
+        sde = make_sde(g)
         L = len(g["obs_times"]) - 1
         if world > L:
             raise ValueError(f"cannot shard {L} intervals over {world} ranks")
         self.range = shard_intervals(L, rank, world)
         dev = torch.cuda.current_device() if device is None else device
         self.local = FreeEnergy(sde, g["mu0"], g["tau0"], g["obs_times"], g["obs_values"],
-                                g["obs_noise"], g["obs_mask"], device=dev,
+                                g["obs_noise"], g.get("obs_mask"), device=dev,
                                 intervals=self.range if world > 1 else None)
         if world > 1:
             self.local.attach_communicator(rank, world)
 
     def E_cost(self, x, output_gradients=True):
         return self.local.E_cost(x, output_gradients)
+
+    def find_minimum(self, x0, **kw):
+        return self.local.find_minimum(x0, **kw)
+
+    def grad_params(self, x):
+        return self.local.grad_params(x)

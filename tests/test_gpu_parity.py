@@ -295,3 +295,41 @@ def test_single_observed_dimension_and_scalar_noise():
     g2["obs_noise"] = np.array([1.7])
     Fo, go = make_oracle(g2, adaptive=True).E_cost(g["x0"])
     assert abs(F - Fo) <= RTOL * abs(Fo) and rel_err(grad, go) <= RTOL
+
+
+def test_scg_class_surface_and_tensor_ekl0_eobs(capsys):
+    """SCG(func, options)(x0) -> (x, fx), .statistics (scaled_cg.py:25, 93-105, 388); the
+    ix_ikm / ix_iks attributes (free_energy.py:176-177); E_kl0 / E_obs on CUDA tensors"""
+    import torch
+    import meanfieldvargp_b200 as mf
+    g = load_golden("scg", "L96_8")
+    fe = make_free_energy(g)
+    opt = mf.SCG(fe.E_cost, {"max_it": int(g["max_iter"]), "x_tol": 1.0e-5, "f_tol": 1.0e-5})
+    with pytest.raises(NotImplementedError):
+        opt.statistics
+    x, fx = opt(g["x0"].copy())
+    st = opt.statistics
+    assert st["nit"] == int(g["nit"]) and st["func_eval"] == int(g["func_eval"])
+    assert abs(fx - float(g["fx_opt"])) <= 1e-8 * abs(float(g["fx_opt"]))
+    assert rel_err(x, g["x_opt"]) <= 1e-6
+    assert "Maximum number of iterations" in capsys.readouterr().out
+    with pytest.raises(TypeError):
+        mf.SCG(lambda v: (0.0, v))(g["x0"])
+    # E_obs through the reference's own index grids, numpy and tensor paths
+    D, M = fe.dim_D, fe.num_M
+    mp = g["x0"][:fe.num_mp].reshape(D, 3 * M + 4)
+    sp = np.exp(g["x0"][fe.num_mp:].reshape(D, 2 * M + 3))
+    o = make_oracle(g)
+    Eo, dmo, dso = o.E_obs(mp[o.ix_ikm], sp[o.ix_iks])
+    E1, dm1, ds1 = fe.E_obs(mp[fe.ix_ikm], sp[fe.ix_iks])
+    E2, dm2, ds2 = fe.E_obs(torch.tensor(mp[fe.ix_ikm], device="cuda"),
+                            torch.tensor(sp[fe.ix_iks], device="cuda"))
+    assert dm2.is_cuda and dm2.shape == dmo.shape
+    for E, dm, ds in ((E1, dm1, ds1), (float(E2), dm2.cpu().numpy(), ds2.cpu().numpy())):
+        assert abs(E - Eo) <= 1e-12 * abs(Eo) and rel_err(dm, dmo) <= 1e-12 and rel_err(ds, dso) <= 1e-12
+    K0, a0, b0 = o.E_kl0(mp[:, 0], sp[:, 0])
+    K2, a2, b2 = fe.E_kl0(torch.tensor(mp[:, 0], device="cuda"), torch.tensor(sp[:, 0], device="cuda"))
+    assert a2.is_cuda and abs(float(K2) - K0) <= 1e-12 * abs(K0)
+    assert rel_err(a2.cpu().numpy(), a0) <= 1e-12 and rel_err(b2.cpu().numpy(), b0) <= 1e-12
+    assert fe.E_kl0(torch.tensor(mp[:, 0], device="cuda"), torch.tensor(sp[:, 0], device="cuda"),
+                    output_gradients=False)[1] is None
