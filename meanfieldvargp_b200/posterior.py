@@ -106,7 +106,8 @@ def unpack(x, dim_D, num_M):
     return x[:nm].reshape(dim_D, 3 * num_M + 4), np.exp(x[nm:]).reshape(dim_D, 2 * num_M + 3)
 
 
-def initial_path(tk, obs_idk, obs_val, h_mask=None, sample_path=None, window=51, polyorder=3):
+def initial_path(tk, obs_idk, obs_val, h_mask=None, sample_path=None, window=51, polyorder=3,
+                 tf=None, dt=None):
     """
     The notebooks' initial sample path ``x0(t)`` [D, len(tk)] (example_500D.ipynb cell 14,
     :356-400): observed dimensions get the cubic B-spline through ``[obs[0], *obs, obs[-1]]`` at
@@ -116,6 +117,11 @@ def initial_path(tk, obs_idk, obs_val, h_mask=None, sample_path=None, window=51,
     :param obs_val: [M, d] noisy observations (d = number of observed dimensions)
     :param h_mask: [D] booleans (default: all observed)
     :param sample_path: [len(tk), D], needed only when some dimension is unobserved
+    :param tf, dt: the notebook's window end and step.  Its spline knots are
+                   ``[t0, *(obs_idk * dt), tf]`` with the NOMINAL ``tf`` -- ``tk`` itself runs one
+                   step further when ``np.arange(t0, tf + dt, dt)`` rounds up (T=[0,4], dt=1e-3:
+                   4 002 points, tk[-1] = 4.001) -- so pass both to reproduce the notebook's path
+                   (tests/golden/initial_*.npz); default: ``tk[-1]`` and ``tk[obs_idk]``.
     """
     from scipy.interpolate import splev, splrep
     from scipy.signal import savgol_filter
@@ -125,7 +131,9 @@ def initial_path(tk, obs_idk, obs_val, h_mask=None, sample_path=None, window=51,
         obs_val = obs_val[:, None]
     D = len(h_mask) if h_mask is not None else obs_val.shape[1]
     mask = [True] * D if h_mask is None else list(h_mask)
-    spl_timex = np.array([tk[0], *tk[np.asarray(obs_idk, dtype=int)], tk[-1]])
+    idk = np.asarray(obs_idk, dtype=int)
+    spl_timex = np.array([tk[0], *(tk[idk] if dt is None else idk * dt),
+                          tk[-1] if tf is None else tf])
     spl_value = np.array([obs_val[0], *obs_val, obs_val[-1]])
     x0, j = [], 0
     for i in range(D):

@@ -155,3 +155,57 @@ def test_initial_path_and_state_follow_the_notebook_cells():
     assert np.array_equal(x, np.concatenate((want[:, mp_idk].flatten(), sp.flatten())))
     with pytest.raises(ValueError, match="sample_path"):
         mf.initial_path(tk, obs_idk, obs_val, h_mask)
+
+
+# ---- initial state x0 against the reference's notebook cells ------------
+class _LegacyRand(object):
+    """the notebook's unseeded global ``np.random.rand`` (example_500D.ipynb cell 19), seeded"""
+
+    def __init__(self, seed):
+        self.rs = np.random.RandomState(seed)
+
+    def random(self, shape):
+        return self.rs.random_sample(shape)
+
+
+def _check_initial_state(g, sample_path, tk):
+    import meanfieldvargp_b200 as mf
+    # the path the notebook started from, regenerated bit for bit
+    assert np.array_equal(sample_path[1000], g["path_row_1000"])
+    assert np.array_equal(np.array([sample_path.sum(), np.abs(sample_path).sum()]), g["path_checksum"])
+    h_mask = [bool(b) for b in g["h_mask"]]
+    x0_path = mf.initial_path(tk, g["obs_idk"], g["obs_val"], h_mask, sample_path,
+                              tf=float(g["tf"]), dt=float(g["dt"]))
+    assert rel_err(x0_path[:, ::400], g["x0_path_probe"]) <= 1e-14       # cell 14
+    x, mp_idk, sp_idk = mf.initial_state(x0_path, g["obs_idk"], rng=_LegacyRand(int(g["np_random_seed"])))
+    assert np.array_equal(mp_idk, g["mp_idk"]) and np.array_equal(sp_idk, g["sp_idk"])   # cell 17
+    D, M = int(g["D"]), len(g["obs_idk"])
+    mp, sp = mf.unpack(x, D, M)
+    assert rel_err(mp, g["mp_t0"]) <= 1e-14                                # cell 19
+    assert rel_err(np.log(sp), g["sp_t0"]) <= 1e-14
+    assert rel_err(x, g["x"]) <= 1e-14                                     # cell 23's argument
+
+
+def test_initial_state_matches_the_reference_notebook_cells():
+    """tests/golden/initial_L96_24p.npz: cells 8, 10, 14, 17, 19 of examples/example_500D.ipynb
+    exec'ed from the notebook itself (oracle/ref_harness/make_golden_initial.py)"""
+    from oracle import trajectory_oracle as O
+    g = _load_any("initial_L96_24p")
+    tk, path = O.make_trajectory(g["sigma"], float(g["theta"][0]), int(g["D"]), float(g["t0"]),
+                                 float(g["tf"]), float(g["dt"]), r_seed=int(g["r_seed"]))
+    _check_initial_state(g, path, tk)
+
+
+@pytest.mark.gpu
+def test_initial_state_from_the_device_sample_path():
+    """the same, the sample path simulated on the device (csrc/trajectory.cuh, bit-identical)"""
+    import meanfieldvargp_b200 as mf
+    g = _load_any("initial_L96_24p")
+    tk, x = mf.simulate_l96(g["sigma"], float(g["theta"][0]), int(g["D"]), float(g["t0"]),
+                            float(g["tf"]), float(g["dt"]), r_seed=int(g["r_seed"]))
+    _check_initial_state(g, x.cpu().numpy(), tk.cpu().numpy())
+
+
+def _load_any(name):
+    z = np.load(GOLDEN / f"{name}.npz")
+    return {k: z[k] for k in z.files}
