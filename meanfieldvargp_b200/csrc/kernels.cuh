@@ -752,6 +752,12 @@ struct FinalArgs {
     int n_begin, n_end, D;    // D = number of apart rows (state dims, or CTAs of the walk / tail kernel)
     int with_e0;
     double eobs_const;        // M (d log 2pi + safe_log(prod R)), 0 on non-owning shards
+    // evaluation in two passes (mfvgp.cu ecost_impl, small problems on device pointers): the
+    // first pass runs without the adaptive kernels; if the guard flagged an interval it raises
+    // *late instead of cleaning up, refine_kernel then does its work and a second pass of the
+    // tail kernel (which returns at once while *late is 0) assembles again and cleans up.
+    int32_t *late = nullptr;        // first pass: set to 1 when an interval is flagged
+    int32_t *late_clear = nullptr;  // second pass: reset to 0 at the end
 };
 
 // body for a CTA of NT threads (also the tail of assemble_tail_kernel, l96_coop.cuh);
@@ -805,12 +811,17 @@ __device__ __forceinline__ void final_body(const FinalArgs &a) {
         if (!isfinite(Eobs)) st |= 4;
         if (sh_flag) st |= 8;
         st |= rs_pre;
-        a.refine_status[0] = 0;
-        if (a.nflagged != nullptr) {
-            if (nf_pre != 0)
-                for (int i = 0; i < a.ngbar; ++i) a.gbar[i] = 0u;
-            a.nflagged[0] = 0;
+        const bool hand_over = a.late != nullptr && nf_pre != 0;   // a second pass follows
+        if (hand_over) a.late[0] = 1;
+        if (!hand_over) {
+            a.refine_status[0] = 0;
+            if (a.nflagged != nullptr) {
+                if (nf_pre != 0)
+                    for (int i = 0; i < a.ngbar; ++i) a.gbar[i] = 0u;
+                a.nflagged[0] = 0;
+            }
         }
+        if (a.late_clear != nullptr) a.late_clear[0] = 0;
         // record[0..3] = F, E0, Esde, Eobs; record[4..9] = the six status bits as 0/1 so
         // that shards can be combined by summation (combine_record_kernel)
         a.out[0] = E0 + Esde + Eobs;

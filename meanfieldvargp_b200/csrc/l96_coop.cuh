@@ -324,6 +324,8 @@ struct TailArgs {
     GuardArgs g;               // guard_ctas > 0: the last guard_ctas CTAs of the grid fold the
     int guard_ctas;            // main kernel's tile partials and apply the guard, a warp per
                                // interval, beside the CTAs that assemble the gradient
+    const int32_t *run_if = nullptr;   // second pass of a two-pass evaluation: return at once
+                                       // unless *run_if != 0 (FinalArgs::late)
 };
 
 constexpr int kTailThreads = 256;
@@ -341,6 +343,10 @@ __device__ __forceinline__ void assemble_tail_body(const TailArgs &t) {
     const bool guard_cta = blockIdx.x >= gridDim.x - (unsigned)t.guard_ctas;
     double acc[3] = {0.0, 0.0, 0.0};
     pdl_launch_dependents();
+    if (t.run_if != nullptr) {
+        pdl_wait();
+        if (__ldcg(t.run_if) == 0) return;       // nothing was flagged: the first pass is the result
+    }
     if (idx0 >= ntot) pdl_wait();
     if (guard_cta) {
         const int nwarps = t.guard_ctas * (kTailThreads / 32);

@@ -117,6 +117,7 @@ struct mfvgp_handle {
     double *tail_part = nullptr;
     int32_t *tail_late = nullptr;
     bool walk_tail = true;        // MFVGP_WALK_TAIL=0: guard / final / exchange as separate launches
+    bool two_pass = true;         // MFVGP_TWO_PASS=0: coop path on device pointers as main -> refine -> tail
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     double *eparam_ws = nullptr;  // mfvgp_eparam: [nl][D] + [nl * ntiles][kMaxTheta] + out + gather
@@ -386,6 +387,8 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     {
         const char *e = getenv("MFVGP_WALK_TAIL");
         h->walk_tail = !(e && e[0] == '0');
+        const char *e2 = getenv("MFVGP_TWO_PASS");
+        h->two_pass = !(e2 && e2[0] == '0');
     }
     CK(cudaMemset(h->flags, 0, L * sizeof(int32_t)));
     CK(cudaMemset(h->esde_n, 0, L * sizeof(double)));
@@ -1058,9 +1061,14 @@ static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double 
     // optimistic L96 evaluations: no refine launch, and the guard moves from the main kernel's
     // last CTAs (ticket + fold on its critical path) into CTAs of the tail kernel
     const bool opt = optimistic && h->coop && h->world == 1;
-    const bool guard_later = opt && h->system == MFVGP_SYS_L96 && h->guard_in_tail;
+    // Lorenz 96 on device pointers (nobody reads the status before using the result): two
+    // passes.  The first is the optimistic one; the adaptive kernel and a second tail pass
+    // follow in the stream and return at once unless the first pass flagged an interval.
+    const bool two_pass = !optimistic && h->coop && h->world == 1 && h->system == MFVGP_SYS_L96 &&
+                          h->guard_in_tail && h->two_pass;
+    const bool guard_later = (opt || two_pass) && h->system == MFVGP_SYS_L96 && h->guard_in_tail;
     rc = launch_esde(h, mean, h->Nm, lvar, h->Ns, 1, want_grad ? h->dm_ws : nullptr,
-                     want_grad ? h->ds_ws : nullptr, st, opt, guard_later);
+                     want_grad ? h->ds_ws : nullptr, st, opt || two_pass, guard_later);
     if (rc) return rc;
     AssembleArgs a;
     a.x = x_d; a.dm = want_grad ? h->dm_ws : nullptr; a.ds = want_grad ? h->ds_ws : nullptr;
@@ -1091,9 +1099,19 @@ static int ecost_impl(mfvgp_handle *h, const double *x_d, int want_grad, double 
             t.guard_ctas = (nl + per_cta - 1) / per_cta;
             if (t.guard_ctas > 64) t.guard_ctas = 64;
         }
+        if (two_pass) t.f.late = h->tail_late;
         CK(launch_pdl(assemble_tail_kernel, dim3(nb + t.guard_ctas), kTailThreads, st, t));
         h->launches++;
         CK(cudaGetLastError());
+        if (two_pass) {
+            rc = launch_refine(h, mean, h->Nm, lvar, h->Ns, 1, want_grad ? h->ds_ws : nullptr, 0, st);
+            if (rc) return rc;
+            t.f.late = nullptr; t.f.late_clear = h->tail_late; t.run_if = h->tail_late;
+            t.guard_ctas = 0;
+            CK(launch_pdl(assemble_tail_kernel, dim3(nb), kTailThreads, st, t));
+            h->launches++;
+            CK(cudaGetLastError());
+        }
         return MFVGP_OK;
     }
     assemble_kernel<<<h->D, 256, 0, st>>>(a);
