@@ -211,10 +211,12 @@ struct WalkArgs {
     double theta;                // L96 forcing (lorenz_96.py:70)
     int D, M, d, Nm, Ns, L;
     int n_begin, n_end;          // intervals of this shard
-    int ntiles, nruns, TN;       // dim tiles, runs, intervals per run
-    int nshort, TNs;             // the first nshort runs are short (TNs intervals): they are taken
-                                 // LAST (runs go from the last one backwards), so the kernel's
-                                 // ragged end is half a short run instead of half a long one
+    int ntiles, nruns;           // dim tiles, runs
+    const int *run_start;        // [nruns + 1] first interval of every run, relative to n_begin.
+                                 // Runs are taken from the LAST one backwards, and the schedule
+                                 // (mfvgp_create) makes them shorter towards the START of the time
+                                 // axis -- long runs first for few prologues, short runs at the
+                                 // end of the kernel for a small ragged end
     int with_e0;
 };
 
@@ -270,9 +272,9 @@ esde_l96_walk_kernel(const WalkArgs a) {
     __syncthreads();
     const int lid = (int)sm.cta_id;
     const int tile = lid % a.ntiles, run = a.nruns - 1 - lid / a.ntiles;
-    const int n0 = a.n_begin + (run < a.nshort ? run * a.TNs
-                                               : a.nshort * a.TNs + (run - a.nshort) * a.TN);
-    const int tnv = run < a.nshort ? a.TNs : min(a.TN, a.n_end - n0);   // intervals in this run
+    const int rs0 = a.run_start[run];
+    const int n0 = a.n_begin + rs0;
+    const int tnv = a.run_start[run + 1] - rs0;                         // intervals in this run
     const int d0 = tile * TD, D = a.D;
     int j = (d0 - 3 + e) % D;
     if (j < 0) j += D;

@@ -63,7 +63,7 @@ struct mfvgp_handle {
     // walk kernel (l96_walk.cuh; fused = 2): dim tile fte, ftn consecutive intervals per run,
     // grid = fntn runs x fntiles tiles.  fused = 0: split / coop kernels with a workspace
     int fte = 64, ftn = 1, fntiles = 1, fntn = 1, fused = 0;
-    int fnshort = 0, ftns = 1;   // walk kernel: short runs at the start of the time axis (taken last)
+    int *run_start = nullptr;    // walk kernel: [fntn + 1] first interval of every run (device)
     double *fedge_m = nullptr, *fedge_s = nullptr, *fapart = nullptr;
     bool have_sde = false, have_prior = false, have_obs = false;
     double eobs_const = 0.0;
@@ -274,26 +274,54 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         h->fntiles = (D + h->fte - 7) / (h->fte - 6);
         h->fntn = (nl + h->ftn - 1) / h->ftn;
         if (h->fused == 2) {
-            // Runs are taken from the last one backwards by CTAs in the order they start, so the
-            // runs at the START of the time axis are processed last.  Making those short (about
-            // two waves of CTAs in runs of TN/4) shrinks the ragged end of the kernel from half a
-            // long run to half a short one.  Measured at D=8192: 463.0 -> 460.2 us (L=512),
-            // 3383.6 -> 3361.5 us (L=4096), i.e. 0.6 %: what separates 0.91 us per interval at
-            // L=32 from 0.81 at L=4096 is the per-run prologue, not this end.
-            // MFVGP_WALK_SHORT=0 switches it off, "S,TNs" sets it.
+            // Run schedule.  Runs are taken from the last one backwards by CTAs in the order they
+            // start, so the runs at the END of the time axis are processed first and those at its
+            // START last.  Every run pays a prologue of ~0.65 interval (un-prefetched loads, three
+            // exp, mailbox hand-over), which asks for few long runs; the kernel ends when the last
+            // run does, which asks for short runs at the end.  Guided schedule: with c = resident
+            // CTAs / dim tiles runs in flight, each run takes 1 / (f c) of the intervals still to
+            // be handed out (f = 1.5), between tmin and tmax.  "MFVGP_WALK_SCHED=uniform" keeps
+            // round 1's schedule (TN = sqrt(0.8 nl nt / R) everywhere, ~2 waves of TN/4 at the
+            // start of the axis); "f,tmin,tmax" sets the guided one.
             const int resident = 148 * (512 / h->fte);
-            int tns = h->ftn / 4 < 2 ? 2 : h->ftn / 4;
-            int ns = (2 * resident + h->fntiles - 1) / h->fntiles;
-            if (const char *e = getenv("MFVGP_WALK_SHORT")) {
-                int a = 0, b = 0;
-                if (sscanf(e, "%d,%d", &a, &b) == 2) { ns = a; tns = b; }
-                else if (e[0] == '0') ns = 0;
+            std::vector<int> lens;                       // from the END of the time axis
+            const char *se = getenv("MFVGP_WALK_SCHED");
+            if (se && se[0] == 'u') {
+                int tns = h->ftn / 4 < 2 ? 2 : h->ftn / 4;
+                int ns = (2 * resident + h->fntiles - 1) / h->fntiles;
+                if (tns >= h->ftn || tns < 1) ns = 0;
+                while (ns > 0 && (int64_t)ns * tns > nl / 2) ns /= 2;
+                int rest = nl - ns * tns;
+                while (rest > 0) { const int t = rest < h->ftn ? rest : h->ftn; lens.push_back(t); rest -= t; }
+                // the partial run of the uniform part sits next to the short ones
+                if (!lens.empty() && lens.size() > 1) std::swap(lens.front(), lens.back());
+                for (int i = 0; i < ns; ++i) lens.push_back(tns);
+            } else {
+                // measured at D=8192 (tools/sched_sweep.py): L=512 463 us (uniform) -> 443; L=4096
+                // 3 358 -> 3 314; f = 1.25 is 0.3 % better still but f = 1 falls off a cliff
+                // (first runs longer than the first wave can balance: 494 us at L=512)
+                double f = 1.5;
+                int tmin = 2, tmax = 64;
+                if (se) sscanf(se, "%lf,%d,%d", &f, &tmin, &tmax);
+                if (tmax > kWalkMaxTN) tmax = kWalkMaxTN;
+                if (tmin < 1) tmin = 1;
+                const double c = (double)resident / h->fntiles > 1.0 ? (double)resident / h->fntiles : 1.0;
+                int rem = nl;
+                while (rem > 0) {
+                    int t = (int)lround(rem / (f * c));
+                    t = t < tmin ? tmin : (t > tmax ? tmax : t);
+                    if (t > rem) t = rem;
+                    lens.push_back(t);
+                    rem -= t;
+                }
             }
-            if (tns >= h->ftn || tns < 1) ns = 0;
-            while (ns > 0 && (int64_t)ns * tns > nl / 2) ns /= 2;      // at most half of the intervals
-            h->fnshort = ns; h->ftns = tns;
-            const int rest = nl - ns * tns;
-            h->fntn = ns + (rest + h->ftn - 1) / h->ftn;
+            h->fntn = (int)lens.size();
+            std::vector<int> start(lens.size() + 1, 0);
+            for (size_t r = 0; r < lens.size(); ++r)          // run 0 = START of the axis = last of lens
+                start[r + 1] = start[r] + lens[lens.size() - 1 - r];
+            h->ftn = lens.front();
+            CK(cudaMalloc((void **)&h->run_start, start.size() * sizeof(int)));
+            CK(cudaMemcpy(h->run_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
     }
     double tab[kNodes * kTabStride];
@@ -414,7 +442,8 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
                     h->gather, h->xchg_send, h->xchg_gather, h->rec_ws, h->fedge_m, h->fedge_s, h->fapart, h->tickets,
                     h->y_dense, h->rinv_row, h->head_flag, h->refine_gpart,
                     h->refine_gbar, h->b_dm, h->b_ds, h->b_part, h->b_apart, h->b_esde_n,
-                    h->b_flags, h->b_rstat, h->b_ticket, h->eparam_ws, h->tail_part, h->tail_late};
+                    h->b_flags, h->b_rstat, h->b_ticket, h->eparam_ws, h->tail_part, h->tail_late,
+                    h->run_start};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int r = 0; r < h->world && r < kPeerMaxWorld; ++r)
@@ -681,8 +710,7 @@ static int launch_walk(mfvgp_handle *h, const double *x, double *grad, cudaStrea
     w.part = h->part; w.apart = h->fapart;
     w.D = h->D; w.M = h->M; w.d = h->d; w.Nm = h->Nm; w.Ns = h->Ns; w.L = h->L;
     w.n_begin = h->n_begin; w.n_end = h->n_end;
-    w.ntiles = h->fntiles; w.nruns = h->fntn; w.TN = h->ftn;
-    w.nshort = h->fnshort; w.TNs = h->ftns;
+    w.ntiles = h->fntiles; w.nruns = h->fntn; w.run_start = h->run_start;
     w.with_e0 = h->n_begin == 0;
     int rc;
     if (h->fte == 32) rc = launch_walk_kernel<32>(w, grid, st);
