@@ -207,7 +207,7 @@ struct WalkArgs {
     int32_t *status;             // OR-ed MFVGP_ST_SYNC_TIMEOUT if a mailbox wait gives up
     int epoch;                   // launch counter of this handle
     double *part;                // [(n_end-n_begin)*ntiles][kPartStride] guard partials
-    double *apart;               // [gridDim.x][4]: sum log(tau0/s0), kl0 quad, obs, -
+    double *apart;               // [gridDim.x][4] by ticket: sum log(tau0/s0), kl0 quad, obs, -
     double theta;                // L96 forcing (lorenz_96.py:70)
     int D, M, d, Nm, Ns, L;
     int n_begin, n_end;          // intervals of this shard
@@ -575,7 +575,10 @@ esde_l96_walk_kernel(const WalkArgs a) {
 #pragma unroll
                 for (int w2 = 1; w2 < NW; ++w2) v += sm.red[e][w2];
             }
-            a.apart[(int64_t)blockIdx.x * 4 + e] = v;
+            // row = the ticket, i.e. the (run, tile) this CTA worked on -- not blockIdx.x, whose
+            // pairing with (run, tile) depends on the order the CTAs happened to start in: the
+            // fold that follows must add the same partials in the same order every time
+            a.apart[(int64_t)lid * 4 + e] = v;
         }
     }
 }

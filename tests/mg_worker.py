@@ -104,6 +104,33 @@ def main():
         e2 = rel_err(xs.cpu().numpy()[idx], x1.cpu().numpy()[idx])
         assert e2 <= 1e-8, e2
         dist.barrier()
+    # soak: the peer-memory exchange (csrc/peer.cuh, walk_tail.cuh) 150 times over -- the same bits
+    # every time on every rank, and identical bits on both owners of a shared column
+    g = synthetic_l96(130, 41, seed=9)
+    os.environ["MFVGP_PATH"] = "walk"
+    sh = ShardedFreeEnergy(g, rank, world, device=local)
+    os.environ.pop("MFVGP_PATH", None)
+    assert sh.local.describe()["xchg"] in ("peer", "nccl")
+    x = torch.tensor(g["x0"], dtype=torch.float64, device="cuda")
+    F0, g0 = sh.E_cost(x)
+    F0, g0 = F0.clone(), g0.clone()
+    for k in range(150):
+        F, gk = sh.E_cost(x)
+        if k % 3 == 0:
+            sh.E_cost(x, output_gradients=False)          # records-only exchanges in between
+    idx = active_columns(sh.local, 130, 41)
+    assert torch.equal(gk[idx].view(torch.int64), g0[idx].view(torch.int64)) and F.item() == F0.item()
+    n0, n1 = sh.local.intervals
+    edge = torch.stack((gk[:130 * 127].view(130, 127)[:, 3 * n0], gk[:130 * 127].view(130, 127)[:, min(3 * n1, 126)]))
+    got = [torch.empty_like(edge) for _ in range(world)]
+    dist.all_gather(got, edge)
+    for r in range(world - 1):                            # right edge of r == left edge of r + 1
+        assert torch.equal(got[r][1].view(torch.int64), got[r + 1][0].view(torch.int64)), r
+    Fs = [torch.empty_like(F.reshape(1)) for _ in range(world)]
+    dist.all_gather(Fs, F.reshape(1))
+    assert all(f.item() == F.item() for f in Fs)
+    assert sh.local.check_last() == 0
+    dist.barrier()
     # the other systems shard the same way (one CTA per interval kernels + assemble + exchange)
     from helpers import load_golden
     for name in ("DW", "L63_T5"):
