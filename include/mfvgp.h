@@ -227,6 +227,17 @@ int mfvgp_reconstruct_host(int device, int D, int M, int num, const double *Tx_h
                            double *tt_h, double *mt_h, double *st_h);
 
 /*
+ * Initial state for find_minimum from an initial sample path that already lives on the device
+ * (examples/example_500D.ipynb cells 17 and 19, :402-428): means = the
+ * path at the mean support indices mp_idk [3M+4] (cell 17), variances = var_base + var_spread *
+ * u [D][2M+3] (the notebook: 4 + 2 * np.random.rand), stored as logs.  path_d [D][T]; x_d is the
+ * wire format of mfvgp_ecost (free_energy.py:678-684).
+ */
+int mfvgp_initial_state(int D, int M, int64_t T, const double *path_d, const int64_t *mp_idk_d,
+                        const double *u_d, double var_base, double var_spread, double *x_d,
+                        void *cuda_stream);
+
+/*
  * Batched evaluation: B independent states x_d [B][n] of the SAME problem in two launches
  * (out_d [B][8]: F, E0, Esde, Eobs; grad_d [B][n]; status_d [B]).  Serves the n + 1 evaluations
  * scipy.optimize.check_grad makes behind find_minimum(check_gradients=True)

@@ -50,6 +50,8 @@ SIGNATURES = {
     "mfvgp_reconstruct": (c_int, [c_int, c_int, c_int, _P, _P, c_int64, _P, c_int64, c_int, _P, _P, _P,
                                   c_void_p]),
     "mfvgp_reconstruct_host": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P]),
+    "mfvgp_initial_state": (c_int, [c_int, c_int, c_int64, _P, _P, _P, c_double, c_double, _P,
+                                    c_void_p]),
     "mfvgp_l96_trajectory": (c_int, [c_int, c_double, c_double, c_int, c_int, c_double, _P, _P,
                                      POINTER(c_int32), c_void_p]),
     "mfvgp_small_trajectory": (c_int, [c_int, _P, c_int, c_double, c_int, c_int, c_double, c_int,

@@ -2367,6 +2367,23 @@ extern "C" int mfvgp_reconstruct_host(int device, int D, int M, int num, const d
     return rc;
 }
 
+// ---- initial state from a device-resident initial path -----------------
+extern "C" int mfvgp_initial_state(int D, int M, int64_t T, const double *path_d,
+                                   const int64_t *mp_idk_d, const double *u_d, double var_base,
+                                   double var_spread, double *x_d, void *cuda_stream) {
+    ARG(path_d && mp_idk_d && u_d && x_d, "mfvgp_initial_state: NULL argument");
+    ARG(D >= 1 && M >= 1 && T >= 1, "mfvgp_initial_state: bad size");
+    InitStateArgs a;
+    a.path = path_d; a.mp_idk = mp_idk_d; a.u = u_d; a.x = x_d;
+    a.var_base = var_base; a.var_spread = var_spread; a.T = T;
+    a.D = D; a.Nm = 3 * M + 4; a.Ns = 2 * M + 3;
+    const int64_t n = (int64_t)D * (a.Nm + a.Ns);
+    const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    initial_state_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(a);
+    CK(cudaGetLastError());
+    return MFVGP_OK;
+}
+
 // ---- Lorenz 96 sample path ------------------------------------------
 extern "C" int mfvgp_l96_trajectory(int D, double theta, double dt, int dim_t, int nburn,
                                     double delta_t, const double *ek_td_d, double *x_out_d,

@@ -131,4 +131,32 @@ reconstruct_kernel(const ReconArgs a, int groups /* <= kReconGroups: row groups 
     }
 }
 
+// Initial state x0 for find_minimum from an initial sample path on the device (SURVEY.md 8(f)
+// rank 2; examples/example_500D.ipynb cells 17 and 19, :402-428): the means are the path at the
+// mean support indices, the variances var_base + var_spread * u at the variance support
+// indices, stored as logs; x = [means [D][Nm] | log-variances [D][Ns]] (free_energy.py:678-684).
+struct InitStateArgs {
+    const double *path;       // [D][T] initial path x0(t), row = state dimension
+    const int64_t *mp_idk;    // [Nm] time indices of the mean support points
+    const double *u;          // [D][Ns] uniform draws in [0, 1)
+    double *x;                // [D*Nm + D*Ns]
+    double var_base, var_spread;
+    int64_t T;
+    int D, Nm, Ns;
+};
+
+__global__ void __launch_bounds__(256)
+initial_state_kernel(const InitStateArgs a) {
+    const int64_t nm = (int64_t)a.D * a.Nm, n = nm + (int64_t)a.D * a.Ns;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < nm) {
+            const int64_t j = i / a.Nm, c = i - j * a.Nm;
+            a.x[i] = a.path[j * a.T + a.mp_idk[c]];
+        } else {
+            a.x[i] = log(fma(a.var_spread, a.u[i - nm], a.var_base));
+        }
+    }
+}
+
 }  // namespace mfvgp

@@ -88,6 +88,38 @@ struct VecMap {
     }
 };
 
+// Visits every local entry of the rank's part of x: f(index into x, owned).  Single GPU: a
+// grid-stride loop over the contiguous vector.  Sharded: the rank's columns are one contiguous
+// segment per row of the mean block and one per row of the log-variance block; a WARP takes
+// chunks of kVmChunk consecutive columns of one row (coalesced, and no 64-bit division per
+// element as an index -> (row, column) map would need; the per-chunk division is amortised
+// over 256 elements).  The assignment of elements to threads is fixed, so the reductions
+// built on it stay reproducible.
+constexpr int kVmChunk = 256;
+template <class F>
+__device__ __forceinline__ void vm_for_each(const VecMap &vm, F f) {
+    if (vm.full) {
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
+             t += (int64_t)gridDim.x * blockDim.x)
+            f(t, true);
+        return;
+    }
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int cm = (vm.wm + kVmChunk - 1) / kVmChunk, cs = (vm.ws + kVmChunk - 1) / kVmChunk;
+    const int64_t tasks_m = (int64_t)vm.D * cm, tasks = tasks_m + (int64_t)vm.D * cs;
+    for (int64_t task = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); task < tasks;
+         task += (int64_t)gridDim.x * wpb) {
+        const bool mean = task < tasks_m;
+        const int64_t r = mean ? task : task - tasks_m;
+        const int per = mean ? cm : cs;
+        const int j = (int)(r / per), c0 = (int)(r - (int64_t)j * per) * kVmChunk;
+        const int w = mean ? vm.wm : vm.ws, own_w = mean ? vm.own_wm : vm.own_ws;
+        const int64_t base = mean ? (int64_t)j * vm.Nm + vm.cm0 : vm.num_mp + (int64_t)j * vm.Ns + vm.cs0;
+        const int c1 = min(c0 + kVmChunk, w);
+        for (int c = c0 + lane; c < c1; c += 32) f(base + c, c < own_w);
+    }
+}
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -313,10 +345,7 @@ scg_direction_kernel(double *d, const double *g, double gamma, int restart, cons
         if (chain_is_void(fa)) return;
         gamma = __ldcg(fa.ctrl + 11);
     }
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        bool own;
-        const int64_t i = vm.at(t, own);
+    vm_for_each(vm, [&](int64_t i, bool own) {
         const double gi = g[i];
         const double di = restart ? -gi : gamma * d[i] - gi;
         d[i] = di;
@@ -324,7 +353,7 @@ scg_direction_kernel(double *d, const double *g, double gamma, int restart, cons
             v[0] = fma(di, gi, v[0]);
             v[1] = fma(di, di, v[1]);
         }
-    }
+    });
     red_store(v, part, fa);
 }
 
@@ -335,12 +364,7 @@ scg_axpy_kernel(double *y, const double *x, const double *d, double a, const dou
     scg_pdl_enter();
     if (void_flag != nullptr && __ldcg(void_flag) != 0.0) return;    // void chain: y untouched
     if (a_dev != nullptr) a = __ldcg(a_dev);      // step length computed on the device
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        bool own;
-        const int64_t i = vm.at(t, own);
-        y[i] = x[i] + a * d[i];
-    }
+    vm_for_each(vm, [&](int64_t i, bool) { y[i] = x[i] + a * d[i]; });
 }
 
 // partial [0] = d.(gp - g)                      (scaled_cg.py:228)
@@ -350,12 +374,9 @@ scg_theta_kernel(const double *d, const double *gp, const double *g, const VecMa
     double v[kRedSlots] = {0.0, 0.0, 0.0, 0.0};
     scg_pdl_enter();
     if (chain_is_void(fa)) return;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        bool own;
-        const int64_t i = vm.at(t, own);
+    vm_for_each(vm, [&](int64_t i, bool own) {
         if (own) v[0] = fma(d[i], gp[i] - g[i], v[0]);
-    }
+    });
     red_store(v, part, fa);
 }
 
@@ -377,17 +398,14 @@ scg_stats_kernel(const double *g_now, const double *g_new, const double *d, cons
         }
         return;
     }
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vm.n;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        bool own;
-        const int64_t i = vm.at(t, own);
-        if (!own) continue;
+    vm_for_each(vm, [&](int64_t i, bool own) {
+        if (!own) return;
         const double a = g_now[i];
         v[0] += fabs(a);
         v[1] = fma(a, a, v[1]);
         v[2] = fma(a, g_new[i] - a, v[2]);
         v[3] = fmax(v[3], fabs(d[i]));
-    }
+    });
     red_store(v, part, fa);
 }
 

@@ -157,7 +157,29 @@ def initial_state(x0_path, obs_idk, rng=None, var_base=4.0, var_spread=2.0):
     :param rng: ``numpy.random.Generator`` (the notebook draws from the unseeded global
                 ``np.random.rand``; pass a generator for a reproducible start)
     :return: ``(x, mp_idk, sp_idk)``
+
+    A CUDA ``torch.float64`` path [D, T] stays on the device: the gather and the logs run in
+    ``initial_state_kernel`` (mfvgp_initial_state) and ``x`` comes back as a CUDA tensor, ready
+    for ``find_minimum``.
     """
+    if _is_tensor(x0_path):
+        import ctypes
+        import torch
+        from . import _lib
+        lib = _lib.require_device()
+        path = x0_path.contiguous()
+        D, T = path.shape
+        mp_idk, sp_idk = support_indices(obs_idk, T)
+        M = len(obs_idk)
+        rng = np.random.default_rng() if rng is None else rng
+        u = torch.as_tensor(np.ascontiguousarray(rng.random((D, len(sp_idk)))), device=path.device)
+        idk = torch.as_tensor(np.asarray(mp_idk, dtype=np.int64), device=path.device)
+        x = torch.empty(D * (len(mp_idk) + len(sp_idk)), dtype=torch.float64, device=path.device)
+        stream = torch.cuda.current_stream(path.device).cuda_stream
+        _lib.check(lib.mfvgp_initial_state(D, M, T, path.data_ptr(), idk.data_ptr(), u.data_ptr(),
+                                           float(var_base), float(var_spread), x.data_ptr(),
+                                           ctypes.c_void_p(stream)), "mfvgp_initial_state")
+        return x, mp_idk, sp_idk
     x0_path = np.atleast_2d(np.asarray(x0_path, dtype=float))
     mp_idk, sp_idk = support_indices(obs_idk, x0_path.shape[1])
     rng = np.random.default_rng() if rng is None else rng

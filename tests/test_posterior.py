@@ -206,6 +206,22 @@ def test_initial_state_from_the_device_sample_path():
     _check_initial_state(g, x.cpu().numpy(), tk.cpu().numpy())
 
 
+@pytest.mark.gpu
+def test_initial_state_device_path_equals_host_path():
+    """mfvgp_initial_state (gather + logs on the device) against the numpy helper, same draws"""
+    import torch
+    import meanfieldvargp_b200 as mf
+    g = _load_any("initial_L96_24p")
+    rng = np.random.default_rng(3)
+    path = rng.normal(size=(int(g["D"]), 4002))
+    xh, mi, si = mf.initial_state(path, g["obs_idk"], rng=_LegacyRand(5))
+    xd, mi2, si2 = mf.initial_state(torch.tensor(path, device="cuda"), g["obs_idk"], rng=_LegacyRand(5))
+    assert xd.is_cuda and np.array_equal(mi, mi2) and np.array_equal(si, si2)
+    nm = path.shape[0] * len(mi)
+    assert np.array_equal(xd.cpu().numpy()[:nm], xh[:nm])
+    assert rel_err(xd.cpu().numpy()[nm:], xh[nm:]) <= 1e-15
+
+
 def _load_any(name):
     z = np.load(GOLDEN / f"{name}.npz")
     return {k: z[k] for k in z.files}
