@@ -1996,6 +1996,21 @@ struct ScgRun {
     }
 };
 
+// copies the entries of a vector in the layout of x that this rank works on: the whole vector
+// on one GPU, the rank's column blocks (one strided block each of the mean and the log-variance
+// part) on a sharded handle -- the copies then shrink with the shard like everything else
+static cudaError_t copy_active(double *dst, const double *src, const VecMap &vm, int64_t n,
+                               cudaStream_t st) {
+    if (vm.full) return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    cudaError_t e = cudaMemcpy2DAsync(dst + vm.cm0, (size_t)vm.Nm * sizeof(double), src + vm.cm0,
+                                      (size_t)vm.Nm * sizeof(double), (size_t)vm.wm * sizeof(double),
+                                      (size_t)vm.D, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy2DAsync(dst + vm.num_mp + vm.cs0, (size_t)vm.Ns * sizeof(double),
+                             src + vm.num_mp + vm.cs0, (size_t)vm.Ns * sizeof(double),
+                             (size_t)vm.ws * sizeof(double), (size_t)vm.D, cudaMemcpyDeviceToDevice, st);
+}
+
 #define RC(call)                \
     do {                        \
         int rc_ = (call);       \
@@ -2059,9 +2074,9 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     double *gp = h->scg_vec[6];
     double s8[8];
     for (int i = 0; i < max_it; ++i) fx_hist_h[i] = dfx_hist_h[i] = 0.0;   // :123-124
-    CK(cudaMemcpyAsync(x, x_d, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    if (!vm.full)   // columns of other ranks are never written: keep them defined in both iterates
-        CK(cudaMemcpyAsync(xt, x_d, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(copy_active(x, x_d, vm, n, st));
+    if (!vm.full)   // the two iterates swap roles: both start from the caller's columns
+        CK(copy_active(xt, x_d, vm, n, st));
 
     int nit = max_it, func_eval = 0;
     double fx = 0.0;
@@ -2072,7 +2087,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     double f_now = s8[4], sa_new = s8[0];
     func_eval++;
     bool failed = (R.status_or & 7) != 0;
-    CK(cudaMemcpyAsync(gold, gnew, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(copy_active(gold, gnew, vm, n, st));
     double sa_old = sa_new, f_old = f_now;
     RC(R.direction(d, gnew, 0.0, 1));                            // d = -grad_new
     RC(R.read(s8));
@@ -2259,7 +2274,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         fprintf(stderr, "mfvgp_scg: nit=%d chains=%ld (%.1f us host enqueue each), record waits "
                         "%.1f us per iteration\n", nit, R.n_chain,
                 R.n_chain ? 1e6 * R.t_chain / R.n_chain : 0.0, nit ? 1e6 * R.t_wait / nit : 0.0);
-    CK(cudaMemcpyAsync(x_d, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(copy_active(x_d, x, vm, n, st));      // sharded: the rank's columns of the caller's x
     CK(cudaStreamSynchronize(st));
     result_h[0] = fx;
     result_h[1] = nit;
