@@ -233,6 +233,10 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -248,11 +252,22 @@ struct WalkSmem {
     double e0[2][TE];             // E_kl0 energy terms of the rows (run 0 only)
     double red[9][TE / 32];
     double dt[kWalkMaxTN], idt[kWalkMaxTN];
-    unsigned cta_id;
+    // persistent CTAs: the next run's first interval, fetched during the last interval of the
+    // current one (P0..P3, log S0..S2, Sigma of the row; observation index; interval times)
+    double nx[8][TE];
+    int nx_jo[TE];
+    double nx_t[kWalkMaxTN + 1];
+    unsigned cta_id, next_id;
     int wait_ok;
 };
 
-template <int TE, int GB>
+// PERSIST: the grid is one CTA per resident slot and a CTA keeps drawing runs until none is left.
+// During the last interval of a run it draws its next ticket and fetches that run's first
+// support points (cp.async into WalkSmem::nx), so the run-to-run hand-over -- CTA exit and
+// launch, the ticket's round trip, un-prefetched loads: ~4.4 us of an SM slot per run, measured
+// as 0.51 us of kernel time per run at D=8192 (tools/sched_sweep.py) -- shrinks to the part
+// that cannot be hidden (three exp, the mailbox, the column stores).
+template <int TE, int GB, bool PERSIST>
 __global__ void __launch_bounds__(TE, MFVGP_WALK_THREADS_PER_SM / TE)
 esde_l96_walk_kernel(const WalkArgs a) {
     constexpr int TD = TE - 6, NW = TE / 32;
@@ -260,17 +275,24 @@ esde_l96_walk_kernel(const WalkArgs a) {
     WalkSmem<TE, GB> &sm = *reinterpret_cast<WalkSmem<TE, GB> *>(walk_smem_raw);
 
     const int e = threadIdx.x;
+    const unsigned total = (unsigned)a.nruns * (unsigned)a.ntiles;
     // CTAs number themselves in the order they start (atomic ticket) and take the runs from the
     // LAST one backwards: a run hands the k=0 part of its first column to the run before it
-    // (mailbox below), so a CTA only ever waits for CTAs that started earlier -- no deadlock,
-    // whatever order the hardware dispatches blocks in.
+    // (mailbox below), so a CTA only ever waits for a run with a smaller ticket, i.e. one that a
+    // CTA holds or has finished -- no deadlock, whatever order the hardware dispatches blocks in.
+    // Reset of the ticket for the next launch: by whoever makes the last draw of this one
+    // (PERSIST: every CTA makes exactly one draw that fails, so total + gridDim.x draws in all).
     if (e == 0) {
         const unsigned id = atomicAdd(a.run_ticket, 1u);
-        if (id == gridDim.x - 1u) *a.run_ticket = 0u;    // everybody has drawn: reset for the next launch
+        if (id == (PERSIST ? total : 0u) + gridDim.x - 1u) *a.run_ticket = 0u;
         sm.cta_id = id;
     }
     __syncthreads();
-    const int lid = (int)sm.cta_id;
+    unsigned cur_id = sm.cta_id;
+    bool have_nx = false;                 // this run's first interval was prefetched
+  for (;;) {
+    if (PERSIST && cur_id >= total) break;
+    const int lid = (int)cur_id;
     const int tile = lid % a.ntiles, run = a.nruns - 1 - lid / a.ntiles;
     const int rs0 = a.run_start[run];
     const int n0 = a.n_begin + rs0;
@@ -283,7 +305,8 @@ esde_l96_walk_kernel(const WalkArgs a) {
     const bool want_grad = a.gm != nullptr;
 
     for (int i = e; i < tnv; i += TE) {
-        const double dt = fabs(a.obs_times[n0 + i + 1] - a.obs_times[n0 + i]);
+        const double dt = have_nx ? fabs(sm.nx_t[i + 1] - sm.nx_t[i])
+                                  : fabs(a.obs_times[n0 + i + 1] - a.obs_times[n0 + i]);
         sm.dt[i] = dt;
         sm.idt[i] = 1.0 / dt;
     }
@@ -292,10 +315,21 @@ esde_l96_walk_kernel(const WalkArgs a) {
     const double *mp = a.x + (int64_t)j * a.Nm + 3 * (int64_t)n0;
     const double *sp = a.x + (int64_t)D * a.Nm + (int64_t)j * a.Ns + 2 * (int64_t)n0;
     const int64_t g_off_m = a.gm - a.x, g_off_s = a.gs - (a.x + (int64_t)D * a.Nm);
-    double P0 = mp[0], P1 = mp[1], P2 = mp[2], P3 = mp[3];
-    double S0 = sp[0], S1 = sp[1], S2 = sp[2];
-    const double Sig = a.sigma[j];
-    const int jo = is_out ? a.obs_idx[j] : -1;
+    double P0, P1, P2, P3, S0, S1, S2, Sig_;
+    int jo_;
+    if (have_nx) {
+        P0 = sm.nx[0][e]; P1 = sm.nx[1][e]; P2 = sm.nx[2][e]; P3 = sm.nx[3][e];
+        S0 = sm.nx[4][e]; S1 = sm.nx[5][e]; S2 = sm.nx[6][e];
+        Sig_ = sm.nx[7][e];
+        jo_ = sm.nx_jo[e];
+    } else {
+        P0 = mp[0]; P1 = mp[1]; P2 = mp[2]; P3 = mp[3];
+        S0 = sp[0]; S1 = sp[1]; S2 = sp[2];
+        Sig_ = a.sigma[j];
+        jo_ = a.obs_idx[j];
+    }
+    const double Sig = Sig_;
+    const int jo = is_out ? jo_ : -1;
     double Ri = 0.0, y0 = 0.0;
     if (jo >= 0) {
         Ri = a.obs_noise[jo];
@@ -322,6 +356,11 @@ esde_l96_walk_kernel(const WalkArgs a) {
             cp_async8(&sm.pf[3][e], sp + 2 * nl + 3);
             cp_async8(&sm.pf[4][e], sp + 2 * nl + 4);
             if (jo >= 0) cp_async8(&sm.pf[5][e], a.obs_values + (int64_t)n * a.d + jo);
+        }
+        if (PERSIST && !more && e == 0) {                // last interval of the run: the next ticket
+            const unsigned nid = atomicAdd(a.run_ticket, 1u);
+            if (nid == total + gridDim.x - 1u) *a.run_ticket = 0u;
+            sm.next_id = nid;
         }
         const double dt = sm.dt[nl], inv_dt = sm.idt[nl];
 
@@ -350,6 +389,32 @@ esde_l96_walk_kernel(const WalkArgs a) {
                 own[gg] = (a.theta - m) - dm;
             }
             __syncthreads();
+            if (PERSIST && g0 == 0 && !more) {
+                // the ticket drawn above is visible now: fetch the next run's first interval
+                // (this row's support points, Sigma, observation index; the interval times)
+                const unsigned nid = sm.next_id;
+                if (nid < total) {
+                    const int tile2 = (int)(nid % (unsigned)a.ntiles);
+                    const int run2 = a.nruns - 1 - (int)(nid / (unsigned)a.ntiles);
+                    const int r20 = a.run_start[run2], tn2 = a.run_start[run2 + 1] - r20;
+                    int j2 = (tile2 * TD - 3 + e) % D;
+                    if (j2 < 0) j2 += D;
+                    const double *mp2 = a.x + (int64_t)j2 * a.Nm + 3 * (int64_t)(a.n_begin + r20);
+                    const double *sp2 = a.x + (int64_t)D * a.Nm + (int64_t)j2 * a.Ns
+                                        + 2 * (int64_t)(a.n_begin + r20);
+                    cp_async8(&sm.nx[0][e], mp2);
+                    cp_async8(&sm.nx[1][e], mp2 + 1);
+                    cp_async8(&sm.nx[2][e], mp2 + 2);
+                    cp_async8(&sm.nx[3][e], mp2 + 3);
+                    cp_async8(&sm.nx[4][e], sp2);
+                    cp_async8(&sm.nx[5][e], sp2 + 1);
+                    cp_async8(&sm.nx[6][e], sp2 + 2);
+                    cp_async8(&sm.nx[7][e], a.sigma + j2);
+                    cp_async4(&sm.nx_jo[e], a.obs_idx + j2);
+                    for (int i = e; i <= tn2; i += TE)
+                        cp_async8(&sm.nx_t[i], a.obs_times + a.n_begin + r20 + i);
+                }
+            }
 #pragma unroll
             for (int gg = 0; gg < GB; ++gg) {
                 if (g0 + gg >= kGL) break;
@@ -478,7 +543,9 @@ esde_l96_walk_kernel(const WalkArgs a) {
             sm.carry[1][e] = dsv[2];
         }
         if (nl == 0 && run > 0 && want_grad) {               // publish the heads of this run
-            __threadfence();
+            // the barrier orders every thread's head stores before thread 0's release store,
+            // and a release is cumulative over that order (PTX memory model): no fence per
+            // thread (it cost 0.1 us of kernel time per run: 462 -> 452 us at L=512, 86 runs)
             __syncthreads();
             if (e == 0) st_release_gpu(a.head_flag + run * a.ntiles + tile, a.epoch);
         }
@@ -581,6 +648,12 @@ esde_l96_walk_kernel(const WalkArgs a) {
             a.apart[(int64_t)lid * 4 + e] = v;
         }
     }
+    if (!PERSIST) break;
+    cur_id = sm.next_id;                  // drawn during the last interval (visible: barriers since)
+    have_nx = cur_id < total;
+    cp_async_wait_all();                  // the prefetched first interval of the next run
+    __syncthreads();
+  }
 }
 
 }  // namespace mfvgp
