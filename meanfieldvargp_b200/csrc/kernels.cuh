@@ -595,6 +595,7 @@ struct GuardArgs {
 __device__ __forceinline__ void guard_interval(const GuardArgs &a, int n, int lane) {
     const int warp = n - a.n_begin;
     double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 3                     // all the loads of up to 96 tiles in flight at once
     for (int t = lane; t < a.ntiles; t += 32) {
         const double *src = a.part + ((int64_t)warp * a.ntiles + t) * kPartStride;
 #pragma unroll

@@ -757,7 +757,7 @@ scg_peer_fold_publish_kernel(const PeerArgs a) {
 #pragma unroll
             for (int i = 0; i < kRedSlots; ++i) dst[i] = r[i];
         }
-        __threadfence_system();
+        // same thread: each release store orders the record stores before it
         for (int p = 0; p < a.world; ++p) st_release_sys(peer_flag(a.box[p], a, a.rank), a.epoch);
     }
 }

@@ -57,7 +57,7 @@ __device__ __forceinline__ long long *tail_chunk_flag(double *box, const PeerArg
 // scalars of the evaluation from the four sums; record / output / status; clean-up for the
 // next evaluation.  One thread.
 __device__ __forceinline__ void tail_finish(const WalkTailArgs &a, const double *acc, int anyflag,
-                                            int late) {
+                                            int late, int32_t refine_status) {
     const double Esde = acc[0];
     double E0 = 0.0;
     if (a.with_e0) {
@@ -66,7 +66,7 @@ __device__ __forceinline__ void tail_finish(const WalkTailArgs &a, const double 
         E0 = 0.5 * (lg + acc[2]);
     }
     const double Eobs = 0.5 * (acc[3] + a.eobs_const);
-    int32_t st = __ldcg(a.refine_status);
+    int32_t st = refine_status;
     if (!isfinite(Esde)) st |= 1;
     if (!isfinite(E0)) st |= 2;
     if (!isfinite(Eobs)) st |= 4;
@@ -90,7 +90,8 @@ __device__ __forceinline__ void tail_publish_record(const PeerArgs &p, const dou
         const double v = rec[lane];
         for (int r = 0; r < p.world; ++r) peer_rec(p.box[r], p, p.rank)[lane] = v;
     }
-    __threadfence_system();
+    // __syncwarp orders the lanes' record stores before each lane's release store, and a
+    // release is cumulative over that order: no separate system-scope fence per lane
     __syncwarp();
     if (lane < p.world) st_release_sys(peer_flag(p.box[lane], p, p.rank), p.epoch);
 }
@@ -113,7 +114,8 @@ __device__ __forceinline__ void tail_publish_edges(const PeerArgs &p, int chunk,
             e[p.D + j] = __ldcg(gs + 2 * p.n_end);
         }
     }
-    __threadfence_system();
+    // the barrier orders all 256 threads' stores before the two release stores below
+    // (cumulative): one system-scope release per neighbour instead of a fence per thread
     __syncthreads();
     if (threadIdx.x == 0 && p.rank > 0)
         st_release_sys(tail_chunk_flag(p.box[p.rank - 1], p, 1, chunk, nchunk), flag_value);
@@ -134,8 +136,14 @@ walk_tail_kernel(const WalkTailArgs a) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) sh_flag = 0;
     __syncthreads();
-    // guard: a warp per interval (writes esde_n, flags, counts the flagged ones)
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // this CTA's slice of the E_kl0 / E_obs partial rows (issued first: independent of the guard)
+    for (int r = blockIdx.x * 256 + threadIdx.x; r < a.napart; r += a.guard_ctas * 256) {
+        acc[1] += __ldcg(a.apart + (int64_t)r * 4 + 0);
+        acc[2] += __ldcg(a.apart + (int64_t)r * 4 + 1);
+        acc[3] += __ldcg(a.apart + (int64_t)r * 4 + 2);
+    }
+    // guard: a warp per interval (writes esde_n, flags, counts the flagged ones)
     const int n = a.g.n_begin + blockIdx.x * 8 + w;
     if (n < a.g.n_end) {
         guard_interval(a.g, n, lane);
@@ -144,12 +152,6 @@ walk_tail_kernel(const WalkTailArgs a) {
             acc[0] = a.g.esde_n[n];
             if (a.g.flags[n]) atomicOr(&sh_flag, a.g.flags[n]);
         }
-    }
-    // this CTA's slice of the E_kl0 / E_obs partial rows
-    for (int r = blockIdx.x * 256 + threadIdx.x; r < a.napart; r += a.guard_ctas * 256) {
-        acc[1] += __ldcg(a.apart + (int64_t)r * 4 + 0);
-        acc[2] += __ldcg(a.apart + (int64_t)r * 4 + 1);
-        acc[3] += __ldcg(a.apart + (int64_t)r * 4 + 2);
     }
     block_sum<4, 256>(acc, sh_red);
     if (threadIdx.x == 0) {
@@ -165,6 +167,11 @@ walk_tail_kernel(const WalkTailArgs a) {
     if (!sh_last) return;
     // last guard CTA: fold the CTA partials in fixed order
     __threadfence();
+    int32_t rs_pre = 0, nf_pre = 0;       // thread 0 needs these at the very end: fetch them now
+    if (threadIdx.x == 0) {
+        rs_pre = __ldcg(a.refine_status);
+        nf_pre = a.g.nflagged != nullptr ? __ldcg(a.g.nflagged) : 0;
+    }
     double tot[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = threadIdx.x; c < a.guard_ctas; c += 256) {
 #pragma unroll
@@ -174,20 +181,17 @@ walk_tail_kernel(const WalkTailArgs a) {
     block_sum<4, 256>(tot, sh_red);
     __shared__ int sh_pub;
     if (threadIdx.x == 0) {
-        const int nflag = a.g.nflagged != nullptr ? __ldcg(a.g.nflagged) : 0;
+        const int nflag = nf_pre;
         sh_pub = 0;
         if (nflag == 0) {
-            tail_finish(a, tot, 0, 0);
+            tail_finish(a, tot, 0, 0, rs_pre);
             sh_pub = a.p.world > 1;
         } else {
             a.late[0] = 1;                // refine_kernel changes Esde: walk_late_kernel finishes
         }
     }
     __syncthreads();
-    if (sh_pub && w == 0) {
-        __threadfence();
-        tail_publish_record(a.p, a.out, lane);
-    }
+    if (sh_pub && w == 0) tail_publish_record(a.p, a.out, lane);      // after the barrier above
 }
 
 // after refine_kernel / apply_refine_kernel of a flagged evaluation; grid = 1 + edge CTAs
@@ -224,7 +228,7 @@ walk_late_kernel(const WalkLateArgs a) {
     block_sum<4, 256>(acc, sh_red);
     __syncthreads();
     if (threadIdx.x == 0) {
-        tail_finish(a.t, acc, sh_flag, 1);
+        tail_finish(a.t, acc, sh_flag, 1, __ldcg(a.t.refine_status));
         for (int i = 0; i < a.t.ngbar; ++i) a.t.gbar[i] = 0u;
         a.t.g.nflagged[0] = 0;
         __threadfence();
