@@ -287,6 +287,10 @@ esde_l96_walk_kernel(const WalkArgs a) {
         if (id == (PERSIST ? total : 0u) + gridDim.x - 1u) *a.run_ticket = 0u;
         sm.cta_id = id;
     }
+    // the kernels behind this one are launched as programmatic dependents and wait for this
+    // grid to complete (griddepcontrol.wait): once every CTA has started they may take the SM
+    // slots the ragged end frees, instead of being launched after the last CTA has exited
+    pdl_launch_dependents();
     __syncthreads();
     unsigned cur_id = sm.cta_id;
     bool have_nx = false;                 // this run's first interval was prefetched
