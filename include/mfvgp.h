@@ -199,12 +199,15 @@ int mfvgp_scg_host(mfvgp_handle *h, double *x_h, int max_it, double x_tol,
  * interval block [n_begin, n_end).  Afterwards mfvgp_ecost / mfvgp_scg are
  * collective calls: x_d / grad_d keep the full reference layout, each rank
  * reads and writes only its own columns (plus the one column it shares with
- * the next rank).  Per evaluation ONE ncclAllGather carries each rank's scalar
- * record (F, E0, Esde, Eobs, the six status bits) and its two shared gradient
- * columns; records are folded in rank order, so every rank holds identical
- * scalars and takes identical SCG branches (MFVGP_XCHG=split selects
- * ncclSend/ncclRecv of the columns + an all-gather of the record instead).
- * NCCL is bound at run time (dlopen).
+ * the next rank).  Per evaluation each rank's scalar record (F, E0, Esde, Eobs, the six
+ * status bits) goes to every rank and its part of the gradient of a shared column to that
+ * neighbour only.  mfvgp_comm_init maps every rank's mailbox into every other rank (CUDA IPC
+ * handles exchanged through the communicator), after which the exchange is plain stores over
+ * NVLink plus release / acquire flags inside the evaluation's own kernels; records are folded
+ * in rank order, so every rank holds identical scalars and takes identical SCG branches.
+ * If the ranks cannot map each other's memory, or with MFVGP_XCHG=nccl|split, the exchange is
+ * one ncclAllGather of record + shared columns (or ncclSend/ncclRecv of the columns + an
+ * all-gather of the record).  NCCL is bound at run time (dlopen).
  */
 int mfvgp_comm_unique_id(void *id128_out /*128 bytes*/);
 int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void *id128);
