@@ -592,7 +592,10 @@ struct GuardArgs {
 
 // one warp: interval n, lane = 0..31 (partials may come from other CTAs of the same launch:
 // read them through L2)
-__device__ __forceinline__ void guard_interval(const GuardArgs &a, int n, int lane) {
+// esde_out / flag_out (lane 0): what was written to esde_n[n] / flags[n], for callers that go on
+// to sum them (saves reading back what this thread has just stored)
+__device__ __forceinline__ void guard_interval(const GuardArgs &a, int n, int lane,
+                                               double *esde_out = nullptr, int *flag_out = nullptr) {
     const int warp = n - a.n_begin;
     double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 3                     // all the loads of up to 96 tiles in flight at once
@@ -623,6 +626,7 @@ __device__ __forceinline__ void guard_interval(const GuardArgs &a, int n, int la
         if (!(ubE < 0.125 * tolE)) f |= 1;
         if (!(ubS < 0.125 * tolS)) f |= 2;
         a.flags[n] = f;
+        if (esde_out != nullptr) { *esde_out = 0.5 * h * p[0]; *flag_out = f; }
         if (f && a.nflagged != nullptr) atomicAdd(a.nflagged, 1);
     }
 }

@@ -146,11 +146,12 @@ walk_tail_kernel(const WalkTailArgs a) {
     // guard: a warp per interval (writes esde_n, flags, counts the flagged ones)
     const int n = a.g.n_begin + blockIdx.x * 8 + w;
     if (n < a.g.n_end) {
-        guard_interval(a.g, n, lane);
-        __syncwarp();
+        double esde = 0.0;
+        int flag = 0;
+        guard_interval(a.g, n, lane, &esde, &flag);
         if (lane == 0) {
-            acc[0] = a.g.esde_n[n];
-            if (a.g.flags[n]) atomicOr(&sh_flag, a.g.flags[n]);
+            acc[0] = esde;
+            if (flag) atomicOr(&sh_flag, flag);
         }
     }
     block_sum<4, 256>(acc, sh_red);
