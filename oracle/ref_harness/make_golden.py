@@ -158,6 +158,51 @@ def scg_branch_case(setup, M, seed, amps_m, amps_s, max_iter, name):
     print(f"scg_{name}: fx={fx:.12g} nit={nit} evals={stats['func_eval']} branches={ev} ({wall:.1f}s)")
 
 
+def scg_hilltop_case(M, seed, sig, c, amp, sv, rn, max_iter, name):
+    """
+    delta <= 0 (scaled_cg.py:233-236) needs negative curvature along the search direction.  On
+    sane inputs that was only found where the double well is genuinely non-convex: the mean
+    path started on the hilltop between the wells (m = c ~ 0, the drift's unstable point), small
+    uniform variances, weak observations (obs_noise rn) and system noise sig.  Found by a random
+    search over (sig, c, amp, sv, rn) with the oracle; the recipe below rebuilds the start.
+    """
+    harness.install()
+    C = harness.reference_classes()
+    s = _truncate(setups.make_dw(), M)
+    sde = C["DoubleWell"](sig, 1.0, r_seed=575)
+    sde.make_trajectory(0.0, 10.0, 0.001)              # only sets the time window FreeEnergy checks
+    s["sde"], s["obs_noise"] = sde, rn
+    r = np.random.default_rng(seed)
+    for grid in ([0.02, 0.05, 0.2, 0.8], [0.0, 0.2, 0.4, 0.58, 0.8], [0.02, 0.1], [0.01, 0.05, 0.2],
+                 [0.04, 1.0, 25.0]):
+        r.choice(grid)                                  # the search drew its parameters first
+    nm = 3 * M + 4
+    x0 = s["x0"].copy()
+    x0[:nm] = c + amp * r.standard_normal(nm)
+    x0[nm:] = np.log(sv) + 0.05 * r.standard_normal(x0.size - nm)
+    s["x0"] = x0
+    from oracle import mfvgp_oracle as O
+    fe = setups.free_energy_of(s, n_jobs=1)
+    t0 = time.perf_counter()
+    x, fx, stats = fe.find_minimum(x0.copy(), max_iter=max_iter)
+    wall = time.perf_counter() - t0
+    out = _inputs(s)
+    o = O.FreeEnergyOracle(out["system"], out["sigma"], out["theta"], out["mu0"], out["tau0"],
+                           out["obs_times"], out["obs_values"], out["obs_noise"], None)
+    ev = {}
+    xo, fxo, so = o.find_minimum(x0.copy(), max_iter=max_iter, events=ev)
+    nit = int(stats["nit"])
+    assert so["nit"] == nit and so["func_eval"] == int(stats["func_eval"]), (so["nit"], nit, so["func_eval"], stats["func_eval"])
+    assert np.abs(so["fx"][:nit] - stats["fx"][:nit]).max() <= 1e-9 * np.abs(stats["fx"][:nit]).max()
+    assert ev["delta<=0"] >= 1
+    out.update(max_iter=max_iter, x_opt=x, fx_opt=float(fx), nit=nit, fx_hist=stats["fx"],
+               dfx_hist=stats["dfx"], func_eval=int(stats["func_eval"]), ref_wall_s=wall,
+               n_reject=ev["reject"], n_delta_le0=ev["delta<=0"], n_mu_ge0=ev["mu>=0"],
+               n_restart=ev["restart"], start_seed=seed)
+    np.savez_compressed(GOLDEN_DIR / f"scg_{name}.npz", **out)
+    print(f"scg_{name}: fx={fx:.12g} nit={nit} evals={stats['func_eval']} branches={ev} ({wall:.1f}s)")
+
+
 # -- special inputs -----------------------------------------------------------
 def _with_x(setup, x, name):
     s = dict(setup)
@@ -229,6 +274,10 @@ CASES = {
     "scg_branch_L96_8": lambda: scg_branch_case(
         setups.make_l96(D=8, tf=2.0), 2, 335045, [0.2, 0.5, 1.0, 2.0], [0.6, 0.8, 1.0, 1.2], 40,
         "branch_L96_8"),
+    "scg_hilltop_DW3": lambda: scg_hilltop_case(3, 38744149, 0.2, 0.0, 0.02, 0.05, 25.0, 25,
+                                                "hilltop_DW3"),
+    "scg_hilltop_DW3b": lambda: scg_hilltop_case(3, 899221749, 0.02, 0.0, 0.02, 0.01, 1.0, 25,
+                                                 "hilltop_DW3b"),
 }
 
 if __name__ == "__main__":

@@ -10,8 +10,8 @@ EVAL_CASES = ["DW", "OU", "L63", "L96_4", "L96_8", "L96_40", "L96_67p", "L96_500
 REFINE_CASES = ["DW_refine", "L96_6_refine"]
 SCG_CASES = ["DW", "OU", "L63_T5", "L96_8"]
 # reference runs that take the rare branches of scaled_cg.py: rejected trial points (:254-279),
-# mu >= 0 (:194-197), restart after dim_x successes (:361-364)
-SCG_BRANCH_CASES = ["branch_DW3", "branch_DW4"]
+# mu >= 0 (:194-197), delta <= 0 (:233-236), restart after dim_x successes (:361-364)
+SCG_BRANCH_CASES = ["branch_DW3", "branch_DW4", "hilltop_DW3", "hilltop_DW3b"]
 
 
 def load_golden(kind, name):

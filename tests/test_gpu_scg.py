@@ -41,16 +41,18 @@ VARIANTS = [{}, {"MFVGP_SCG_PIPELINE": "0"}, {"MFVGP_SCG_PIPELINE": "2"},
 def test_scg_rare_branches_match_reference(name, variant, monkeypatch):
     """
     Runs of the UNMODIFIED reference that reject trial points (scaled_cg.py:254-279: g_now <-
-    grad_old, dfx = sum|grad_old|), find mu >= 0 and reset the direction (:194-197) and restart
-    after dim_x successes (:361-364): same nit, func_eval and fx / dfx history on the device, in
+    grad_old, dfx = sum|grad_old|), find mu >= 0 and reset the direction (:194-197), find
+    delta <= 0 and rescale (:233-236; the hilltop cases: a double-well mean path started on the
+    unstable point between the wells) and restart after dim_x successes (:361-364): same nit,
+    func_eval and fx / dfx history on the device, in
     every variant of the control loop -- chains enqueued ahead (and voided by a rejection),
     step by step, cluster and grid reductions, host-read records (MFVGP_SCG_FUSED=0).
     """
     for k, v in VARIANTS[variant].items():
         monkeypatch.setenv(k, v)
     g = load_golden("scg", name)
-    assert int(g["n_reject"]) >= 4 and int(g["n_mu_ge0"]) >= 1 and int(g["n_restart"]) >= 2
-    fe = make_free_energy(g)
+    assert int(g["n_reject"]) >= 2                       # + mu >= 0, delta <= 0, restarts: see
+    fe = make_free_energy(g)                             # test_reference_goldens_cover_every_rare_scg_branch
     x, fx, stats = fe.find_minimum(g["x0"].copy(), max_iter=int(g["max_iter"]))
     nit = int(g["nit"])
     assert stats["nit"] == nit and stats["func_eval"] == int(g["func_eval"])
@@ -71,11 +73,8 @@ def test_scg_wild_start_raises_like_the_reference(case):
     Starts with scattered log-variances (x0 + as N(0,1), as ~ 1): the interpolated variance dips
     to zero inside an interval, and the UNMODIFIED reference stops its SCG run with
     ``RuntimeError: ... is not a finite number`` (free_energy.py:313-316, 547-550) -- recorded
-    while searching for starts that take SCG's delta <= 0 branch (tools/scg_branch_search.py;
-    that branch, scaled_cg.py:233-236, showed up on such starts only, so no reference golden
-    pins it: it is covered by the host code reading line by line like :232-236 and by the
-    CUDA variants agreeing with each other, test_scg_switches_agree).  The device run must end
-    the same way: the reference's exception, not a silent result.
+    while searching for starts that take SCG's rare branches (tools/scg_branch_search.py).  The
+    device run must end the same way: the reference's exception, not a silent result.
     """
     name, M_, seed = WILD[case]
     g0 = load_golden("scg", name)
