@@ -112,6 +112,7 @@ struct mfvgp_handle {
     int64_t peer_slot = 0;
     long long xchg_epoch = 0;
     unsigned *peer_ticket = nullptr;
+    PeerLayout *peer_layout = nullptr;   // device copy for kernels that exchange by themselves
     int peer_nchunk = 1;
     // walk path tail (walk_tail.cuh)
     double *tail_part = nullptr;
@@ -453,6 +454,7 @@ extern "C" int mfvgp_destroy(mfvgp_handle *h) {
     for (int r = 0; r < h->world && r < kPeerMaxWorld; ++r)
         if (h->peer_ok && r != h->rank && h->peer_box[r]) cudaIpcCloseMemHandle(h->peer_box[r]);
     if (h->mbox) cudaFree(h->mbox);
+    if (h->peer_layout) cudaFree(h->peer_layout);
     if (h->peer_ticket) cudaFree(h->peer_ticket);
     if (h->comm && nccl().lib) nccl().CommDestroy(h->comm);
     if (h->pin) cudaFreeHost(h->pin);
@@ -1031,6 +1033,14 @@ extern "C" int mfvgp_comm_init(mfvgp_handle *h, int rank, int world, const void 
                     if (r != rank && h->peer_box[r]) { cudaIpcCloseMemHandle(h->peer_box[r]); h->peer_box[r] = nullptr; }
             }
             h->peer_ok = all_ok;
+            if (all_ok) {
+                PeerLayout pl;
+                for (int r = 0; r < kPeerMaxWorld; ++r) pl.box[r] = r < world ? h->peer_box[r] : nullptr;
+                pl.slot_doubles = h->peer_slot; pl.rank = rank; pl.world = world; pl.D = h->D;
+                CK(cudaMalloc((void **)&h->peer_layout, sizeof(PeerLayout)));
+                CK(cudaMemcpy(h->peer_layout, &pl, sizeof(PeerLayout), cudaMemcpyHostToDevice));
+                CK(cudaDeviceSynchronize());
+            }
         }
     }
     if (dev_alloc(&h->edge_send, 4 * (size_t)h->D) || dev_alloc(&h->edge_recv, 4 * (size_t)h->D) ||
@@ -1793,6 +1803,11 @@ struct ScgRun {
         fa.epoch = 0;
         fa.spec = 0; fa.decide = 0; fa.refined_mask = 0;
         fa.f_old_in = fa.x_tol = fa.f_tol = 0.0;
+        fa.peer = nullptr; fa.peer_epoch = 0; fa.sync_status = h->refine_status;
+        if (fused && h->world > 1) {              // every fold is one exchange between the ranks
+            fa.peer = h->peer_layout;
+            fa.peer_epoch = ++h->xchg_epoch;
+        }
         if (fused) {
             fa.ticket = h->tickets + h->L;
             if (mode == 0 || mode == 3) {                             // only these publish
@@ -2072,10 +2087,14 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     ScgRun R{h, st, vm};
     {
         const char *e = getenv("MFVGP_SCG_FUSED");
-        R.fused = h->world == 1 && !(e && e[0] == '0');
-        R.peer_rec = h->world > 1 && h->peer_ok && !(e && e[0] == '0');
+        // sharded over peer memory: the same fused folds, each followed by an exchange in the
+        // last block (MFVGP_SCG_FUSED=2 keeps round 2's first version: fold + send and
+        // rank-ordered fold as two kernels per reduction, host computes the step lengths)
+        const bool off = e && e[0] == '0', two_kernel = e && e[0] == '2';
+        R.fused = !off && (h->world == 1 || (h->peer_ok && !two_kernel));
+        R.peer_rec = h->world > 1 && h->peer_ok && two_kernel;
         const char *c = getenv("MFVGP_SCG_CLUSTER");
-        if (R.fused && n <= kClMaxElems && !(c && c[0] == '0')) {
+        if (R.fused && h->world == 1 && n <= kClMaxElems && !(c && c[0] == '0')) {
             const bool wide = scg_cluster16_ok(h->device);
             R.cl_nt = wide ? 512 : 1024;
             const int max_ctas = wide ? 16 : 8;
@@ -2111,6 +2130,9 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     int64_t count_success = 0;
     if (failed) { nit = 0; fx = f_now; }
 
+    // optimistic evaluations exist on the small-problem path of one GPU only (ecost_impl); a
+    // chain must not be voided for MFVGP_ST_REFINED when its evaluations did run the adaptive path
+    const bool can_opt = h->coop && h->world == 1;
     bool chained = false;          // a speculative chain for this iteration is in flight
     bool chain_optimistic = false; // ... whose evaluations ran without the refine_kernel launch
     long long chain_epoch = 0;     // ... and publishes its record under this epoch
@@ -2120,7 +2142,9 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
     bool ahead = false, ahead_optimistic = false, ahead_valid = false;
     long long ahead_epoch = 0;
     int clean_run = 0;
-    bool pipeline = R.fused;
+    // (sharded: no chain ahead of its predecessor's outcome -- a void chain would skip its
+    // exchanges, and the mailboxes' two slots rely on every exchange epoch being used)
+    bool pipeline = R.fused && h->world == 1;
     int clean_needed = 2;
     {
         const char *e = getenv("MFVGP_SCG_PIPELINE");       // 0: off, 2: after every chain (tests)
@@ -2136,7 +2160,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
             if (pipeline && clean_run >= clean_needed && j + 1 < max_it) {
                 // roles after an accepted iteration j: x <-> xt, (gold, gnew, gnow) rotate
                 const int restart1 = count_success + 1 == n_total;
-                ahead_optimistic = h->opt_cooldown == 0;
+                ahead_optimistic = can_opt && h->opt_cooldown == 0;
                 RC(R.chain(d, gnow, 0.0, restart1, 0.0, xt, x, gp, gold, ahead_optimistic, true,
                            0.0, x_tol, f_tol));
                 ahead_epoch = R.last_epoch;
@@ -2258,7 +2282,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         if (count_success == n_total) {
             count_success = 0;
             if (spec) {
-                chain_optimistic = h->opt_cooldown == 0;
+                chain_optimistic = can_opt && h->opt_cooldown == 0;
                 RC(R.chain(d, gnew, 0.0, 1, beta, x, xt, gp, gnow, chain_optimistic, false, f_old,
                            x_tol, f_tol));
                 chain_epoch = R.last_epoch;
@@ -2271,7 +2295,7 @@ extern "C" int mfvgp_scg(mfvgp_handle *h, double *x_d, int max_it, double x_tol,
         } else if (success) {
             const double gamma = fmax(prnum / mu, 0.0);
             if (spec) {
-                chain_optimistic = h->opt_cooldown == 0;
+                chain_optimistic = can_opt && h->opt_cooldown == 0;
                 RC(R.chain(d, gnew, gamma, 0, beta, x, xt, gp, gnow, chain_optimistic, false,
                            f_old, x_tol, f_tol));
                 chain_epoch = R.last_epoch;

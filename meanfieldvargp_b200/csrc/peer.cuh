@@ -64,6 +64,21 @@ __device__ __forceinline__ long long *peer_flag(double *box, const PeerArgs &a, 
                                          + (int64_t)a.world * kPeerRec + 4 * (int64_t)a.D) + i;
 }
 
+// The mailboxes as a kernel that does its exchange itself (scg.cuh red_store) sees them: lives
+// in device memory, written once by mfvgp_comm_init.  Same layout as PeerArgs describes.
+struct PeerLayout {
+    double *box[kPeerMaxWorld];
+    int64_t slot_doubles;
+    int rank, world, D;
+};
+__device__ __forceinline__ double *pl_rec(const PeerLayout &L, double *box, long long epoch, int r) {
+    return box + (epoch & 1) * L.slot_doubles + (int64_t)r * kPeerRec;
+}
+__device__ __forceinline__ long long *pl_flag(const PeerLayout &L, double *box, long long epoch, int i) {
+    return reinterpret_cast<long long *>(box + (epoch & 1) * L.slot_doubles
+                                         + (int64_t)L.world * kPeerRec + 4 * (int64_t)L.D) + i;
+}
+
 __device__ __forceinline__ void st_release_sys(long long *p, long long v) {
     asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -71,6 +86,43 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long *p) {
     long long v;
     asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+
+// One thread: sends four partial sums to every rank, waits for every rank's, folds them in rank
+// order (slots 0-2 summed, slot 3 max'ed) -- identical bits on every rank.  false: a peer did
+// not answer within 30 s.
+__device__ __forceinline__ bool peer_allreduce4(const PeerLayout &L, long long epoch, double (&r)[4]) {
+    for (int p = 0; p < L.world; ++p) {
+        double *dst = pl_rec(L, L.box[p], epoch, L.rank);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = r[i];
+    }
+    for (int p = 0; p < L.world; ++p) st_release_sys(pl_flag(L, L.box[p], epoch, L.rank), epoch);
+    double *mine = L.box[L.rank];
+    bool ok = true;
+    unsigned long long t0 = 0, t1 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int p = 0; p < L.world; ++p) {
+        const long long *f = pl_flag(L, mine, epoch, p);
+        for (long spin = 0; ld_acquire_sys(f) != epoch; ++spin) {
+            __nanosleep(20);
+            if ((spin & 1023) == 1023) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 30000000000ull) { ok = false; break; }
+            }
+        }
+    }
+    double acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = pl_rec(L, mine, epoch, 0)[i];
+    for (int p = 1; p < L.world; ++p) {
+        const double *src = pl_rec(L, mine, epoch, p);
+        acc[0] += src[0]; acc[1] += src[1]; acc[2] += src[2];
+        acc[3] = fmax(acc[3], src[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = acc[i];
+    return ok;
 }
 
 // grid = ceil(D / 256) (or 1 without edges).  The last CTA to finish releases the flags.

@@ -55,6 +55,11 @@ struct FoldArgs {
     int decide;                // mode 3: take the decision
     int refined_mask;          // status bits that void an optimistic chain (0 if not optimistic)
     double f_old_in, x_tol, f_tol;
+    // sharded handles: the last block's fold goes through every rank before the scalars are
+    // used (peer_allreduce4), so the chain logic above runs on identical numbers on every rank
+    const PeerLayout *peer;    // nullptr on one GPU
+    long long peer_epoch;
+    int32_t *sync_status;      // MFVGP_ST_SYNC_TIMEOUT is OR-ed in here if a rank does not answer
 };
 
 __device__ __forceinline__ bool chain_is_void(const FoldArgs &fa) {
@@ -331,7 +336,11 @@ __device__ __forceinline__ void red_store(double (&v)[kRedSlots], double *part,
     __threadfence();
     double r[kRedSlots];
     fold_partials(part, (int)gridDim.x, r, sh);
-    if (threadIdx.x == 0) fold_finish(r, fa);
+    if (threadIdx.x == 0) {
+        if (fa.peer != nullptr && !peer_allreduce4(*fa.peer, fa.peer_epoch, r))
+            atomicOr(fa.sync_status, 32);
+        fold_finish(r, fa);
+    }
 }
 
 // d = gamma*d - g (gamma = 0 and d arbitrary gives the restart d = -g);
