@@ -91,3 +91,17 @@ def test_status_bits_survive_the_rank_combine():
                     env_extra={"MG_MODE": "inject", "MFVGP_INJECT_STATUS": "32@1"}, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "MG_INJECT_OK 2" in res.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"MFVGP_SCG_FUSED": "2"}, {"MFVGP_SCG_FUSED": "0"},
+                                 {"MFVGP_XCHG": "nccl"}, {"MFVGP_WALK_TAIL": "0"}])
+def test_sharded_variants_match_single_gpu(env):
+    """the same worker under the other exchange / control-loop variants: two-kernel SCG folds
+    over peer memory, host-driven SCG, the NCCL all-gather exchange, the unfused walk tail"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    res = _torchrun(2, [str(ROOT / "tests" / "mg_worker.py")], env_extra=env, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "MG_OK 2" in res.stdout
