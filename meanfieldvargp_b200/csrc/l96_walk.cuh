@@ -37,12 +37,19 @@ namespace mfvgp {
 
 __constant__ __align__(16) double c_pair[kPairs * kPairStride];
 __constant__ double c_vcentre;
+// part (B), weights applied by the consumer (MFVGP_WALK_DEFERW): per Gauss-Legendre node
+// [0..3] 2 v B3_k, [4..7] 2 v dB3_k, [8..10] v B2_k, [11] v
+constexpr int kGlwStride = 12;
+__constant__ __align__(16) double c_glw[kGL * kGlwStride];
 
 constexpr int kWalkMaxTN = 64;
 
 // tuning knobs (tools/build_variant.sh builds variants with -D overrides)
 #ifndef MFVGP_WALK_GB
 #define MFVGP_WALK_GB 2
+#endif
+#ifndef MFVGP_WALK_DEFERW
+#define MFVGP_WALK_DEFERW 1
 #endif
 #ifndef MFVGP_WALK_THREADS_PER_SM
 #define MFVGP_WALK_THREADS_PER_SM 512
@@ -57,8 +64,8 @@ struct PanelSums {
 // s(x) = al0 + al1 x + al2 x^2, q(x) = be0 + be1 x on the panel.
 __device__ __forceinline__ void panel_sums(double al0, double al1, double al2, double be0,
                                            double be1, PanelSums &o) {
-    double kE = 0.0, N0 = 0.0, N1 = 0.0, N2 = 0.0, N3 = 0.0, L0 = 0.0, L1 = 0.0, L2 = 0.0;
-    double gE = 0.0, GN0 = 0.0, GN1 = 0.0, GN2 = 0.0, GL0 = 0.0, GL1 = 0.0;
+    double N0 = 0.0, N1 = 0.0, N2 = 0.0, N3 = 0.0, L0 = 0.0, L1 = 0.0, L2 = 0.0;
+    double GN0 = 0.0, GN1 = 0.0, GN2 = 0.0, GL0 = 0.0, GL1 = 0.0;
     // two pairs per trip (even pair: Kronrod only; odd pair: also a Gauss-10 node); the loop
     // is kept rolled so the live ranges of the reciprocals stay short (no spills)
 #pragma unroll 1
@@ -73,10 +80,8 @@ __device__ __forceinline__ void panel_sums(double al0, double al1, double al2, d
             const double sm = fma(fma(al2, -x, al1), -x, al0);
             const double qp = fma(be1, x, be0), qm = fma(-be1, x, be0);
             const double ip = qp * fast_rcp3(sp), im = qm * fast_rcp3(sm);   // q / s
-            const double tE = fma(qp, ip, qm * im);                          // sum of q^2 / s
             const double p2 = ip * ip, m2 = im * im;                         // (q/s)^2
             const double ue = p2 + m2, uo = p2 - m2, le = ip + im, lo = ip - im;
-            kE = fma(v, tE, kE);
             N0 = fma(v, ue, N0);
             N2 = fma(vx2, ue, N2);
             N1 = fma(vx, uo, N1);
@@ -86,7 +91,6 @@ __device__ __forceinline__ void panel_sums(double al0, double al1, double al2, d
             L1 = fma(vx, lo, L1);
             if (h == 1) {
                 const double w = c45.y, wx = c67.x, wx2 = c67.y;
-                gE = fma(w, tE, gE);
                 GN0 = fma(w, ue, GN0);
                 GN2 = fma(wx2, ue, GN2);
                 GN1 = fma(wx, uo, GN1);
@@ -97,10 +101,14 @@ __device__ __forceinline__ void panel_sums(double al0, double al1, double al2, d
     }
     {   // centre node x = 0 (Kronrod only)
         const double ic = be0 * fast_rcp3(al0), vc = c_vcentre;
-        kE = fma(vc, be0 * ic, kE);
         N0 = fma(vc, ic * ic, N0);
         L0 = fma(vc, ic, L0);
     }
+    // q^2/s = q (q/s) with q = be0 + be1 x:  sum v q^2/s = be0 sum v (q/s) + be1 sum v x (q/s),
+    // i.e. the energy sums follow from the first-power sums that the gradient needs anyway
+    // (3.5 FP64 instructions per node pair less; the terms of a sum have one sign unless q
+    // changes sign inside the panel, so nothing cancels beyond a small factor)
+    const double kE = fma(be0, L0, be1 * L1), gE = fma(be0, GL0, be1 * GL1);
     o.kE = kE; o.N0 = N0; o.N1 = N1; o.N2 = N2; o.N3 = N3; o.L0 = L0; o.L1 = L1; o.L2 = L2;
     o.gE = gE; o.GN0 = GN0; o.GN1 = GN1; o.GN2 = GN2; o.GL0 = GL0; o.GL1 = GL1;
 }
@@ -251,6 +259,7 @@ struct WalkSmem {
     double carry[2][TE];          // k=3 / k=2 part of the previous interval
     double e0[2][TE];             // E_kl0 energy terms of the rows (run 0 only)
     double red[9][TE / 32];
+    double isg[TE];               // 1 / Sigma of the rows (the neighbours' weights, DEFERW)
     double dt[kWalkMaxTN], idt[kWalkMaxTN];
     // persistent CTAs: the next run's first interval, fetched during the last interval of the
     // current one (P0..P3, log S0..S2, Sigma of the row; observation index; interval times)
@@ -342,12 +351,21 @@ esde_l96_walk_kernel(const WalkArgs a) {
     S0 = exp(S0); S1 = exp(S1); S2 = exp(S2);
     if (jo >= 0) Ri = 1.0 / Ri;
     const double inv_sig = 1.0 / Sig;
+    sm.isg[e] = inv_sig;
     sm.carry[0][e] = 0.0;
     sm.carry[1][e] = 0.0;
     sm.e0[0][e] = 0.0;
     sm.e0[1][e] = 0.0;
     double acc_obs = 0.0;
     __syncthreads();
+#if MFVGP_WALK_DEFERW
+    // the exchanged derivative terms carry no weight: the row that adds them applies the
+    // producing row's 1 / Sigma (a multiply-add where an add stood), the node weight sits in
+    // the basis table c_glw -- 5 FP64 instructions per (row, node) less than weighting at the
+    // producer
+    const double is_l = sm.isg[e >= 1 ? e - 1 : e], is_r = sm.isg[e + 1 < TE ? e + 1 : e],
+                 is_rr = sm.isg[e + 2 < TE ? e + 2 : e];
+#endif
 
     for (int nl = 0; nl < tnv; ++nl) {
         const int n = n0 + nl;
@@ -377,6 +395,9 @@ esde_l96_walk_kernel(const WalkArgs a) {
 
         // ---- (B) coupled polynomial part, 7 Gauss-Legendre nodes ---------------------------
         double accM[4] = {0, 0, 0, 0}, accS[3] = {0, 0, 0}, accE = 0.0;
+#if MFVGP_WALK_DEFERW
+        const double isdt = inv_sig * inv_dt;
+#endif
 #pragma unroll
         for (int g0 = 0; g0 < kGL; g0 += GB) {
             double own[GB];          // phase 1-2: theta - m - dm;  phase 2-3: w dE_i/dm_i
@@ -431,12 +452,19 @@ esde_l96_walk_kernel(const WalkArgs a) {
                     const double R = fma(u, mb, own[gg]);          // E[f_i] - dm_i
                     const double t1 = sb * u, t2 = mb * su;
                     const double Ec = fma(R, R, fma(t1, u, fma(t2, mb, su * sb)));
+#if MFVGP_WALK_DEFERW
+                    sm.AC[gg][e] = make_double2(fma(R, mb, t1), fma(mb, mb, sb));
+                    sm.BD[gg][e] = make_double2(fma(R, u, t2), fma(u, u, su));
+                    own[gg] = R;
+                    accE = fma(T[T_V], Ec, accE);
+#else
                     const double w = T[T_V] * inv_sig, w2 = w + w;
                     const double wR2 = w2 * R;
                     sm.AC[gg][e] = make_double2(fma(wR2, mb, w2 * t1), w * fma(mb, mb, sb));
                     sm.BD[gg][e] = make_double2(fma(wR2, u, w2 * t2), w * fma(u, u, su));
                     own[gg] = -wR2;
                     accE = fma(w, Ec, accE);
+#endif
                 }
             }
             __syncthreads();
@@ -444,8 +472,19 @@ esde_l96_walk_kernel(const WalkArgs a) {
             for (int gg = 0; gg < GB; ++gg) {
                 if (g0 + gg >= kGL) break;
                 if (is_out) {
-                    const double *T = c_gl + (g0 + gg) * kTabStride;
                     const double2 l = sm.AC[gg][e - 1], r = sm.BD[gg][e + 1], rr = sm.AC[gg][e + 2];
+#if MFVGP_WALK_DEFERW
+                    const double *W = c_glw + (g0 + gg) * kGlwStride;
+                    const double Gm = fma(is_l, l.x, fma(is_r, r.x, fma(-is_rr, rr.x, -inv_sig * own[gg])));
+                    const double Gs = fma(is_l, l.y, fma(is_r, r.y, is_rr * rr.y));
+                    const double Hm = -isdt * own[gg];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        accM[k] = fma(Gm, W[k], fma(Hm, W[4 + k], accM[k]));
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) accS[k] = fma(Gs, W[8 + k], accS[k]);
+#else
+                    const double *T = c_gl + (g0 + gg) * kTabStride;
                     const double Gm = own[gg] + l.x + r.x - rr.x;
                     const double Gs = l.y + r.y + rr.y;
                     const double Hm = own[gg] * inv_dt;
@@ -454,6 +493,7 @@ esde_l96_walk_kernel(const WalkArgs a) {
                         accM[k] += Gm * T[T_B3 + k] + Hm * T[T_DB3 + k];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) accS[k] = fma(Gs, T[T_B2 + k], accS[k]);
+#endif
                 }
             }
         }
@@ -461,7 +501,11 @@ esde_l96_walk_kernel(const WalkArgs a) {
         // ---- per-interval results (same algebra as esde_l96_split_kernel) -------------------
         const double four_inv_dt = 4.0 * inv_dt;
         const double own_poly = dt * (S0 + 4.0 * S1 + S2) * (1.0 / 6.0) + (S2 - S0) - Sig * dt;
+#if MFVGP_WALK_DEFERW
+        const double ksum_E = 0.25 * ro.aE + 4.0 * accE + four_inv_dt * own_poly;
+#else
         const double ksum_E = 0.25 * ro.aE + 4.0 * accE * Sig + four_inv_dt * own_poly;
+#endif
         const double polyS[3] = {dt * (1.0 / 6.0) - 1.0, dt * (4.0 / 6.0), dt * (1.0 / 6.0) + 1.0};
         double dsv[3], own2 = 0.0;
         {

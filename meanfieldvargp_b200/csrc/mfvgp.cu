@@ -249,7 +249,8 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
             // dim tile: the TE in {32, 64, 128} that wastes the fewest threads on halo / padding
             // (TE=64 measures 1.5 % faster in the main kernel at D=8192 but doubles the tile
             // partials the guard / final kernels read: a wash end to end; 96 and 160 -- 3 / 5
-            // warps over 4 schedulers -- are 8-20 % slower)
+            // warps over 4 schedulers -- are 8-20 % slower; 256 -- half the halo rows, but two
+            // CTAs of eight warps per SM wait longer at the barriers -- 3 600 vs 3 139 us)
             int best = 128;
             int64_t best_thr = (int64_t)((D + 121) / 122) * 128;
             for (int te : {64, 32}) {
@@ -336,6 +337,18 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
         double gl[kGL * kTabStride];
         build_gl_table(gl);
         CK(cudaMemcpyToSymbol(c_gl, gl, sizeof(gl)));
+        double glw[kGL * kGlwStride];
+        for (int g = 0; g < kGL; ++g) {
+            const double *T = gl + g * kTabStride;
+            double *W = glw + g * kGlwStride;
+            for (int k = 0; k < 4; ++k) {
+                W[k] = 2.0 * T[T_V] * T[T_B3 + k];
+                W[4 + k] = 2.0 * T[T_V] * T[T_DB3 + k];
+            }
+            for (int k = 0; k < 3; ++k) W[8 + k] = T[T_V] * T[T_B2 + k];
+            W[11] = T[T_V];
+        }
+        CK(cudaMemcpyToSymbol(c_glw, glw, sizeof(glw)));
         double vxB[kNodes], vxD[kNodes], m1poly[4], gkx[kNodesPerPanel];
         build_moment_table(vxB, vxD, m1poly);
         for (int r = 0; r < kNodesPerPanel; ++r) gkx[r] = (double)gk21_x(r);
