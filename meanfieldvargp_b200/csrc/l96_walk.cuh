@@ -48,12 +48,17 @@ constexpr int kWalkMaxTN = 64;
 #ifndef MFVGP_WALK_GB
 #define MFVGP_WALK_GB 2
 #endif
+#ifndef MFVGP_PANEL_UNROLL
+#define MFVGP_PANEL_UNROLL 1
+#endif
 #ifndef MFVGP_WALK_DEFERW
 #define MFVGP_WALK_DEFERW 1
 #endif
 #ifndef MFVGP_WALK_THREADS_PER_SM
 #define MFVGP_WALK_THREADS_PER_SM 512
 #endif
+
+constexpr int kPanelUnroll = MFVGP_PANEL_UNROLL;
 
 // Sums of one Kronrod panel in panel-local coordinates x in [-1, 1].
 struct PanelSums {
@@ -67,8 +72,10 @@ __device__ __forceinline__ void panel_sums(double al0, double al1, double al2, d
     double N0 = 0.0, N1 = 0.0, N2 = 0.0, N3 = 0.0, L0 = 0.0, L1 = 0.0, L2 = 0.0;
     double GN0 = 0.0, GN1 = 0.0, GN2 = 0.0, GL0 = 0.0, GL1 = 0.0;
     // two pairs per trip (even pair: Kronrod only; odd pair: also a Gauss-10 node); the loop
-    // is kept rolled so the live ranges of the reciprocals stay short (no spills)
-#pragma unroll 1
+    // is kept rolled so the live ranges of the reciprocals stay short (fully unrolled --
+    // -DMFVGP_PANEL_UNROLL=5, node constants as immediate constant-bank operands instead of
+    // LDCU, 12 % of the warp instructions -- the walk kernel spills 400 bytes at 128 registers)
+#pragma unroll kPanelUnroll
     for (int ii = 0; ii < kPairs / 2; ++ii) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {

@@ -246,16 +246,19 @@ extern "C" int mfvgp_create(mfvgp_handle **out, int system, int D, int M, int d,
     }
     if (system == MFVGP_SYS_L96) {
         if (h->fused == 2) {
-            // dim tile: the TE in {32, 64, 128} that wastes the fewest threads on halo / padding
-            // (TE=64 measures 1.5 % faster in the main kernel at D=8192 but doubles the tile
-            // partials the guard / final kernels read: a wash end to end; 96 and 160 -- 3 / 5
-            // warps over 4 schedulers -- are 8-20 % slower; 256 -- half the halo rows, but two
-            // CTAs of eight warps per SM wait longer at the barriers -- 3 600 vs 3 139 us)
+            // dim tile TE in {32, 64, 128}: fewest threads spent on halo / padding, with a 7 %
+            // handicap on 128 -- its CTAs of four warps wait longer at the barriers than twice as
+            // many CTAs of two.  Measured at D=8192 (tools/walk_ab.py), where TE=64 runs 4.4 % more
+            // threads (142 tiles of 58 rows against 68 of 122): kernel 3 066 vs 3 141 us at L=4096,
+            // 412 vs 418 at L=512, evaluation 3 107 vs 3 172 and 435 vs 439 (twice the tile
+            // partials for the tail kernel to read).  Before the instruction count of the kernel
+            // fell by 11 % the two were a wash.  96 and 160 -- 3 / 5 warps over 4 schedulers --
+            // are 8-20 % slower; 256 -- half the halo rows of 128 -- 3 600 us.
             int best = 128;
-            int64_t best_thr = (int64_t)((D + 121) / 122) * 128;
+            double best_cost = 1.07 * (double)((D + 121) / 122) * 128;
             for (int te : {64, 32}) {
-                const int64_t thr = (int64_t)((D + te - 7) / (te - 6)) * te;
-                if (thr < best_thr) { best = te; best_thr = thr; }
+                const double cost = (double)((D + te - 7) / (te - 6)) * te;
+                if (cost < best_cost) { best = te; best_cost = cost; }
             }
             h->fte = best;
             const int nt = (D + h->fte - 7) / (h->fte - 6);

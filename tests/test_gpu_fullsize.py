@@ -102,11 +102,12 @@ def test_safe_log_clamps_at_full_size(problem):
     assert abs(fe.last_terms["Eobs"] - Eobs) <= 1e-12 * abs(Eobs)
 
 
-# ---- the walk kernel against the oracle at D=8192 (68 dim tiles, wrap-around halo) --------------
-@pytest.mark.parametrize("M_", [9, 33])
-def test_walk_kernel_equals_oracle_at_D8192(M_):
+# ---- the walk kernel against the oracle at D=8192 (wrap-around halo over many dim tiles) --------
+@pytest.mark.parametrize("M_,ftile,ntiles", [(9, None, 142), (33, None, 142), (9, "128,2", 68)])
+def test_walk_kernel_equals_oracle_at_D8192(M_, ftile, ntiles, monkeypatch):
     """
-    lorenz_96.py:221-236 (circular neighbours) over 68 tiles of 122 rows, free_energy.py:651-751.
+    lorenz_96.py:221-236 (circular neighbours) over 142 tiles of 58 rows (the default at this D)
+    and 68 tiles of 122 rows, free_energy.py:651-751.
     Two bands of rows get a steep variance mid-point so that scipy's quad_vec bisects further on
     those intervals (the oracle calls the real quad_vec): the guard must flag them and
     refine_kernel must reproduce the refined integrals.  Tolerance 1e-10 (north_star) on F, on the
@@ -122,8 +123,11 @@ def test_walk_kernel_equals_oracle_at_D8192(M_):
     Fo, go = oracle.E_cost(x)
     neval = np.array(oracle.neval)
     assert (neval[:, 2] > 63).sum() >= 2          # the reference's quadrature did refine
+    if ftile:
+        monkeypatch.setenv("MFVGP_FTILE", ftile)
     fe = make_free_energy(g)
-    assert fe.describe()["path"] == "walk" and int(fe.describe()["ntiles"]) == 68
+    monkeypatch.delenv("MFVGP_FTILE", raising=False)
+    assert fe.describe()["path"] == "walk" and int(fe.describe()["ntiles"]) == ntiles
     F, grad = fe.E_cost(x)
     assert fe.last_status & 8                     # MFVGP_ST_REFINED
     info = fe.refine_info()
