@@ -15,6 +15,7 @@
 #include "nccl_dyn.h"
 #include "refine.cuh"
 #include "l96_walk.cuh"
+#include "l96_lean.cuh"
 #include "l96_coop.cuh"
 #include "posterior.cuh"
 #include "trajectory.cuh"
@@ -1222,11 +1223,15 @@ extern "C" int mfvgp_ecost_batch(mfvgp_handle *h, int B, const double *x_d, int 
     // which main kernel: the cooperative one (two lanes per cell, 26 dimensions per CTA) is built
     // for the latency of ONE evaluation; once the batch alone fills the GPU the one-thread-per-
     // cell split kernel does the same work in a third of the time.  MFVGP_BATCH_KERNEL=coop|split
+    // ("lean": the same shape with the walk kernel's instruction count, l96_lean.cuh; "split":
+    // the independently written esde_l96_split_body, kept as the cross-check)
     bool split = l96 && (int64_t)B * D * nl >= 148 * 2048;
+    bool lean = true;
     if (l96) {
         const char *e = getenv("MFVGP_BATCH_KERNEL");
         if (e && e[0] == 'c') split = false;
-        if (e && e[0] == 's') split = true;
+        if (e && e[0] == 's') { split = true; lean = false; }
+        if (e && e[0] == 'l') split = true;
     }
     // tile width with the fewest padded threads (D=500: 9 x 64 = 576 against 5 x 128 = 640)
     int te = ((D + 121) / 122) * 128 <= ((D + 57) / 58) * 64 ? 128 : 64;
@@ -1283,6 +1288,10 @@ extern "C" int mfvgp_ecost_batch(mfvgp_handle *h, int B, const double *x_d, int 
         CK(launch_pdl(esde_small_batch_kernel<2>, dim3(nl, B), 64, st, c, bs, L));
     } else if (!split) {
         CK(launch_pdl(esde_l96_coop_batch_kernel, dim3(ntiles, nl, B), kCoopNT, st, c, bs));
+    } else if (lean && te == 128) {
+        esde_l96_lean_batch_kernel<128><<<dim3(nl * ntiles, B), 128, 0, st>>>(c.a, bs);
+    } else if (lean) {
+        esde_l96_lean_batch_kernel<64><<<dim3(nl * ntiles, B), 64, 0, st>>>(c.a, bs);
     } else if (te == 128) {
         esde_l96_split_batch_kernel<128><<<dim3(nl * ntiles, B), 128, 0, st>>>(c.a, bs);
     } else {

@@ -20,7 +20,7 @@ def _states(g, B, seed, scale=0.05):
     return X
 
 
-@pytest.mark.parametrize("kernel", ["coop", "split"])
+@pytest.mark.parametrize("kernel", ["coop", "split", "lean"])
 @pytest.mark.parametrize("case,B", [("L96_40", 37), ("L96_500p", 9), ("L96_5_irregular", 130),
                                     ("L96_67p", 70)])
 def test_batch_rows_equal_single_evaluations(case, B, kernel, monkeypatch):
@@ -63,7 +63,7 @@ def test_batch_flagged_rows_take_the_adaptive_stage():
         assert f1 == F[b] and np.array_equal(g1, G[b]), b
 
 
-@pytest.mark.parametrize("kernel", ["coop", "split"])
+@pytest.mark.parametrize("kernel", ["coop", "split", "lean"])
 def test_batched_gradient_check_equals_scipy_check_grad(kernel, capsys, monkeypatch):
     from scipy.optimize import check_grad
     monkeypatch.setenv("MFVGP_BATCH_KERNEL", kernel)

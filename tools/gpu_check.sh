@@ -15,3 +15,8 @@ for f in ("gpurun_out/bench_n1_new.json", "gpurun_out/bench_again.json"):
           "c_abi", d["c_abi"], "large", lg.get("value"), lg.get("roofline"), lg.get("scg"),
           "batched", (d.get("batched") or {}).get("value"))
 PY
+if [ -n "$NCU_BATCH" ]; then
+  python tools/batch_target.py 1024 | tail -1
+  ncu --set full --clock-control none --import-source on -k regex:esde_l96_lean_batch -s 2 -c 1 -o gpurun_out/r2c_lean_batch -f python tools/batch_target.py 1024 > gpurun_out/ncu_lean.log 2>&1
+  tail -1 gpurun_out/ncu_lean.log
+fi
