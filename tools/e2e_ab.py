@@ -1,6 +1,8 @@
 """e2e A/B: FreeEnergy.E_cost(numpy x) calls per second, pinned and pageable x (run with env switches).
 Tried with it and NOT kept: the kernels reading a page-locked x straight over PCIe instead of the
-H2D copy in front of them -- 80.5 us per call against 48.0 (8-byte strided reads over PCIe)."""
+H2D copy in front of them -- 80.5 us per call against 48.0 (8-byte strided reads over PCIe); and a
+separate pull kernel (one 16-byte load per thread, all in flight at once) in place of the
+copy-engine transfer -- 48.4 us against 46.4 (median of 15 blocks, twice each, same box)."""
 import sys, time
 from pathlib import Path
 import numpy as np, torch
