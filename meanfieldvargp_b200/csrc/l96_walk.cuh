@@ -45,8 +45,13 @@ __constant__ __align__(16) double c_glw[kGL * kGlwStride];
 constexpr int kWalkMaxTN = 64;
 
 // tuning knobs (tools/build_variant.sh builds variants with -D overrides)
-#ifndef MFVGP_WALK_GB
-#define MFVGP_WALK_GB 2
+// Gauss-Legendre nodes per pair of barriers in part (B).  Measured at D=8192, L=4096
+// (tools/walk_ab.py): TE=128 -- 1: 3 237 us, 2: 3 141, 4: 3 178;  TE=64 -- 1: 3 155, 2: 3 066,
+// 4: 3 029.  -DMFVGP_WALK_GB=n forces one value for every TE.
+#ifdef MFVGP_WALK_GB
+constexpr int walk_gb(int) { return MFVGP_WALK_GB; }
+#else
+constexpr int walk_gb(int te) { return te <= 64 ? 4 : 2; }
 #endif
 #ifndef MFVGP_PANEL_UNROLL
 #define MFVGP_PANEL_UNROLL 1

@@ -700,11 +700,11 @@ static int launch_esde(mfvgp_handle *h, const double *mean, int64_t ldm, const d
 template <int TE, bool PERSIST>
 static int launch_walk_kernel_p(const WalkArgs &w, unsigned grid, cudaStream_t st) {
     static uint64_t configured = 0;                 // one bit per device (attribute is per device)
-    const size_t smem = sizeof(WalkSmem<TE, MFVGP_WALK_GB>);
+    const size_t smem = sizeof(WalkSmem<TE, walk_gb(TE)>);
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (!(configured >> (dev & 63) & 1)) {
-        CK(cudaFuncSetAttribute(esde_l96_walk_kernel<TE, MFVGP_WALK_GB, PERSIST>,
+        CK(cudaFuncSetAttribute(esde_l96_walk_kernel<TE, walk_gb(TE), PERSIST>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured |= 1ull << (dev & 63);
     }
@@ -712,7 +712,7 @@ static int launch_walk_kernel_p(const WalkArgs &w, unsigned grid, cudaStream_t s
         const unsigned resident = 148u * (unsigned)(MFVGP_WALK_THREADS_PER_SM / TE);
         if (grid > resident) grid = resident;
     }
-    esde_l96_walk_kernel<TE, MFVGP_WALK_GB, PERSIST><<<grid, TE, smem, st>>>(w);
+    esde_l96_walk_kernel<TE, walk_gb(TE), PERSIST><<<grid, TE, smem, st>>>(w);
     return MFVGP_OK;
 }
 
